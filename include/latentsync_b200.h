@@ -1,0 +1,170 @@
+/*
+ * latentsync_b200 C-ABI — hand-written sm_100a kernels for the LatentSync inference hot path
+ * (audio-conditioned UNet3DConditionModel denoising loop + AutoencoderKL decode).
+ *
+ * The reference (Saltfish-AB/LatentSync) has NO native ABI on this path: everything is nn.Module calls into
+ * ATen/cuDNN.  Each entry point below therefore replaces one *library call class* the reference
+ * reaches from the cited Python line; the Python host (latentsync_b200/unet.py, vae.py, pipeline.py) keeps the
+ * reference's module/pipeline signatures and calls these through ctypes.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (PyTorch); nothing here allocates or frees.
+ *  - Activations are channels-last fp16: a (b f) x H x W x C video tensor is a row-major [rows, C] matrix with
+ *    rows = (b f) * H * W ("tokens").  Weights are packed fp16 [N][K] (K contiguous).
+ *  - Every function takes the CUDA stream to launch on (as void*) and returns 0 on success; on failure a
+ *    message is available from ls_last_error().  No function synchronises the device.
+ *  - Not re-entrant per stream; one host thread per GPU (the reference's server is single-consumer,
+ *    scripts/api.py:24-27,95).
+ */
+#ifndef LATENTSYNC_B200_H
+#define LATENTSYNC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LS_ABI_VERSION 1
+
+/* returns the message of the last failing call on this thread ("" if none) */
+const char* ls_last_error(void);
+int ls_abi_version(void);
+/* number of kernels launched by this library since process start / last reset (bench.py "gpu_launches") */
+int64_t ls_launch_count(void);
+void ls_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM / implicit-GEMM convolution (tcgen05.mma + TMEM accumulators + TMA operand staging).
+ *
+ *   out[m, n] = epilogue( sum_seg sum_tap sum_c  A_seg[pixel(m) + tap, c] * W[n, k(seg, tap, c)] )
+ *
+ * Replaces: nn.Conv2d 3x3 / 1x1 under InflatedConv3d.forward (latentsync/models/resnet.py:10-18), nn.Linear
+ * in Attention / FeedForward / TemporalTransformer3DModel (attention.py:230-235, motion_module.py:102,124),
+ * Conv2d proj_in/proj_out (attention.py:55,80), conv_shortcut (resnet.py:180) — the shortcut and the
+ * skip-concat (unet_blocks.py:624,745) are expressed as extra K segments of the same GEMM.
+ * ------------------------------------------------------------------------------------------------------- */
+#define LS_GEMM_MAX_SEG 3
+#define LS_EPI_GEGLU 1   /* W rows are packed [value | gate] per N tile; out[m, j] = v * gelu_erf(g) (diffusers GEGLU) */
+#define LS_EPI_OUT_F32 2 /* store fp32 instead of fp16 */
+#define LS_EPI_SILU 4    /* out = silu(out) */
+
+typedef struct LsGemmArgs {
+  /* A operand: up to 3 K-segments, each an fp16 channels-last tensor [nimg, H, W, ld] using the first `ch`
+   * channels (ch % 64 == 0), with taps = 1 (pointwise) or 9 (3x3, stride 1, zero pad 1). */
+  int32_t nseg;
+  const void* a_ptr[LS_GEMM_MAX_SEG];
+  int32_t a_ch[LS_GEMM_MAX_SEG];
+  int32_t a_ld[LS_GEMM_MAX_SEG];
+  int32_t a_taps[LS_GEMM_MAX_SEG];
+  /* geometry shared by all segments.  A plain [M, K] matrix is nimg = 1, H = 1, W = M.  A batched GEMM over
+   * `nimg` problems of M_b rows is nimg = batch, H = 1, W = M_b. */
+  int32_t nimg, H, W;
+  /* B operand: fp16 [N][Ktot], Ktot = sum_seg taps*ch, K index = ((seg, tap, c)); b_batch_stride != 0 selects a
+   * different [N][Ktot] matrix per image (batched GEMM), in elements. */
+  const void* b_ptr;
+  int32_t N;
+  int32_t Ktot;
+  int64_t b_batch_stride;
+  /* epilogue */
+  const float* bias; /* fp32 [bias_rows][N] or NULL */
+  int32_t bias_div;  /* rows of `out` per bias row (e.g. F*H*W for a per-batch-element time embedding); 0 = one row */
+  const void* residual; /* fp16 [M][ldr] or NULL, added after bias */
+  int32_t ldr;
+  void* out; /* fp16 (or fp32 with LS_EPI_OUT_F32) [M][ldo]; with LS_EPI_GEGLU N_out = N/2 */
+  int32_t ldo;
+  int32_t flags;
+  int32_t tile_n; /* 0 = auto; else one of 32, 64, 128, 160, 256 */
+} LsGemmArgs;
+
+int ls_gemm(const LsGemmArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Normalisation (fp16 in/out, fp32 statistics).
+ * ------------------------------------------------------------------------------------------------------- */
+/* GroupNorm statistics over `rows_per_inst` consecutive rows x (C/groups) channels of the virtual concatenation
+ * [x1 | x2] (x2 may be NULL).  stats: fp32 [ninst][groups][2] = (sum, sum of squares); MUST be zeroed by the
+ * caller (ls_fill_zero) before the call.
+ * Replaces the reduction half of nn.GroupNorm: resnet.py:140,164 (5-D input: rows_per_inst = F*H*W),
+ * attention.py:51, motion_module.py:101 (per frame: rows_per_inst = H*W), unet.py:236. */
+int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows, int32_t rows_per_inst,
+                       int32_t groups, float* stats, void* stream);
+/* y = (x - mean) * rstd * gamma + beta (+ SiLU), y is [rows][c1+c2] fp16.  resnet.py:185-187,207-215. */
+int ls_groupnorm_apply(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows, int32_t rows_per_inst,
+                       int32_t groups, const float* stats, const float* gamma, const float* beta, float eps,
+                       int32_t silu, void* y, void* stream);
+/* LayerNorm over C (nn.LayerNorm defaults, attention.py:145,157,172; motion_module.py:195,201), optionally adding
+ * the temporal sinusoidal table pe[frame][C] (motion_module.py:232-234) with frame = (row / rows_per_frame) % nframes.
+ * pe may be NULL. */
+int ls_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps,
+                 const float* pe, int32_t rows_per_frame, int32_t nframes, void* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Attention (flash-style, fp16 operands, fp32 softmax/accumulate).  softmax scale must be folded into Q.
+ * Row addressing:  row(batch b, position i) = (b / inner) * outer_stride + (b % inner) * inner_stride + i * seq_stride
+ *   spatial self / audio cross attention (attention.py:250-280): inner = 1, outer_stride = S, seq_stride = 1
+ *   temporal attention over frames (motion_module.py:262-313):   inner = H*W, outer_stride = F*H*W, inner_stride = 1,
+ *                                                               seq_stride = H*W   (no "(b f) s c -> (b s) f c" copy)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct LsAttnArgs {
+  const void* q; /* fp16, row stride ldq, head h at column h*head_dim */
+  const void* k;
+  const void* v;
+  void* out;
+  int32_t ldq, ldk, ldv, ldo;
+  int32_t batch, heads, head_dim; /* head_dim in {40, 80, 160} */
+  int32_t sq, skv;
+  int32_t q_inner;
+  int64_t q_outer_stride, q_inner_stride, q_seq_stride;
+  int32_t kv_inner;
+  int64_t kv_outer_stride, kv_inner_stride, kv_seq_stride;
+} LsAttnArgs;
+int ls_attention(const LsAttnArgs* args, void* stream);
+
+/* row softmax for the VAE mid-block attention (diffusers AutoencoderKL: 1 head, d = 512): p = softmax(s) over
+ * `cols`, fp16 in/out.  scale is folded into q upstream. */
+int ls_softmax_rows(const void* s, int64_t rows, int32_t cols, void* p, void* stream);
+/* batched fp16 transpose [batch][R][C] -> [batch][C][R] */
+int ls_transpose(const void* x, int32_t batch, int32_t R, int32_t C, void* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Memory-bound steps of the denoising loop (lipsync_pipeline.py:540-575) and layout helpers.
+ * ------------------------------------------------------------------------------------------------------- */
+/* cat([latents]*2) + cat([x, mask, masked, ref], dim=1) (lipsync_pipeline.py:542-549) -> channels-last fp16
+ * [nb*F*H*W][64] (13 real channels, zero padded to 64 so that conv_in's K is a whole TMA box).
+ * latents fp32 [1][4][F][H][W]; mask fp32 [1][1][F][H][W]; masked, ref fp32 [1][4][F][H][W]; nb = 2 with CFG. */
+int ls_concat13(const float* latents, const float* mask, const float* masked, const float* ref, int32_t nb, int32_t F,
+                int32_t HW, void* out, void* stream);
+/* CFG combine + DDIM step (eta = 0), lipsync_pipeline.py:557-562 + diffusers DDIMScheduler.step:
+ *   eps = eu + g*(ec - eu);  x0 = (x - sqrt(1-a_t)*eps)/sqrt(a_t);  x_prev = sqrt(a_prev)*x0 + sqrt(1-a_prev)*eps
+ * eps_cl: fp32 channels-last [nb*F*HW][ld_eps] (conv_out output; uncond rows first); latents fp32 NCFHW, updated
+ * in place; eps_out (optional, fp32 NCFHW [1][4][F][H][W]) receives the guided noise for the parity trace. */
+int ls_cfg_ddim_step(const float* eps_cl, int32_t ld_eps, int32_t nb, int32_t F, int32_t HW, float guidance,
+                     float alpha_t, float alpha_prev, float* latents, float* eps_out, void* stream);
+/* fp32 [B][C][F][HW] -> fp16 channels-last [(b f) HW][cpad] (zero padded, scaled); F = 1 is plain NCHW.
+ * Used for UNet3DConditionModel.forward's `sample` (unet.py:312) and decode_latents (lipsync_pipeline.py:145-147). */
+int ls_ncfhw_to_cl(const float* x, int32_t B, int32_t C, int32_t F, int32_t HW, int32_t cpad, float scale, void* out,
+                   void* stream);
+/* fp32 channels-last [(b f) HW][ld] -> fp32 [B][C][F][HW] */
+int ls_cl_to_ncfhw(const float* x, int32_t ld, int32_t B, int32_t C, int32_t F, int32_t HW, float* out, void* stream);
+/* nearest x2 upsample on (H, W), channels-last fp16 (resnet.py:65; diffusers Upsample2D). */
+int ls_upsample2x(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t C, void* y, void* stream);
+/* explicit im2col for the 3x3 stride-2 pad-1 Downsample3D conv (resnet.py:89): out [nimg*(H/2)*(W/2)][9*C]. */
+int ls_im2col_s2(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t C, void* y, void* stream);
+/* paste_surrounding_pixels_back (lipsync_pipeline.py:328-333, called with 1-masks at :572-574):
+ *   out = decoded*(1-m) + ref*m.  decoded_cl: fp32 channels-last [n*HW][ld] (VAE conv_out, 3 real channels);
+ *   ref fp32 [n][3][HW]; mask fp32 [n][1][HW]; out fp32 [n][3][HW]. */
+int ls_paste_back(const float* decoded_cl, int32_t ld, const float* ref, const float* mask, int32_t n, int32_t HW,
+                  float* out, void* stream);
+/* timestep path (unet.py:361-382, resnet.py:190-205): small dense layers on (B, 1280) vectors.
+ *   y[b][n] = act_out( sum_k act_in(x[b][k]) * W[n][k] + bias[n] ) (+ add[n]);  x, y, bias, add fp32; W fp16. */
+int ls_small_linear(const float* x, int32_t B, int32_t K, const void* W, const float* bias, const float* add,
+                    int32_t N, int32_t silu_in, int32_t silu_out, float* y, void* stream);
+/* sinusoidal timestep embedding (diffusers get_timestep_embedding, flip_sin_to_cos=True, shift=0): out fp32 [B][dim] */
+int ls_timestep_embedding(const float* t, int32_t B, int32_t dim, float* out, void* stream);
+int ls_fill_zero(void* p, int64_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATENTSYNC_B200_H */

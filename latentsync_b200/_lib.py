@@ -1,0 +1,317 @@
+"""ctypes binding of the C-ABI in include/latentsync_b200.h (built in-tree as latentsync_b200/_C.so).
+
+There is deliberately no CPU or PyTorch fallback: every op raises if the CUDA extension is missing or a call
+fails.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_C.so")
+_CSRC = os.path.join(_HERE, "csrc")
+
+EPI_GEGLU = 1
+EPI_OUT_F32 = 2
+EPI_SILU = 4
+MAX_SEG = 3
+
+
+class LsGemmArgs(C.Structure):
+    _fields_ = [
+        ("nseg", C.c_int32),
+        ("a_ptr", C.c_void_p * MAX_SEG),
+        ("a_ch", C.c_int32 * MAX_SEG),
+        ("a_ld", C.c_int32 * MAX_SEG),
+        ("a_taps", C.c_int32 * MAX_SEG),
+        ("nimg", C.c_int32),
+        ("H", C.c_int32),
+        ("W", C.c_int32),
+        ("b_ptr", C.c_void_p),
+        ("N", C.c_int32),
+        ("Ktot", C.c_int32),
+        ("b_batch_stride", C.c_int64),
+        ("bias", C.c_void_p),
+        ("bias_div", C.c_int32),
+        ("residual", C.c_void_p),
+        ("ldr", C.c_int32),
+        ("out", C.c_void_p),
+        ("ldo", C.c_int32),
+        ("flags", C.c_int32),
+        ("tile_n", C.c_int32),
+    ]
+
+
+class LsAttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p),
+        ("k", C.c_void_p),
+        ("v", C.c_void_p),
+        ("out", C.c_void_p),
+        ("ldq", C.c_int32),
+        ("ldk", C.c_int32),
+        ("ldv", C.c_int32),
+        ("ldo", C.c_int32),
+        ("batch", C.c_int32),
+        ("heads", C.c_int32),
+        ("head_dim", C.c_int32),
+        ("sq", C.c_int32),
+        ("skv", C.c_int32),
+        ("q_inner", C.c_int32),
+        ("q_outer_stride", C.c_int64),
+        ("q_inner_stride", C.c_int64),
+        ("q_seq_stride", C.c_int64),
+        ("kv_inner", C.c_int32),
+        ("kv_outer_stride", C.c_int64),
+        ("kv_inner_stride", C.c_int64),
+        ("kv_seq_stride", C.c_int64),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/latentsync_b200.h declares (tests check this)
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SYMBOLS = {
+    "ls_last_error": (C.c_char_p, []),
+    "ls_abi_version": (C.c_int, []),
+    "ls_launch_count": (C.c_int64, []),
+    "ls_reset_launch_count": (None, []),
+    "ls_gemm": (C.c_int, [C.POINTER(LsGemmArgs), _vp]),
+    "ls_groupnorm_stats": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    "ls_groupnorm_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _i32, _vp, _vp]),
+    "ls_layernorm": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp]),
+    "ls_attention": (C.c_int, [C.POINTER(LsAttnArgs), _vp]),
+    "ls_softmax_rows": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "ls_transpose": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "ls_concat13": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "ls_cfg_ddim_step": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    "ls_ncfhw_to_cl": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
+    "ls_cl_to_ncfhw": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ls_upsample2x": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ls_im2col_s2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ls_paste_back": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "ls_small_linear": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "ls_timestep_embedding": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "ls_fill_zero": (C.c_int, [_vp, _i64, _vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into latentsync_b200/_C.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", _CSRC, "-j8"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building latentsync_b200/_C.so failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout)
+    return _SO
+
+
+def lib() -> C.CDLL:
+    """Load the extension; raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise RuntimeError(
+                f"latentsync_b200: CUDA extension {_SO} is missing - run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (there is no CPU fallback)"
+            )
+        _lib = C.CDLL(_SO)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().ls_last_error().decode()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda, "latentsync_b200 ops need CUDA tensors (no CPU fallback)"
+    return t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(lib().ls_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().ls_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------ op wrappers
+class Seg:
+    """One K segment of the GEMM A operand: channels-last fp16 tensor, `ch` channels used, 1 or 9 taps."""
+
+    __slots__ = ("t", "ch", "ld", "taps")
+
+    def __init__(self, t: torch.Tensor, ch: int, ld: int, taps: int = 1):
+        self.t, self.ch, self.ld, self.taps = t, ch, ld, taps
+
+
+def gemm(
+    segs: Sequence[Seg],
+    nimg: int,
+    H: int,
+    W: int,
+    weight: torch.Tensor,
+    N: int,
+    out: torch.Tensor,
+    ldo: int,
+    bias: Optional[torch.Tensor] = None,
+    bias_div: int = 0,
+    residual: Optional[torch.Tensor] = None,
+    ldr: int = 0,
+    flags: int = 0,
+    tile_n: int = 0,
+    b_batch_stride: int = 0,
+) -> None:
+    a = LsGemmArgs()
+    a.nseg = len(segs)
+    ktot = 0
+    for i, s in enumerate(segs):
+        assert s.t.dtype == torch.float16
+        a.a_ptr[i] = _ptr(s.t)
+        a.a_ch[i] = s.ch
+        a.a_ld[i] = s.ld
+        a.a_taps[i] = s.taps
+        ktot += s.ch * s.taps
+    a.nimg, a.H, a.W = nimg, H, W
+    assert weight.dtype == torch.float16
+    a.b_ptr = _ptr(weight)
+    a.N, a.Ktot = N, ktot
+    a.b_batch_stride = b_batch_stride
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    a.bias = _ptr(bias)
+    a.bias_div = bias_div
+    a.residual = _ptr(residual)
+    a.ldr = ldr
+    a.out = _ptr(out)
+    a.ldo = ldo
+    a.flags = flags
+    a.tile_n = tile_n
+    _check(lib().ls_gemm(C.byref(a), _stream()), "ls_gemm")
+
+
+def groupnorm(
+    x1: torch.Tensor,
+    c1: int,
+    x2: Optional[torch.Tensor],
+    c2: int,
+    rows: int,
+    rows_per_inst: int,
+    groups: int,
+    gamma: torch.Tensor,
+    beta: torch.Tensor,
+    eps: float,
+    silu: bool,
+    out: torch.Tensor,
+    stats: torch.Tensor,
+) -> None:
+    L = lib()
+    ninst = rows // rows_per_inst
+    assert stats.dtype == torch.float32 and stats.numel() >= ninst * groups * 2
+    st = _stream()
+    _check(L.ls_fill_zero(_ptr(stats), ninst * groups * 2 * 4, st), "ls_fill_zero")
+    _check(L.ls_groupnorm_stats(_ptr(x1), c1, _ptr(x2), c2, rows, rows_per_inst, groups, _ptr(stats), st),
+           "ls_groupnorm_stats")
+    _check(
+        L.ls_groupnorm_apply(_ptr(x1), c1, _ptr(x2), c2, rows, rows_per_inst, groups, _ptr(stats), _ptr(gamma),
+                             _ptr(beta), eps, int(silu), _ptr(out), st),
+        "ls_groupnorm_apply",
+    )
+
+
+def layernorm(x, rows, Cc, gamma, beta, eps, out, pe=None, rows_per_frame=1, nframes=1) -> None:
+    _check(
+        lib().ls_layernorm(_ptr(x), rows, Cc, _ptr(gamma), _ptr(beta), eps, _ptr(pe), rows_per_frame, nframes,
+                           _ptr(out), _stream()),
+        "ls_layernorm",
+    )
+
+
+def attention(q, k, v, out, ldq, ldk, ldv, ldo, batch, heads, head_dim, sq, skv, q_addr=None, kv_addr=None) -> None:
+    """q_addr / kv_addr = (inner, outer_stride, inner_stride, seq_stride); default = contiguous sequences."""
+    a = LsAttnArgs()
+    a.q, a.k, a.v, a.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
+    a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
+    a.batch, a.heads, a.head_dim, a.sq, a.skv = batch, heads, head_dim, sq, skv
+    qi = q_addr or (1, sq, 0, 1)
+    ki = kv_addr or (1, skv, 0, 1)
+    a.q_inner, a.q_outer_stride, a.q_inner_stride, a.q_seq_stride = qi
+    a.kv_inner, a.kv_outer_stride, a.kv_inner_stride, a.kv_seq_stride = ki
+    _check(lib().ls_attention(C.byref(a), _stream()), "ls_attention")
+
+
+def softmax_rows(s, rows, cols, p) -> None:
+    _check(lib().ls_softmax_rows(_ptr(s), rows, cols, _ptr(p), _stream()), "ls_softmax_rows")
+
+
+def transpose(x, batch, R, Cc, y) -> None:
+    _check(lib().ls_transpose(_ptr(x), batch, R, Cc, _ptr(y), _stream()), "ls_transpose")
+
+
+def concat13(latents, mask, masked, ref, nb, F, HW, out) -> None:
+    for t in (latents, mask, masked, ref):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _check(lib().ls_concat13(_ptr(latents), _ptr(mask), _ptr(masked), _ptr(ref), nb, F, HW, _ptr(out), _stream()),
+           "ls_concat13")
+
+
+def cfg_ddim_step(eps_cl, ld_eps, nb, F, HW, guidance, alpha_t, alpha_prev, latents, eps_out=None) -> None:
+    _check(
+        lib().ls_cfg_ddim_step(_ptr(eps_cl), ld_eps, nb, F, HW, guidance, alpha_t, alpha_prev, _ptr(latents),
+                               _ptr(eps_out), _stream()),
+        "ls_cfg_ddim_step",
+    )
+
+
+def ncfhw_to_cl(x, B, Cc, F, HW, cpad, scale, out) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    _check(lib().ls_ncfhw_to_cl(_ptr(x), B, Cc, F, HW, cpad, scale, _ptr(out), _stream()), "ls_ncfhw_to_cl")
+
+
+def cl_to_ncfhw(x, ld, B, Cc, F, HW, out) -> None:
+    assert x.dtype == torch.float32 and out.dtype == torch.float32
+    _check(lib().ls_cl_to_ncfhw(_ptr(x), ld, B, Cc, F, HW, _ptr(out), _stream()), "ls_cl_to_ncfhw")
+
+
+def upsample2x(x, nimg, H, W, Cc, y) -> None:
+    _check(lib().ls_upsample2x(_ptr(x), nimg, H, W, Cc, _ptr(y), _stream()), "ls_upsample2x")
+
+
+def im2col_s2(x, nimg, H, W, Cc, y) -> None:
+    _check(lib().ls_im2col_s2(_ptr(x), nimg, H, W, Cc, _ptr(y), _stream()), "ls_im2col_s2")
+
+
+def paste_back(decoded_cl, ld, ref, mask, n, HW, out) -> None:
+    _check(lib().ls_paste_back(_ptr(decoded_cl), ld, _ptr(ref), _ptr(mask), n, HW, _ptr(out), _stream()),
+           "ls_paste_back")
+
+
+def small_linear(x, B, K, W, bias, add, N, silu_in, silu_out, y) -> None:
+    _check(
+        lib().ls_small_linear(_ptr(x), B, K, _ptr(W), _ptr(bias), _ptr(add), N, int(silu_in), int(silu_out), _ptr(y),
+                              _stream()),
+        "ls_small_linear",
+    )
+
+
+def timestep_embedding(t, B, dim, out) -> None:
+    _check(lib().ls_timestep_embedding(_ptr(t), B, dim, _ptr(out), _stream()), "ls_timestep_embedding")

@@ -1,0 +1,326 @@
+// Memory-bound steps of the denoising loop and layout helpers: 13-channel concat + CFG duplicate, CFG combine +
+// DDIM update, NC(F)HW <-> channels-last conversion, nearest x2 upsample, stride-2 im2col, paste-back, the tiny
+// timestep-embedding layers.  Single pass, vectorised where the layout allows.
+//
+// Reference: latentsync/pipelines/lipsync_pipeline.py:542-549 (concat), :557-559 (CFG), :562 + diffusers
+// DDIMScheduler.step (update), :328-333,:572-574 (paste-back), latentsync/models/resnet.py:65 (nearest upsample),
+// :89 (stride-2 conv), unet.py:361-382 + resnet.py:190-205 (time embedding path).
+#include "common.cuh"
+#include "../../include/latentsync_b200.h"
+
+#include <atomic>
+#include <stdarg.h>
+
+namespace ls {
+
+std::atomic<int64_t> g_launch_count{0};
+static thread_local char g_err[512] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+__global__ void concat13_kernel(const float* __restrict__ lat, const float* __restrict__ mask,
+                                const float* __restrict__ masked, const float* __restrict__ ref, int nb, int F, int HW,
+                                __half* __restrict__ out) {
+  const int64_t rows = (int64_t)nb * F * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * 8) return;
+  const int64_t row = idx >> 3;
+  const int vec = (int)(idx & 7);
+  const int64_t fr = row % ((int64_t)F * HW);  // (f, hw) inside one batch element; both CFG halves share inputs
+  const int f = (int)(fr / HW), hw = (int)(fr % HW);
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto at = [&](const float* p, int c) { return p[((int64_t)c * F + f) * HW + hw]; };
+  if (vec == 0) {
+    v[0] = at(lat, 0);
+    v[1] = at(lat, 1);
+    v[2] = at(lat, 2);
+    v[3] = at(lat, 3);
+    v[4] = at(mask, 0);
+    v[5] = at(masked, 0);
+    v[6] = at(masked, 1);
+    v[7] = at(masked, 2);
+  } else if (vec == 1) {
+    v[0] = at(masked, 3);
+    v[1] = at(ref, 0);
+    v[2] = at(ref, 1);
+    v[3] = at(ref, 2);
+    v[4] = at(ref, 3);
+  }
+  uint4 w;
+  __half2* o2 = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+  *reinterpret_cast<uint4*>(out + row * 64 + vec * 8) = w;
+}
+
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps_cl, int ld, int nb, int F, int HW, float g, float sa_t,
+                                float sb_t, float sa_p, float sb_p, float* __restrict__ lat,
+                                float* __restrict__ eps_out) {
+  const int64_t n = (int64_t)4 * F * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int c = (int)(idx / ((int64_t)F * HW));
+  const int64_t fr = idx % ((int64_t)F * HW);
+  const float eu = eps_cl[fr * ld + c];
+  float eps = eu;
+  if (nb == 2) {
+    const float ec = eps_cl[((int64_t)F * HW + fr) * ld + c];
+    eps = eu + g * (ec - eu);
+  }
+  const float x = lat[idx];
+  const float x0 = (x - sb_t * eps) / sa_t;
+  lat[idx] = sa_p * x0 + sb_p * eps;
+  if (eps_out != nullptr) eps_out[idx] = eps;
+}
+
+__global__ void ncfhw_to_cl_kernel(const float* __restrict__ x, int B, int C, int F, int HW, int cpad, float scale,
+                                   __half* __restrict__ out) {
+  const int64_t rows = (int64_t)B * F * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cpad) return;
+  const int64_t row = idx / cpad;
+  const int c = (int)(idx % cpad);
+  float v = 0.f;
+  if (c < C) {
+    const int hw = (int)(row % HW);
+    const int64_t bf = row / HW;
+    const int f = (int)(bf % F), b = (int)(bf / F);
+    v = x[(((int64_t)b * C + c) * F + f) * HW + hw] * scale;
+  }
+  out[idx] = __float2half_rn(v);
+}
+
+__global__ void cl_to_ncfhw_kernel(const float* __restrict__ x, int ld, int B, int C, int F, int HW,
+                                   float* __restrict__ out) {
+  const int64_t n = (int64_t)B * C * F * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int hw = (int)(idx % HW);
+  int64_t r = idx / HW;
+  const int f = (int)(r % F);
+  r /= F;
+  const int c = (int)(r % C);
+  const int b = (int)(r / C);
+  out[idx] = x[(((int64_t)b * F + f) * HW + hw) * ld + c];
+}
+
+__global__ void upsample2x_kernel(const __half* __restrict__ x, int nimg, int H, int W, int C, __half* __restrict__ y) {
+  const int nvec = C >> 3;
+  const int64_t total = (int64_t)nimg * (2 * H) * (2 * W) * nvec;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % nvec);
+    int64_t r = idx / nvec;
+    const int wo = (int)(r % (2 * W));
+    r /= (2 * W);
+    const int ho = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (((int64_t)n * H + (ho >> 1)) * W + (wo >> 1)) * C + v * 8);
+    *reinterpret_cast<uint4*>(y + (((int64_t)n * 2 * H + ho) * 2 * W + wo) * C + v * 8) = u;
+  }
+}
+
+__global__ void im2col_s2_kernel(const __half* __restrict__ x, int nimg, int H, int W, int C, __half* __restrict__ y) {
+  const int nvec = C >> 3;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = (int64_t)nimg * Ho * Wo * 9 * nvec;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % nvec);
+    int64_t r = idx / nvec;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const int hi = 2 * ho - 1 + tap / 3, wi = 2 * wo - 1 + tap % 3;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+      u = *reinterpret_cast<const uint4*>(x + (((int64_t)n * H + hi) * W + wi) * C + v * 8);
+    *reinterpret_cast<uint4*>(y + ((((int64_t)n * Ho + ho) * Wo + wo) * 9 + tap) * C + v * 8) = u;
+  }
+}
+
+__global__ void paste_back_kernel(const float* __restrict__ dec, int ld, const float* __restrict__ ref,
+                                  const float* __restrict__ mask, int n, int HW, float* __restrict__ out) {
+  const int64_t total = (int64_t)n * 3 * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int hw = (int)(idx % HW);
+  const int64_t r = idx / HW;
+  const int c = (int)(r % 3);
+  const int64_t img = r / 3;
+  const float m = mask[img * HW + hw];
+  const float d = dec[(img * HW + hw) * ld + c];
+  out[idx] = d * (1.f - m) + ref[idx] * m;
+}
+
+// y[b][n] = act_out(sum_k act_in(x[b][k]) * W[n][k] + bias[n]) + add[n];  one warp per output column
+__global__ void small_linear_kernel(const float* __restrict__ x, int B, int K, const __half* __restrict__ W,
+                                    const float* __restrict__ bias, const float* __restrict__ add, int N, int silu_in,
+                                    int silu_out, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  for (int b0 = 0; b0 < B; b0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 u = *reinterpret_cast<const uint4*>(W + (int64_t)n * K + k);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+      float w[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        w[2 * e] = f.x;
+        w[2 * e + 1] = f.y;
+      }
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        if (b0 + bb < B) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float xv = x[(int64_t)(b0 + bb) * K + k + e];
+            if (silu_in) xv = silu_f(xv);
+            acc[bb] += xv * w[e];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[bb] += __shfl_xor_sync(0xffffffffu, acc[bb], o);
+      if (lane == 0 && b0 + bb < B) {
+        float r = acc[bb] + (bias ? bias[n] : 0.f);
+        if (silu_out) r = silu_f(r);
+        if (add) r += add[n];
+        y[(int64_t)(b0 + bb) * N + n] = r;
+      }
+    }
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * dim) return;
+  const int b = idx / dim, i = idx % dim;
+  const int half = dim / 2;
+  const int k = (i < half) ? i : i - half;
+  const float freq = expf(-logf(10000.0f) * (float)k / (float)half);
+  const float a = t[b] * freq;
+  out[idx] = (i < half) ? cosf(a) : sinf(a);  // flip_sin_to_cos=True: [cos | sin]
+}
+
+}  // namespace ls
+
+using namespace ls;
+
+static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+#define LS_LAUNCHED()                                       \
+  do {                                                      \
+    LS_CUDA(cudaGetLastError());                            \
+    g_launch_count.fetch_add(1, std::memory_order_relaxed); \
+  } while (0)
+
+extern "C" const char* ls_last_error(void) { return ls::g_err; }
+extern "C" int ls_abi_version(void) { return LS_ABI_VERSION; }
+extern "C" int64_t ls_launch_count(void) { return g_launch_count.load(); }
+extern "C" void ls_reset_launch_count(void) { g_launch_count.store(0); }
+
+extern "C" int ls_concat13(const float* latents, const float* mask, const float* masked, const float* ref, int32_t nb,
+                           int32_t F, int32_t HW, void* out, void* stream) {
+  LS_CHECK(latents && mask && masked && ref && out && nb >= 1 && nb <= 2 && F > 0 && HW > 0, "ls_concat13: bad args");
+  const int64_t n = (int64_t)nb * F * HW * 8;
+  concat13_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(latents, mask, masked, ref, nb, F, HW,
+                                                                         (__half*)out);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_cfg_ddim_step(const float* eps_cl, int32_t ld_eps, int32_t nb, int32_t F, int32_t HW, float guidance,
+                                float alpha_t, float alpha_prev, float* latents, float* eps_out, void* stream) {
+  LS_CHECK(eps_cl && latents && nb >= 1 && nb <= 2 && ld_eps >= 4, "ls_cfg_ddim_step: bad args");
+  LS_CHECK(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f, "ls_cfg_ddim_step: bad alphas");
+  const int64_t n = (int64_t)4 * F * HW;
+  cfg_ddim_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      eps_cl, ld_eps, nb, F, HW, guidance, sqrtf(alpha_t), sqrtf(1.f - alpha_t), sqrtf(alpha_prev),
+      sqrtf(1.f - alpha_prev), latents, eps_out);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_ncfhw_to_cl(const float* x, int32_t B, int32_t C, int32_t F, int32_t HW, int32_t cpad, float scale,
+                              void* out, void* stream) {
+  LS_CHECK(x && out && B > 0 && C > 0 && F > 0 && HW > 0 && cpad >= C, "ls_ncfhw_to_cl: bad args");
+  const int64_t n = (int64_t)B * F * HW * cpad;
+  ncfhw_to_cl_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, B, C, F, HW, cpad, scale, (__half*)out);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_cl_to_ncfhw(const float* x, int32_t ld, int32_t B, int32_t C, int32_t F, int32_t HW, float* out,
+                              void* stream) {
+  LS_CHECK(x && out && B > 0 && C > 0 && F > 0 && HW > 0 && ld >= C, "ls_cl_to_ncfhw: bad args");
+  const int64_t n = (int64_t)B * C * F * HW;
+  cl_to_ncfhw_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, ld, B, C, F, HW, out);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_upsample2x(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t C, void* y, void* stream) {
+  LS_CHECK(x && y && C % 8 == 0, "ls_upsample2x: bad args");
+  const int64_t n = (int64_t)nimg * 4 * H * W * (C / 8);
+  unsigned blocks = blocks_for(n, 256);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  upsample2x_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, nimg, H, W, C, (__half*)y);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_im2col_s2(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t C, void* y, void* stream) {
+  LS_CHECK(x && y && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "ls_im2col_s2: bad args");
+  const int64_t n = (int64_t)nimg * (H / 2) * (W / 2) * 9 * (C / 8);
+  unsigned blocks = blocks_for(n, 256);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  im2col_s2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, nimg, H, W, C, (__half*)y);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_paste_back(const float* decoded_cl, int32_t ld, const float* ref, const float* mask, int32_t n,
+                             int32_t HW, float* out, void* stream) {
+  LS_CHECK(decoded_cl && ref && mask && out && ld >= 3, "ls_paste_back: bad args");
+  const int64_t total = (int64_t)n * 3 * HW;
+  paste_back_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(decoded_cl, ld, ref, mask, n, HW, out);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_small_linear(const float* x, int32_t B, int32_t K, const void* W, const float* bias, const float* add,
+                               int32_t N, int32_t silu_in, int32_t silu_out, float* y, void* stream) {
+  LS_CHECK(x && W && y && B > 0 && K % 8 == 0 && N > 0, "ls_small_linear: bad args");
+  const int wpb = 8;
+  small_linear_kernel<<<(N + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(x, B, K, (const __half*)W, bias, add,
+                                                                                   N, silu_in, silu_out, y);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_timestep_embedding(const float* t, int32_t B, int32_t dim, float* out, void* stream) {
+  LS_CHECK(t && out && B > 0 && dim % 2 == 0, "ls_timestep_embedding: bad args");
+  timestep_embedding_kernel<<<blocks_for((int64_t)B * dim, 128), 128, 0, (cudaStream_t)stream>>>(t, B, dim, out);
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_fill_zero(void* p, int64_t bytes, void* stream) {
+  LS_CHECK(p && bytes >= 0, "ls_fill_zero: bad args");
+  LS_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
+  return 0;
+}
