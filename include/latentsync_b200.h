@@ -100,7 +100,7 @@ int ls_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, con
                  const float* pe, int32_t rows_per_frame, int32_t nframes, void* y, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Attention (flash-style, fp16 operands, fp32 softmax/accumulate).  softmax scale must be folded into Q.
+ * Attention (flash-style, fp16 operands, fp32 softmax/accumulate): out = softmax(scale * Q K^T) V.
  * Row addressing:  row(batch b, position i) = (b / inner) * outer_stride + (b % inner) * inner_stride + i * seq_stride
  *   spatial self / audio cross attention (attention.py:250-280): inner = 1, outer_stride = S, seq_stride = 1
  *   temporal attention over frames (motion_module.py:262-313):   inner = H*W, outer_stride = F*H*W, inner_stride = 1,
@@ -118,6 +118,7 @@ typedef struct LsAttnArgs {
   int64_t q_outer_stride, q_inner_stride, q_seq_stride;
   int32_t kv_inner;
   int64_t kv_outer_stride, kv_inner_stride, kv_seq_stride;
+  float scale; /* softmax scale (head_dim^-0.5 in the reference, attention.py:271), applied to the fp32 scores */
 } LsAttnArgs;
 int ls_attention(const LsAttnArgs* args, void* stream);
 

@@ -70,6 +70,7 @@ class LsAttnArgs(C.Structure):
         ("kv_outer_stride", C.c_int64),
         ("kv_inner_stride", C.c_int64),
         ("kv_seq_stride", C.c_int64),
+        ("scale", C.c_float),
     ]
 
 
@@ -246,7 +247,8 @@ def layernorm(x, rows, Cc, gamma, beta, eps, out, pe=None, rows_per_frame=1, nfr
     )
 
 
-def attention(q, k, v, out, ldq, ldk, ldv, ldo, batch, heads, head_dim, sq, skv, q_addr=None, kv_addr=None) -> None:
+def attention(q, k, v, out, ldq, ldk, ldv, ldo, batch, heads, head_dim, sq, skv, q_addr=None, kv_addr=None,
+              scale=None) -> None:
     """q_addr / kv_addr = (inner, outer_stride, inner_stride, seq_stride); default = contiguous sequences."""
     a = LsAttnArgs()
     a.q, a.k, a.v, a.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
@@ -256,6 +258,7 @@ def attention(q, k, v, out, ldq, ldk, ldv, ldo, batch, heads, head_dim, sq, skv,
     ki = kv_addr or (1, skv, 0, 1)
     a.q_inner, a.q_outer_stride, a.q_inner_stride, a.q_seq_stride = qi
     a.kv_inner, a.kv_outer_stride, a.kv_inner_stride, a.kv_seq_stride = ki
+    a.scale = float(head_dim) ** -0.5 if scale is None else scale
     _check(lib().ls_attention(C.byref(a), _stream()), "ls_attention")
 
 
@@ -315,3 +318,18 @@ def small_linear(x, B, K, W, bias, add, N, silu_in, silu_out, y) -> None:
 
 def timestep_embedding(t, B, dim, out) -> None:
     _check(lib().ls_timestep_embedding(_ptr(t), B, dim, _ptr(out), _stream()), "ls_timestep_embedding")
+
+
+def pack_geglu(weight: torch.Tensor, bias: Optional[torch.Tensor], tile_n: int):
+    """Re-order the rows of diffusers' GEGLU projection ([value rows | gate rows], attention.py:171) so that every
+    `tile_n`-row tile of the GEMM's B operand holds tile_n/2 value rows followed by their tile_n/2 gate rows; the
+    LS_EPI_GEGLU epilogue then finds value and gate of one output column in the same TMEM accumulator."""
+    two_inner = weight.shape[0]
+    inner = two_inner // 2
+    half = tile_n // 2
+    assert inner % half == 0
+    idx = torch.arange(inner, device=weight.device).reshape(inner // half, half)
+    order = torch.cat([idx, idx + inner], dim=1).reshape(-1)
+    wp = weight[order].contiguous()
+    bp = bias[order].contiguous() if bias is not None else None
+    return wp, bp

@@ -26,6 +26,7 @@ struct AttnKParams {
   int64_t q_outer, q_in_stride, q_seq;
   int kv_inner;
   int64_t kv_outer, kv_in_stride, kv_seq;
+  float scale_log2;  // softmax scale * log2(e), applied to the fp32 scores
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  const float sl = p.scale_log2;
   const int64_t qbase = (int64_t)(b / p.q_inner) * p.q_outer + (int64_t)(b % p.q_inner) * p.q_in_stride;
   const int64_t kvbase = (int64_t)(b / p.kv_inner) * p.kv_outer + (int64_t)(b % p.kv_inner) * p.kv_in_stride;
 
@@ -171,16 +173,16 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
     const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
-    const float al_lo = exp2f((m_lo - mn_lo) * kLog2e), al_hi = exp2f((m_hi - mn_hi) * kLog2e);
+    const float al_lo = exp2f((m_lo - mn_lo) * sl), al_hi = exp2f((m_hi - mn_hi) * sl);
     m_lo = mn_lo;
     m_hi = mn_hi;
     float rs_lo = 0.f, rs_hi = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f((s[nt][0] - mn_lo) * kLog2e);
-      s[nt][1] = exp2f((s[nt][1] - mn_lo) * kLog2e);
-      s[nt][2] = exp2f((s[nt][2] - mn_hi) * kLog2e);
-      s[nt][3] = exp2f((s[nt][3] - mn_hi) * kLog2e);
+      s[nt][0] = exp2f((s[nt][0] - mn_lo) * sl);
+      s[nt][1] = exp2f((s[nt][1] - mn_lo) * sl);
+      s[nt][2] = exp2f((s[nt][2] - mn_hi) * sl);
+      s[nt][3] = exp2f((s[nt][3] - mn_hi) * sl);
       rs_lo += s[nt][0] + s[nt][1];
       rs_hi += s[nt][2] + s[nt][3];
     }
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(128) attn_short_kernel(const AttnKParams p) {
   extern __shared__ __align__(16) uint8_t attn_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const float sl = p.scale_log2;
   __half* sQ = reinterpret_cast<__half*>(attn_smem) + warp * 3 * 16 * DS;
   __half* sK = sQ + 16 * DS;
   __half* sV = sK + 16 * DS;
@@ -299,10 +302,10 @@ __global__ void __launch_bounds__(128) attn_short_kernel(const AttnKParams p) {
   float l_lo = 0.f, l_hi = 0.f;
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
-    s[nt][0] = exp2f((s[nt][0] - mx_lo) * kLog2e);
-    s[nt][1] = exp2f((s[nt][1] - mx_lo) * kLog2e);
-    s[nt][2] = exp2f((s[nt][2] - mx_hi) * kLog2e);
-    s[nt][3] = exp2f((s[nt][3] - mx_hi) * kLog2e);
+    s[nt][0] = exp2f((s[nt][0] - mx_lo) * sl);
+    s[nt][1] = exp2f((s[nt][1] - mx_lo) * sl);
+    s[nt][2] = exp2f((s[nt][2] - mx_hi) * sl);
+    s[nt][3] = exp2f((s[nt][3] - mx_hi) * sl);
     l_lo += s[nt][0] + s[nt][1];
     l_hi += s[nt][2] + s[nt][3];
   }
@@ -397,6 +400,8 @@ static int attention_impl(const LsAttnArgs* a, cudaStream_t stream) {
   p.kv_outer = a->kv_outer_stride;
   p.kv_in_stride = a->kv_inner_stride;
   p.kv_seq = a->kv_seq_stride;
+  LS_CHECK(a->scale > 0.f, "ls_attention: scale must be > 0");
+  p.scale_log2 = a->scale * kLog2e;
   switch (a->head_dim) {
     case 40: return launch_attn<40>(p, stream);
     case 80: return launch_attn<80>(p, stream);

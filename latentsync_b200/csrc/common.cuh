@@ -66,7 +66,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 22)) {
       printf("latentsync_b200: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }

@@ -1,0 +1,374 @@
+"""Per-kernel numerics: every C-ABI op against a plain PyTorch fp32 statement of the reference op it replaces.
+
+Tolerances: operands are fp16 (inputs are generated in fp16 so both sides see identical values); accumulation is
+fp32 on both sides, so the only difference is summation order and the final fp16 store: rel-L2 <= 2e-3.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def setup_module(module):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _ops():
+    from latentsync_b200 import _lib
+
+    return _lib
+
+
+def rel_l2(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def cl(x):
+    """(N, C, H, W) -> channels-last rows [(N H W), C]"""
+    n, c, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(n * h * w, c).contiguous()
+
+
+def uncl(rows, n, h, w):
+    return rows.reshape(n, h, w, -1).permute(0, 3, 1, 2).contiguous()
+
+
+def pack_conv_w(w):
+    """OIHW -> [N][(tap, c)] fp16"""
+    n, c, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(n, kh * kw * c).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------- GEMM (Linear)
+@pytest.mark.parametrize(
+    "M,K,N,tile_n",
+    [
+        (256, 64, 32, 0),
+        (128, 128, 128, 128),
+        (1000, 320, 320, 0),
+        (32768, 320, 960, 0),
+        (2048, 1280, 1280, 256),
+        (512, 1280, 1280, 160),
+        (4096, 640, 2560, 64),
+        (300, 384, 40, 0),
+    ],
+)
+def test_gemm_linear(M, K, N, tile_n):
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    a = torch.randn(M, K, generator=g).half().to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).half().to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).half().to(DEV)
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    L.gemm([L.Seg(a, K, K, 1)], 1, 1, M, w, N, out, N, bias=bias, residual=res, ldr=N, tile_n=tile_n)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    assert rel_l2(out, ref) < 2e-3
+    # fp32 output, no bias/residual
+    out32 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    L.gemm([L.Seg(a, K, K, 1)], 1, 1, M, w, N, out32, N, flags=L.EPI_OUT_F32, tile_n=tile_n)
+    ref = a.float() @ w.float().t()
+    assert rel_l2(out32, ref) < 1e-4
+
+
+def test_gemm_bias_div_and_silu():
+    """per-batch-element bias rows (time embedding add, resnet.py:205) and SiLU epilogue"""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(2)
+    M, K, N = 2 * 1024, 128, 192
+    a = torch.randn(M, K, generator=g).half().to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).half().to(DEV)
+    bias = torch.randn(2, N, generator=g).to(DEV)
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    L.gemm([L.Seg(a, K, K, 1)], 1, 1, M, w, N, out, N, bias=bias, bias_div=1024, flags=L.EPI_SILU)
+    ref = a.float() @ w.float().t() + bias.repeat_interleave(1024, 0)
+    ref = F.silu(ref)
+    assert rel_l2(out, ref) < 2e-3
+
+
+def test_gemm_geglu():
+    """diffusers GEGLU: [h | g] = Linear(C -> 8C)(x); y = h * gelu_erf(g)"""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    M, C = 1024, 320
+    inner = 4 * C
+    for tile_n in (64, 128, 256):
+        a = torch.randn(M, C, generator=g).half().to(DEV)
+        w = (torch.randn(2 * inner, C, generator=g) / math.sqrt(C)).half().to(DEV)
+        b = torch.randn(2 * inner, generator=g).to(DEV)
+        wp, bp = L.pack_geglu(w, b, tile_n)
+        out = torch.empty(M, inner, dtype=torch.float16, device=DEV)
+        L.gemm([L.Seg(a, C, C, 1)], 1, 1, M, wp, 2 * inner, out, inner, bias=bp, flags=L.EPI_GEGLU, tile_n=tile_n)
+        hg = a.float() @ w.float().t() + b
+        ref = hg[:, :inner] * F.gelu(hg[:, inner:])
+        assert rel_l2(out, ref) < 2e-3, tile_n
+
+
+def test_gemm_batched():
+    """batched GEMM (VAE mid attention QK^T and PV): out[b] = A[b] @ B[b]^T"""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(4)
+    nb, M, K, N = 4, 1024, 512, 1024
+    a = torch.randn(nb, M, K, generator=g).half().to(DEV)
+    b = (torch.randn(nb, N, K, generator=g) / math.sqrt(K)).half().to(DEV)
+    out = torch.empty(nb, M, N, dtype=torch.float16, device=DEV)
+    L.gemm([L.Seg(a, K, K, 1)], nb, 1, M, b, N, out, N, b_batch_stride=N * K)
+    ref = torch.bmm(a.float(), b.float().transpose(1, 2))
+    assert rel_l2(out, ref) < 2e-3
+
+
+# -------------------------------------------------------------------------------------------- implicit-GEMM conv
+@pytest.mark.parametrize(
+    "nimg,H,W,Cin,Cout",
+    [
+        (2, 32, 32, 64, 64),
+        (32, 32, 32, 320, 320),
+        (32, 16, 16, 640, 640),
+        (32, 8, 8, 1280, 1280),
+        (32, 4, 4, 1280, 1280),
+        (3, 4, 4, 128, 96),
+        (2, 64, 64, 128, 128),
+        (1, 256, 256, 128, 3),
+        (2, 128, 128, 64, 32),
+        (5, 8, 8, 64, 40),
+    ],
+)
+def test_conv3x3(nimg, H, W, Cin, Cout):
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(nimg, Cin, H, W, generator=g).half().to(DEV)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)).half().to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    xcl = cl(x)
+    out = torch.empty(nimg * H * W, Cout, dtype=torch.float32, device=DEV)
+    L.gemm([L.Seg(xcl, Cin, Cin, 9)], nimg, H, W, pack_conv_w(w), Cout, out, Cout, bias=b, flags=L.EPI_OUT_F32)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1)
+    assert rel_l2(uncl(out, nimg, H, W), ref) < 1e-4
+
+
+def test_conv3x3_concat_and_shortcut():
+    """skip-concat conv (unet_blocks.py:624) as two K segments + fused 1x1 shortcut (resnet.py:219-221) as a third"""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(6)
+    nimg, H, W, c1, c2, cs, Cout = 4, 16, 16, 128, 64, 192, 128
+    x1 = torch.randn(nimg, c1, H, W, generator=g).half().to(DEV)
+    x2 = torch.randn(nimg, c2, H, W, generator=g).half().to(DEV)
+    xs = torch.randn(nimg, cs, H, W, generator=g).half().to(DEV)
+    w = (torch.randn(Cout, c1 + c2, 3, 3, generator=g) / math.sqrt(9 * (c1 + c2))).half().to(DEV)
+    ws = (torch.randn(Cout, cs, 1, 1, generator=g) / math.sqrt(cs)).half().to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    wp = torch.cat([pack_conv_w(w[:, :c1]), pack_conv_w(w[:, c1:]), ws.reshape(Cout, cs)], dim=1).contiguous()
+    out = torch.empty(nimg * H * W, Cout, dtype=torch.float16, device=DEV)
+    L.gemm([L.Seg(cl(x1), c1, c1, 9), L.Seg(cl(x2), c2, c2, 9), L.Seg(cl(xs), cs, cs, 1)], nimg, H, W, wp, Cout, out,
+           Cout, bias=b)
+    ref = F.conv2d(torch.cat([x1, x2], 1).float(), w.float(), b, padding=1) + F.conv2d(xs.float(), ws.float())
+    assert rel_l2(uncl(out, nimg, H, W), ref) < 2e-3
+
+
+def test_conv_stride2_via_im2col():
+    """Downsample3D (resnet.py:89): 3x3 stride 2 pad 1"""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(7)
+    nimg, H, W, C, Cout = 4, 16, 16, 64, 64
+    x = torch.randn(nimg, C, H, W, generator=g).half().to(DEV)
+    w = (torch.randn(Cout, C, 3, 3, generator=g) / math.sqrt(9 * C)).half().to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    cols = torch.empty(nimg * (H // 2) * (W // 2), 9 * C, dtype=torch.float16, device=DEV)
+    L.im2col_s2(cl(x), nimg, H, W, C, cols)
+    out = torch.empty(nimg * (H // 2) * (W // 2), Cout, dtype=torch.float16, device=DEV)
+    M = cols.shape[0]
+    L.gemm([L.Seg(cols, 9 * C, 9 * C, 1)], 1, 1, M, pack_conv_w(w), Cout, out, Cout, bias=b)
+    ref = F.conv2d(x.float(), w.float(), b, stride=2, padding=1)
+    assert rel_l2(uncl(out, nimg, H // 2, W // 2), ref) < 2e-3
+
+
+def test_upsample2x():
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(8)
+    x = torch.randn(3, 64, 8, 4, generator=g).half().to(DEV)
+    y = torch.empty(3 * 16 * 8, 64, dtype=torch.float16, device=DEV)
+    L.upsample2x(cl(x), 3, 8, 4, 64, y)
+    ref = F.interpolate(x.float(), scale_factor=2.0, mode="nearest")
+    assert torch.equal(uncl(y, 3, 16, 8).float(), ref)
+
+
+# --------------------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("c1,c2,rows_per_inst,ninst", [(320, 0, 16 * 1024, 2), (1280, 640, 64, 32), (640, 320, 256, 4),
+                                                       (128, 0, 65536, 2), (512, 0, 1024, 3)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm(c1, c2, rows_per_inst, ninst, silu):
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(9)
+    C = c1 + c2
+    rows = rows_per_inst * ninst
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.5).half().to(DEV)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    x1 = x[:, :c1].contiguous()
+    x2 = x[:, c1:].contiguous() if c2 else None
+    out = torch.empty(rows, C, dtype=torch.float16, device=DEV)
+    stats = torch.empty(ninst * 32 * 2, dtype=torch.float32, device=DEV)
+    L.groupnorm(x1, c1, x2, c2, rows, rows_per_inst, 32, gamma, beta, 1e-5, silu, out, stats)
+    xr = x.float().reshape(ninst, rows_per_inst, C).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(rows, C)
+    assert rel_l2(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("C", [320, 640, 1280])
+def test_layernorm_and_pe(C):
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(10)
+    Fr, HW, B = 16, 20, 2
+    rows = B * Fr * HW
+    x = (torch.randn(rows, C, generator=g) * 3 + 1).half().to(DEV)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    out = torch.empty_like(x)
+    L.layernorm(x, rows, C, gamma, beta, 1e-5, out)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    assert rel_l2(out, ref) < 1e-3
+    pe = torch.randn(Fr, C, generator=g).to(DEV)
+    L.layernorm(x, rows, C, gamma, beta, 1e-5, out, pe=pe, rows_per_frame=HW, nframes=Fr)
+    ref2 = (ref.reshape(B, Fr, HW, C) + pe[None, :, None, :]).reshape(rows, C)
+    assert rel_l2(out, ref2) < 1e-3
+
+
+def test_softmax_and_transpose():
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(11)
+    s = (torch.randn(512, 1024, generator=g) * 4).half().to(DEV)
+    p = torch.empty_like(s)
+    L.softmax_rows(s, 512, 1024, p)
+    assert rel_l2(p, torch.softmax(s.float(), -1)) < 2e-3
+    x = torch.randn(3, 100, 72, generator=g).half().to(DEV)
+    y = torch.empty(3, 72, 100, dtype=torch.float16, device=DEV)
+    L.transpose(x, 3, 100, 72, y)
+    assert torch.equal(y, x.transpose(1, 2).contiguous())
+
+
+# ----------------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize(
+    "batch,heads,d,sq,skv",
+    [(4, 8, 40, 1024, 1024), (4, 8, 80, 256, 256), (4, 8, 160, 64, 64), (3, 8, 160, 16, 16), (4, 8, 40, 1024, 50),
+     (4, 8, 80, 256, 50), (2, 8, 160, 64, 50), (2, 8, 160, 16, 50), (2, 8, 40, 100, 77), (1, 8, 40, 4096, 4096)],
+)
+def test_attention(batch, heads, d, sq, skv):
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(12)
+    C = heads * d
+    q = torch.randn(batch * sq, C, generator=g).half().to(DEV)
+    k = torch.randn(batch * skv, C, generator=g).half().to(DEV)
+    v = torch.randn(batch * skv, C, generator=g).half().to(DEV)
+    out = torch.empty_like(q)
+    L.attention(q, k, v, out, C, C, C, C, batch, heads, d, sq, skv)
+    qh = (q.float() * d ** -0.5).reshape(batch, sq, heads, d).transpose(1, 2)
+    kh = k.float().reshape(batch, skv, heads, d).transpose(1, 2)
+    vh = v.float().reshape(batch, skv, heads, d).transpose(1, 2)
+    ref = torch.softmax(qh @ kh.transpose(-1, -2), -1) @ vh
+    ref = ref.transpose(1, 2).reshape(batch * sq, C)
+    assert rel_l2(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("d,HW", [(40, 64), (80, 16), (160, 4)])
+def test_attention_temporal(d, HW):
+    """VersatileAttention (motion_module.py:262-313): sequences run over the 16 frames at each pixel, addressed by
+    stride inside the (b f) x HW token matrix; q, k, v come packed as one [rows, 3C] matrix."""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(13)
+    B, Fr, heads = 2, 16, 8
+    C = heads * d
+    rows = B * Fr * HW
+    qkv = torch.randn(rows, 3 * C, generator=g).half().to(DEV)
+    out = torch.empty(rows, C, dtype=torch.float16, device=DEV)
+    addr = (HW, Fr * HW, 1, HW)
+    L.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, 3 * C, 3 * C, 3 * C, C, B * HW, heads, d, Fr, Fr,
+                q_addr=addr, kv_addr=addr)
+    x = qkv.float().reshape(B, Fr, HW, 3, heads, d).permute(3, 0, 2, 4, 1, 5)  # (3, B, HW, h, F, d)
+    ref = torch.softmax(x[0] @ x[1].transpose(-1, -2) * d ** -0.5, -1) @ x[2]  # (B, HW, h, F, d)
+    ref = ref.permute(0, 3, 1, 2, 4).reshape(rows, C)
+    assert rel_l2(out, ref) < 3e-3
+
+
+# ------------------------------------------------------------------------------------- denoising-loop pointwise
+def test_concat13_cfg_ddim_paste():
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(14)
+    Fr, H, W = 16, 32, 32
+    HW = H * W
+    lat = torch.randn(1, 4, Fr, H, W, generator=g).to(DEV)
+    mask = (torch.rand(1, 1, Fr, H, W, generator=g) > 0.5).float().to(DEV)
+    masked = torch.randn(1, 4, Fr, H, W, generator=g).to(DEV)
+    ref = torch.randn(1, 4, Fr, H, W, generator=g).to(DEV)
+    out = torch.empty(2 * Fr * HW, 64, dtype=torch.float16, device=DEV)
+    L.concat13(lat, mask, masked, ref, 2, Fr, HW, out)
+    x = torch.cat([lat, mask, masked, ref], dim=1)
+    x = torch.cat([x] * 2)  # (2, 13, F, H, W)
+    want = x.permute(0, 2, 3, 4, 1).reshape(2 * Fr * HW, 13)
+    assert torch.equal(out[:, :13], want.half())
+    assert torch.count_nonzero(out[:, 13:]) == 0
+
+    # CFG combine + DDIM update
+    eps_cl = torch.randn(2 * Fr * HW, 32, generator=g).to(DEV)
+    lat0 = lat.clone()
+    eps_out = torch.empty(1, 4, Fr, H, W, device=DEV)
+    gs, a_t, a_p = 1.5, 0.0081550, 0.0120
+    L.cfg_ddim_step(eps_cl, 32, 2, Fr, HW, gs, a_t, a_p, lat, eps_out)
+    e = eps_cl[:, :4].reshape(2, Fr, H, W, 4).permute(0, 4, 1, 2, 3)
+    eps = e[0:1] + gs * (e[1:2] - e[0:1])
+    x0 = (lat0 - math.sqrt(1 - a_t) * eps) / math.sqrt(a_t)
+    want = math.sqrt(a_p) * x0 + math.sqrt(1 - a_p) * eps
+    assert torch.allclose(eps_out, eps, rtol=1e-6, atol=1e-6)
+    assert rel_l2(lat, want) < 1e-6
+
+    # paste-back
+    n, HWp = 4, 64 * 64
+    dec = torch.randn(n * HWp, 32, generator=g).to(DEV)
+    refp = torch.randn(n, 3, HWp, generator=g).to(DEV)
+    m = (torch.rand(n, 1, HWp, generator=g) > 0.4).float().to(DEV)
+    o = torch.empty(n, 3, HWp, device=DEV)
+    L.paste_back(dec, 32, refp, m, n, HWp, o)
+    d = dec[:, :3].reshape(n, HWp, 3).permute(0, 2, 1)
+    assert torch.allclose(o, d * (1 - m) + refp * m, rtol=1e-6, atol=1e-6)
+
+
+def test_layout_and_time_embedding():
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(15)
+    B, C, Fr, HW = 2, 13, 4, 64
+    x = torch.randn(B, C, Fr, HW, generator=g).to(DEV)
+    out = torch.empty(B * Fr * HW, 64, dtype=torch.float16, device=DEV)
+    L.ncfhw_to_cl(x, B, C, Fr, HW, 64, 0.5, out)
+    want = (x * 0.5).permute(0, 2, 3, 1).reshape(B * Fr * HW, C).half()
+    assert torch.equal(out[:, :C], want) and torch.count_nonzero(out[:, C:]) == 0
+    y = torch.randn(B * Fr * HW, 32, generator=g).to(DEV)
+    back = torch.empty(B, 4, Fr, HW, device=DEV)
+    L.cl_to_ncfhw(y, 32, B, 4, Fr, HW, back)
+    assert torch.equal(back, y[:, :4].reshape(B, Fr, HW, 4).permute(0, 3, 1, 2))
+
+    t = torch.tensor([951.0, 1.0], device=DEV)
+    emb = torch.empty(2, 320, device=DEV)
+    L.timestep_embedding(t, 2, 320, emb)
+    k = torch.arange(160, device=DEV, dtype=torch.float32)
+    freq = torch.exp(-math.log(10000.0) * k / 160)
+    e = t[:, None] * freq[None]
+    want = torch.cat([torch.cos(e), torch.sin(e)], -1)
+    assert torch.allclose(emb, want, atol=2e-4)
+
+    w = (torch.randn(1280, 320, generator=g) / math.sqrt(320)).half().to(DEV)
+    b = torch.randn(1280, generator=g).to(DEV)
+    add = torch.randn(1280, generator=g).to(DEV)
+    yv = torch.empty(2, 1280, device=DEV)
+    L.small_linear(emb, 2, 320, w, b, add, 1280, True, True, yv)
+    want = F.silu(F.silu(emb) @ w.float().t() + b) + add
+    assert rel_l2(yv, want) < 1e-5
