@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Headline benchmark: lip-synced frames/s (256^2, 20 DDIM steps, CFG 1.5) + UNet step ms (BASELINE.json).
+
+A "step" is ONE 16-frame segment through the whole hot path: 20 x {13-channel concat + CFG duplicate, UNet forward,
+CFG combine + DDIM update}, VAE decode, paste-back (BASELINE.json configs[1], the single-GPU configuration the metric
+is quoted on).  With N > 1 every rank processes its own K segments (segments of a clip are independent: weak
+scaling) and the decoded frames are gathered to rank 0 with NCCL inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]         # this framework (CUDA kernels behind the C-ABI)
+    python bench.py --impl reference ...                         # CPU reference arm: oracle port on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FRAMES, HEIGHT, WIDTH, DDIM_STEPS, GUIDANCE = 16, 256, 256, 20, 1.5
+METRIC = "lip-synced frames/s (256x256, 20 DDIM steps, CFG 1.5)"
+WORKLOAD = "configs[1]: one 16-frame 256x256 segment per step: 20x(UNet3D fwd, CFG batch 2, 13x16x32x32 in, " \
+           "Whisper embeds 16x50x384) + DDIM + VAE decode + paste-back, random-init stage2 weights"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_forward_sample(threads: int):
+    """the oracle port (oracle/unet_ref.py, fp32) on the host cores: ONE CFG-batched UNet forward of the 20 a segment
+    needs; frames/s extrapolated as 16 / (20 * t) (VAE decode, 5.8 % of the FLOPs, left out => flatters the CPU)"""
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.spec import STAGE2_UNET_CONFIG
+    from oracle.unet_ref import unet_forward
+
+    torch.set_num_threads(threads)
+    sd = syn.unet_state_dict(STAGE2_UNET_CONFIG, seed=0)
+    seg = syn.segment_inputs(11, 0, FRAMES, HEIGHT, WIDTH)
+    x = torch.cat([seg["latents"]] * 2)
+    x = torch.cat([x, torch.cat([seg["mask_latents"]] * 2), torch.cat([seg["masked_image_latents"]] * 2),
+                   torch.cat([seg["ref_latents"]] * 2)], dim=1)
+    a = seg["audio_embeds"][None]
+    a = torch.cat([torch.zeros_like(a), a])
+
+    def one():
+        t0 = time.perf_counter()
+        unet_forward(sd, STAGE2_UNET_CONFIG, x, 951, a)
+        return time.perf_counter() - t0
+
+    return one
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for the same workload.  The reference is Python and cannot travel to
+    the GPU box (no diffusers / decord there, and /root/reference is absent), so this times the oracle port, which
+    oracle/make_golden.py pins to the reference's own modules at rel-L2 2e-6."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    one = cpu_forward_sample(threads)
+    budget = 400.0
+    t_first = one()
+    warm_done = 1
+    times = []
+    for _ in range(max(args.warmup - 1, 0)):
+        if t_first * (warm_done + 1 + args.steps) > budget:
+            break
+        one()
+        warm_done += 1
+    for _ in range(args.steps):
+        times.append(one())
+        if sum(times) + t_first * warm_done > budget and len(times) >= 1:
+            break
+    t = sum(times) / len(times)
+    fps = FRAMES / (DDIM_STEPS * t)
+    sample = (f"each step = 1 CFG-batched UNet forward (fp32, oracle port) of the {DDIM_STEPS} per segment; "
+              f"frames/s = 16 / (20 * t_fwd), VAE decode excluded; {len(times)} timed + {warm_done} warm-up samples")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": warm_done, "ms_per_step": DDIM_STEPS * t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD}, "unet_step_ms": t * 1e3,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-kind time table to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.pipeline import LipsyncPipeline
+    from latentsync_b200.scheduler import DDIMScheduler
+    from latentsync_b200.spec import STAGE2_UNET_CONFIG
+    from latentsync_b200.unet import UNet3DConditionModel
+    from latentsync_b200.vae import AutoencoderKLDecoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+
+    # ---- model with synthetic stage2 weights, plans captured into CUDA graphs
+    cfg = STAGE2_UNET_CONFIG
+    unet = UNet3DConditionModel.from_config(cfg)
+    unet.load_state_dict(syn.unet_state_dict(cfg, seed=0))
+    unet = unet.to(dev).eval()
+    vae = AutoencoderKLDecoder(syn.vae_decoder_state_dict(seed=0), device=dev)
+    pipe = LipsyncPipeline(vae, None, unet, DDIMScheduler()).to(dev)
+    h, w = HEIGHT // 8, WIDTH // 8
+    uplan = unet.plan(2, FRAMES, h, w, 50)
+    vplan = vae.plan(FRAMES, h, w)
+
+    # ---- synthetic segments: device-resident copies for `value`, pinned host copies for `e2e`
+    nseg = args.steps + args.warmup
+    host = [{k: v.pin_memory() for k, v in syn.segment_inputs(100 + rank, s, FRAMES, HEIGHT, WIDTH).items()}
+            for s in range(min(nseg, 4))]
+    resident = [{k: v.to(dev) for k, v in s.items()} for s in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    out_host = torch.empty(FRAMES, 3, HEIGHT, WIDTH, dtype=torch.float32).pin_memory()
+    d2h = out_host.numel() * out_host.element_size()
+    gather_list = [torch.empty(FRAMES, 3, HEIGHT, WIDTH, device=dev) for _ in range(world)] if rank == 0 else None
+
+    def step(seg, e2e: bool):
+        frames = pipe.run_segments([seg], DDIM_STEPS, GUIDANCE)[0]
+        if world > 1:
+            dist.gather(frames, gather_list, dst=0)
+        if e2e:
+            out_host.copy_(frames, non_blocking=True)
+        return frames
+
+    def timed(segs, e2e: bool):
+        for i in range(args.warmup):
+            step(segs[i % len(segs)], e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            step(segs[(args.warmup + i) % len(segs)], e2e)
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(resident, e2e=False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(host, e2e=True)
+    frames_total = FRAMES * args.steps * world
+    value = frames_total / (ms_total * 1e-3)
+    e2e_value = frames_total / (ms_e2e * 1e-3)
+
+    # ---- UNet step alone (graph replay) and the per-kernel table (eager, one event pair per launch)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        uplan.replay()
+    a.record()
+    for _ in range(DDIM_STEPS):
+        uplan.replay()
+    b.record()
+    torch.cuda.synchronize()
+    unet_ms = a.elapsed_time(b) / DDIM_STEPS
+    uplan.run_timed()
+    table = uplan.run_timed()
+    vtable = vplan.run_timed()
+    peak_tf, peak_bw, peak_src = measured_peaks()
+    n_gemm, gemm_ms = table["gemm"]
+    gemm_tf = uplan.flops("gemm") / (gemm_ms * 1e-3) / 1e12
+    seg_flops = DDIM_STEPS * uplan.flops() + vplan.flops()
+    launches_per_step = DDIM_STEPS * (uplan.launches + 2) + vplan.launches + 2 + (1 if world > 1 else 0)
+    if args.profile_kernels and rank == 0:
+        tot = sum(ms for _, ms in table.values())
+        for k, (n, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+            print(f"unet  {k:20s} {n:4d} launches {ms:8.3f} ms {100 * ms / tot:5.1f} %", file=sys.stderr)
+        tot = sum(ms for _, ms in vtable.values())
+        for k, (n, ms) in sorted(vtable.items(), key=lambda kv: -kv[1][1]):
+            print(f"vae   {k:20s} {n:4d} launches {ms:8.3f} ms {100 * ms / tot:5.1f} %", file=sys.stderr)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t = cpu_forward_sample(threads)()
+        cpu = {"value": FRAMES / (DDIM_STEPS * t), "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "1 CFG-batched fp32 UNet forward (oracle port of the reference modules) of the 20 per segment, "
+                         f"{t:.1f} s; frames/s = 16 / (20 * t), VAE decode excluded"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "segments_per_gpu": args.steps, "frames_per_segment": FRAMES,
+                       "ddim_steps": DDIM_STEPS, "guidance_scale": GUIDANCE, "parallelism": f"segments x{world}",
+                       "operands": "fp16 tensor-core operands, fp32 accumulate (bf16 cannot meet rel-L2 1e-2, DESIGN.md)",
+                       "l2": "no explicit flush: 2.5 GB of fp16 weights stream through the 126 MB L2 every UNet forward"},
+            "unet_step_ms": unet_ms,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": gemm_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
+                         "launches_per_unet_forward": n_gemm,
+                         "flops_per_unet_forward": uplan.flops("gemm"),
+                         "avg_launch_us": 1e3 * gemm_ms / n_gemm,
+                         "share_of_unet_forward": gemm_ms / sum(ms for _, ms in table.values()),
+                         "whole_step": {"flops_per_segment": seg_flops,
+                                        "achieved": seg_flops * args.steps / (ms_total * 1e-3) / 1e12 / 1.0,
+                                        "frac": seg_flops * args.steps / (ms_total * 1e-3) / 1e12 / peak_tf}},
+            "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,7 @@ typedef struct LsGemmArgs {
   /* epilogue */
   const float* bias; /* fp32 [bias_rows][N] or NULL */
   int32_t bias_div;  /* rows of `out` per bias row (e.g. F*H*W for a per-batch-element time embedding); 0 = one row */
+  int32_t bias_ld;   /* stride between bias rows in floats; 0 = N */
   const void* residual; /* fp16 [M][ldr] or NULL, added after bias */
   int32_t ldr;
   void* out; /* fp16 (or fp32 with LS_EPI_OUT_F32) [M][ldo]; with LS_EPI_GEGLU N_out = N/2 */
@@ -83,8 +84,9 @@ int ls_gemm(const LsGemmArgs* args, void* stream);
  * Normalisation (fp16 in/out, fp32 statistics).
  * ------------------------------------------------------------------------------------------------------- */
 /* GroupNorm statistics over `rows_per_inst` consecutive rows x (C/groups) channels of the virtual concatenation
- * [x1 | x2] (x2 may be NULL).  stats: fp32 [ninst][groups][2] = (sum, sum of squares); MUST be zeroed by the
- * caller (ls_fill_zero) before the call.
+ * [x1 | x2] (x2 may be NULL).  stats: fp32 [ninst][groups][2] = (sum, sum of squares), fully
+ * overwritten.  The reduction is deterministic (fixed-order partials, no floating-point atomics); its scratch is owned
+ * by the library and sized by the first (non-captured) call.
  * Replaces the reduction half of nn.GroupNorm: resnet.py:140,164 (5-D input: rows_per_inst = F*H*W),
  * attention.py:51, motion_module.py:101 (per frame: rows_per_inst = H*W), unet.py:236. */
 int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows, int32_t rows_per_inst,
@@ -122,9 +124,9 @@ typedef struct LsAttnArgs {
 } LsAttnArgs;
 int ls_attention(const LsAttnArgs* args, void* stream);
 
-/* row softmax for the VAE mid-block attention (diffusers AutoencoderKL: 1 head, d = 512): p = softmax(s) over
- * `cols`, fp16 in/out.  scale is folded into q upstream. */
-int ls_softmax_rows(const void* s, int64_t rows, int32_t cols, void* p, void* stream);
+/* row softmax for the VAE mid-block attention (diffusers AutoencoderKL: 1 head, d = 512, S = 1024 - too wide for
+ * the fused kernel above): p = softmax(scale * s) over `cols`; s fp32 (GEMM with LS_EPI_OUT_F32), p fp16. */
+int ls_softmax_rows(const float* s, int64_t rows, int32_t cols, float scale, void* p, void* stream);
 /* batched fp16 transpose [batch][R][C] -> [batch][C][R] */
 int ls_transpose(const void* x, int32_t batch, int32_t R, int32_t C, void* y, void* stream);
 

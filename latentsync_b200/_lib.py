@@ -38,6 +38,7 @@ class LsGemmArgs(C.Structure):
         ("b_batch_stride", C.c_int64),
         ("bias", C.c_void_p),
         ("bias_div", C.c_int32),
+        ("bias_ld", C.c_int32),
         ("residual", C.c_void_p),
         ("ldr", C.c_int32),
         ("out", C.c_void_p),
@@ -86,7 +87,7 @@ SYMBOLS = {
     "ls_groupnorm_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _i32, _vp, _vp]),
     "ls_layernorm": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp]),
     "ls_attention": (C.c_int, [C.POINTER(LsAttnArgs), _vp]),
-    "ls_softmax_rows": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "ls_softmax_rows": (C.c_int, [_vp, _i64, _i32, _f32, _vp, _vp]),
     "ls_transpose": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "ls_concat13": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "ls_cfg_ddim_step": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _vp]),
@@ -176,6 +177,7 @@ def gemm(
     ldo: int,
     bias: Optional[torch.Tensor] = None,
     bias_div: int = 0,
+    bias_ld: int = 0,
     residual: Optional[torch.Tensor] = None,
     ldr: int = 0,
     flags: int = 0,
@@ -201,6 +203,7 @@ def gemm(
         assert bias.dtype == torch.float32
     a.bias = _ptr(bias)
     a.bias_div = bias_div
+    a.bias_ld = bias_ld
     a.residual = _ptr(residual)
     a.ldr = ldr
     a.out = _ptr(out)
@@ -229,7 +232,6 @@ def groupnorm(
     ninst = rows // rows_per_inst
     assert stats.dtype == torch.float32 and stats.numel() >= ninst * groups * 2
     st = _stream()
-    _check(L.ls_fill_zero(_ptr(stats), ninst * groups * 2 * 4, st), "ls_fill_zero")
     _check(L.ls_groupnorm_stats(_ptr(x1), c1, _ptr(x2), c2, rows, rows_per_inst, groups, _ptr(stats), st),
            "ls_groupnorm_stats")
     _check(
@@ -262,8 +264,9 @@ def attention(q, k, v, out, ldq, ldk, ldv, ldo, batch, heads, head_dim, sq, skv,
     _check(lib().ls_attention(C.byref(a), _stream()), "ls_attention")
 
 
-def softmax_rows(s, rows, cols, p) -> None:
-    _check(lib().ls_softmax_rows(_ptr(s), rows, cols, _ptr(p), _stream()), "ls_softmax_rows")
+def softmax_rows(s, rows, cols, p, scale=1.0) -> None:
+    assert s.dtype == torch.float32
+    _check(lib().ls_softmax_rows(_ptr(s), rows, cols, scale, _ptr(p), _stream()), "ls_softmax_rows")
 
 
 def transpose(x, batch, R, Cc, y) -> None:

@@ -43,6 +43,7 @@ struct GemmKParams {
   int stages;
   const float* bias;
   int bias_div;
+  int bias_ld;
   const __half* residual;
   int ldr;
   void* out;
@@ -115,9 +116,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmKParams& p, int64_t m
 
 __device__ __forceinline__ void add_bias32(const GemmKParams& p, int64_t m, int n_base, float (&f)[32]) {
   if (p.bias == nullptr) return;
-  const float* b = p.bias + (p.bias_div > 0 ? (m / p.bias_div) * (int64_t)p.N : 0) + n_base;
+  const float* b = p.bias + (p.bias_div > 0 ? (m / p.bias_div) * (int64_t)p.bias_ld : 0) + n_base;
   const int nvalid = min(32, p.N - n_base);
-  if (nvalid == 32 && (p.N & 3) == 0) {
+  if (nvalid == 32 && (p.bias_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(b + j * 4));
@@ -490,6 +491,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
 
   p.bias = a->bias;
   p.bias_div = a->bias_div;
+  p.bias_ld = a->bias_ld > 0 ? a->bias_ld : a->N;
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.ldr = a->ldr;
   p.out = a->out;

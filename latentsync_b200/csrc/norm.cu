@@ -14,18 +14,21 @@ namespace ls {
 extern std::atomic<int64_t> g_launch_count;
 
 // -------------------------------------------------------------------------------------------------- GroupNorm
+// Deterministic two-level reduction (no floating-point atomics): every CTA reduces its row chunk per channel pair,
+// folds pairs into groups in a fixed order and writes one partial per (instance, chunk, group); the CTA that arrives
+// last at the per-instance ticket (an integer atomic) sums the partials in chunk order and resets the ticket.
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
-                                int rows_per_inst, int rows_per_chunk, int groups, float* __restrict__ stats) {
-  __shared__ float s_sum[64], s_sq[64];
+                                int rows_per_inst, int rows_per_chunk, int groups, float* __restrict__ partial,
+                                float* __restrict__ stats, unsigned int* __restrict__ tickets) {
+  extern __shared__ float gs_sm[];  // [npairs] sums, [npairs] sums of squares
+  __shared__ int s_last;
   const int C = c1 + c2;
   const int cg = C / groups;
   const int npairs = C >> 1;
-  if (threadIdx.x < 64) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
+  float* sh_s = gs_sm;
+  float* sh_q = gs_sm + npairs;
   const int inst = blockIdx.y;
+  const int chunks = gridDim.x;
   const int64_t row0 = (int64_t)inst * rows_per_inst + (int64_t)blockIdx.x * rows_per_chunk;
   int64_t row_end = row0 + rows_per_chunk;
   const int64_t inst_end = (int64_t)(inst + 1) * rows_per_inst;
@@ -50,15 +53,42 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __h
       s += f.x + f.y;
       ss += f.x * f.x + f.y * f.y;
     }
-    const int g = c / cg;
-    atomicAdd(&s_sum[g], s);
-    atomicAdd(&s_sq[g], ss);
+    sh_s[pair] = s;
+    sh_q[pair] = ss;
   }
   __syncthreads();
+  float* my_partial = partial + ((int64_t)inst * chunks + blockIdx.x) * groups * 2;
   if (threadIdx.x < groups) {
-    atomicAdd(&stats[((int64_t)inst * groups + threadIdx.x) * 2], s_sum[threadIdx.x]);
-    atomicAdd(&stats[((int64_t)inst * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    const int ppg = cg >> 1;
+    float s = 0.f, ss = 0.f;
+    for (int i = 0; i < ppg; ++i) {
+      s += sh_s[threadIdx.x * ppg + i];
+      ss += sh_q[threadIdx.x * ppg + i];
+    }
+    my_partial[threadIdx.x * 2] = s;
+    my_partial[threadIdx.x * 2 + 1] = ss;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(&tickets[inst], 1u);
+    s_last = (old == (unsigned int)chunks - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // 4 threads per (group, stat): interleaved chunk ranges, combined in a fixed shuffle order
+  const int item = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const bool active = item < groups * 2;
+  float acc = 0.f;
+  if (active) {
+    const float* base = partial + (int64_t)inst * chunks * groups * 2 + item;
+    for (int ch = part; ch < chunks; ch += 4) acc += __ldcg(base + (int64_t)ch * groups * 2);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (active && part == 0) stats[(int64_t)inst * groups * 2 + item] = acc;
+  if (threadIdx.x == 0) tickets[inst] = 0u;
 }
 
 __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
@@ -193,26 +223,25 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int64_t rows, int
 // ------------------------------------------------------------------------------------------------- row softmax
 constexpr int SM_MAXV = 8;  // cols <= 8 * 32 * 8 = 2048
 
-__global__ void softmax_rows_kernel(const __half* __restrict__ s, int64_t rows, int cols, __half* __restrict__ p) {
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int64_t rows, int cols, float scale,
+                                    __half* __restrict__ p) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = cols >> 3;
+  const float sl = scale * 1.4426950408889634f;
   float v[SM_MAXV][8];
   float mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < SM_MAXV; ++i) {
     const int vi = lane + 32 * i;
     if (vi < nvec) {
-      const uint4 u = *reinterpret_cast<const uint4*>(s + row * cols + vi * 8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+      const float4 a = *reinterpret_cast<const float4*>(s + row * cols + vi * 8);
+      const float4 b = *reinterpret_cast<const float4*>(s + row * cols + vi * 8 + 4);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+      v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h2[e]);
-        v[i][2 * e] = f.x;
-        v[i][2 * e + 1] = f.y;
-        mx = fmaxf(mx, fmaxf(f.x, f.y));
-      }
+      for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[i][e]);
     }
   }
 #pragma unroll
@@ -224,7 +253,7 @@ __global__ void softmax_rows_kernel(const __half* __restrict__ s, int64_t rows, 
     if (vi < nvec) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        v[i][e] = exp2f((v[i][e] - mx) * 1.4426950408889634f);
+        v[i][e] = exp2f((v[i][e] - mx) * sl);
         sum += v[i][e];
       }
     }
@@ -265,22 +294,56 @@ __global__ void transpose_kernel(const __half* __restrict__ x, int R, int C, __h
 
 using namespace ls;
 
+// scratch for the partial sums + tickets, owned by the library (one per device, grown on demand; single stream use)
+namespace ls {
+struct GnScratch {
+  float* partial = nullptr;
+  size_t partial_floats = 0;
+  unsigned int* tickets = nullptr;
+  size_t ntickets = 0;
+};
+static GnScratch g_gn[16];
+}  // namespace ls
+
 extern "C" int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows,
                                   int32_t rows_per_inst, int32_t groups, float* stats, void* stream) {
   const int C = c1 + (x2 ? c2 : 0);
   if (!x2) c2 = 0;
   LS_CHECK(x1 && stats && rows > 0 && rows_per_inst > 0 && rows % rows_per_inst == 0, "ls_groupnorm_stats: bad args");
-  LS_CHECK(groups > 0 && groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0 && c1 % 2 == 0,
+  LS_CHECK(groups > 0 && groups <= 32 && C % groups == 0 && (C / groups) % 2 == 0 && c1 % 2 == 0,
            "ls_groupnorm_stats: C=%d groups=%d unsupported", C, groups);
   int ninst, chunks, rpc;
   gn_chunking(rows, rows_per_inst, 1184, ninst, chunks, rpc);
+  int dev = 0;
+  LS_CUDA(cudaGetDevice(&dev));
+  LS_CHECK(dev >= 0 && dev < 16, "ls_groupnorm_stats: device index %d out of range", dev);
+  GnScratch& sc = g_gn[dev];
+  const size_t need = (size_t)ninst * chunks * groups * 2;
+  if (need > sc.partial_floats || (size_t)ninst > sc.ntickets) {
+    // growing is not stream-ordered: only legal outside graph capture (plans warm up eagerly before capturing)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+    LS_CHECK(cs == cudaStreamCaptureStatusNone, "ls_groupnorm_stats: scratch must be sized by an eager warm-up run");
+    LS_CUDA(cudaDeviceSynchronize());
+    if (need > sc.partial_floats) {
+      if (sc.partial) cudaFree(sc.partial);
+      sc.partial_floats = need > (1u << 20) ? need : (1u << 20);
+      LS_CUDA(cudaMalloc(&sc.partial, sc.partial_floats * sizeof(float)));
+    }
+    if ((size_t)ninst > sc.ntickets) {
+      if (sc.tickets) cudaFree(sc.tickets);
+      sc.ntickets = ninst > 4096 ? ninst : 4096;
+      LS_CUDA(cudaMalloc(&sc.tickets, sc.ntickets * sizeof(unsigned int)));
+      LS_CUDA(cudaMemset(sc.tickets, 0, sc.ntickets * sizeof(unsigned int)));
+    }
+  }
   int threads = C / 2;
-  if (threads > 1024) threads = (threads + 1) / 2;
+  if (threads > 512) threads = 512;
   threads = (threads + 31) / 32 * 32;
-  if (threads < 64) threads = 64;
-  if (threads > 1024) threads = 1024;
-  gn_stats_kernel<<<dim3(chunks, ninst), threads, 0, (cudaStream_t)stream>>>(
-      (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, stats);
+  if (threads < 256) threads = 256;  // the final reduction uses 4 threads per (group, stat): 4 * 64 = 256
+  const size_t smem = (size_t)C * sizeof(float);
+  gn_stats_kernel<<<dim3(chunks, ninst), threads, smem, (cudaStream_t)stream>>>(
+      (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial, stats, sc.tickets);
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -318,11 +381,12 @@ extern "C" int ls_layernorm(const void* x, int64_t rows, int32_t C, const float*
   return 0;
 }
 
-extern "C" int ls_softmax_rows(const void* s, int64_t rows, int32_t cols, void* p, void* stream) {
-  LS_CHECK(s && p && rows > 0 && cols % 8 == 0 && cols <= SM_MAXV * 256, "ls_softmax_rows: cols=%d unsupported", cols);
+extern "C" int ls_softmax_rows(const float* s, int64_t rows, int32_t cols, float scale, void* p, void* stream) {
+  LS_CHECK(s && p && rows > 0 && cols % 8 == 0 && cols <= SM_MAXV * 256 && scale > 0.f,
+           "ls_softmax_rows: cols=%d unsupported", cols);
   const int wpb = 8;
   softmax_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)s, rows, cols, (__half*)p);
+      s, rows, cols, scale, (__half*)p);
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;

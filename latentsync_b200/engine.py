@@ -1,0 +1,838 @@
+"""Host-side execution engine: turns a state_dict into packed fp16 weights and a shape-specialised *plan* - a fixed
+sequence of C-ABI kernel launches over pre-allocated HBM buffers - which is captured once into a CUDA graph and
+replayed for every denoising step (the reference's eager forward is ~600 module calls).
+
+Activation layout everywhere: channels-last fp16, a (b f) x H x W x C video tensor is the row-major matrix
+[(b f h w), C].  Reference module semantics are cited at each builder function.
+
+PyTorch is used for device memory, streams and CUDA-graph capture only; every arithmetic op is a kernel from
+latentsync_b200/csrc reached through include/latentsync_b200.h.  There is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .spec import SD_VAE_FT_MSE_CONFIG, unet_config
+
+GEGLU_TILE = 256
+KPAD = 64  # GEMM K granularity (one 128-byte swizzle row of fp16)
+
+
+# --------------------------------------------------------------------------------------------------- buffers
+class _Pool:
+    """Exact-size free lists of device buffers.  A `Buf` returns its storage on garbage collection; because the plan is
+    built in execution order and runs on one stream, a later op may safely overwrite a buffer whose last reader was
+    recorded earlier.  Re-using storage keeps the working set inside the 126 MB L2 instead of streaming fresh lines."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free: Dict[int, List[torch.Tensor]] = {}
+        self.all: List[torch.Tensor] = []
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        lst = self.free.get(nbytes)
+        if lst:
+            return lst.pop()
+        t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.all.append(t)
+        return t
+
+    def give(self, t: torch.Tensor) -> None:
+        self.free.setdefault(t.numel(), []).append(t)
+
+    def total_bytes(self) -> int:
+        return sum(t.numel() for t in self.all)
+
+
+class Buf:
+    """[rows, cols] device matrix handle; closures recorded in a plan capture only `.ptr` (an int)."""
+
+    __slots__ = ("pool", "store", "ptr", "rows", "cols", "dtype")
+
+    def __init__(self, pool: _Pool, rows: int, cols: int, dtype=torch.float16):
+        self.pool = pool
+        self.rows, self.cols, self.dtype = rows, cols, dtype
+        nbytes = rows * cols * torch.empty((), dtype=dtype).element_size()
+        nbytes = (nbytes + 255) // 256 * 256
+        self.store = pool.take(nbytes)
+        self.ptr = self.store.data_ptr()
+
+    def __del__(self):
+        try:
+            self.pool.give(self.store)
+        except Exception:  # interpreter shutdown
+            pass
+
+    def tensor(self) -> torch.Tensor:
+        n = self.rows * self.cols
+        return self.store.view(self.dtype)[:n].view(self.rows, self.cols)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {L.lib().ls_last_error().decode()}")
+
+
+class Plan:
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.pool = _Pool(self.device)
+        self.ops = []  # (callable, name)
+        self.keep = []  # Bufs / tensors that must outlive the build (static inputs, outputs)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.lib = L.lib()
+        self.stats_cursor = 0
+        self.stats: Optional[torch.Tensor] = None
+        self.launches = 0
+        self.kinds: List[str] = []  # one tag per recorded launch (bench.py times kernels by kind)
+        self.op_flops: List[float] = []  # algorithmic FLOPs of each launch (2*M*N*K for GEMM/conv, 4*B*h*Sq*Sk*d for SDPA)
+
+    # ---- buffers
+    def buf(self, rows, cols, dtype=torch.float16) -> Buf:
+        return Buf(self.pool, rows, cols, dtype)
+
+    def static(self, rows, cols, dtype=torch.float16) -> Buf:
+        b = Buf(self.pool, rows, cols, dtype)
+        self.keep.append(b)
+        return b
+
+    # ---- execution
+    def run(self) -> None:
+        for fn in self.ops:
+            fn()
+
+    def run_timed(self) -> Dict[str, Tuple[int, float]]:
+        """eager run with a CUDA event pair around every launch: kind -> (launches, total ms).  Diagnostic only."""
+        evs = []
+        for fn in self.ops:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(self.device)
+        out: Dict[str, Tuple[int, float]] = {}
+        for kind, (a, b) in zip(self.kinds, evs):
+            n, ms = out.get(kind, (0, 0.0))
+            out[kind] = (n + 1, ms + a.elapsed_time(b))
+        return out
+
+    def capture(self) -> None:
+        """warm up eagerly (sets function attributes, validates every launch), then record the CUDA graph"""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.run()
+            self.run()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+
+    def replay(self) -> None:
+        if self.graph is None:
+            self.run()
+        else:
+            self.graph.replay()
+
+    # ---- emitters (each records ONE launch)
+    def _emit(self, fn, kind: str = "other", flops: float = 0.0) -> None:
+        self.ops.append(fn)
+        self.kinds.append(kind)
+        self.op_flops.append(flops)
+        self.launches += 1
+
+    def flops(self, kind: Optional[str] = None) -> float:
+        return sum(f for k, f in zip(self.kinds, self.op_flops) if kind is None or k == kind)
+
+    def gemm(self, segs: Sequence[Tuple[int, int, int, int]], nimg: int, H: int, W: int, w: torch.Tensor, N: int,
+             out_ptr: int, ldo: int, bias_ptr: int = 0, bias_div: int = 0, bias_ld: int = 0, residual_ptr: int = 0,
+             ldr: int = 0, flags: int = 0, tile_n: int = 0, b_batch_stride: int = 0, b_ptr: int = 0) -> None:
+        """segs: (ptr, channels, ld, taps).  w: packed fp16 [N, Ktot] tensor (kept alive by the engine) or b_ptr."""
+        a = L.LsGemmArgs()
+        a.nseg = len(segs)
+        ktot = 0
+        for i, (ptr, ch, ld, taps) in enumerate(segs):
+            a.a_ptr[i], a.a_ch[i], a.a_ld[i], a.a_taps[i] = ptr, ch, ld, taps
+            ktot += ch * taps
+        a.nimg, a.H, a.W = nimg, H, W
+        if w is not None:
+            assert w.dtype == torch.float16 and w.is_contiguous() and w.shape[-1] == ktot and w.shape[0] == N, (
+                tuple(w.shape), N, ktot)
+            a.b_ptr = w.data_ptr()
+        else:
+            a.b_ptr = b_ptr
+        a.N, a.Ktot, a.b_batch_stride = N, ktot, b_batch_stride
+        a.bias = bias_ptr or None
+        a.bias_div, a.bias_ld = bias_div, bias_ld
+        a.residual = residual_ptr or None
+        a.ldr = ldr
+        a.out, a.ldo, a.flags, a.tile_n = out_ptr, ldo, flags, tile_n
+        fn = self.lib.ls_gemm
+        self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_gemm"), "gemm", 2.0 * nimg * H * W * N * ktot)
+
+    def begin_stats(self, nfloats: int) -> None:
+        """one fp32 arena for the (sum, sumsq) results of every GroupNorm of the plan"""
+        self.stats = torch.zeros(nfloats, dtype=torch.float32, device=self.device)
+
+    def groupnorm(self, x1: int, c1: int, x2: int, c2: int, rows: int, rows_per_inst: int, groups: int,
+                  gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool, out_ptr: int) -> None:
+        ninst = rows // rows_per_inst
+        n = ninst * groups * 2
+        assert self.stats is not None and self.stats_cursor + n <= self.stats.numel(), "GroupNorm stats arena too small"
+        sp = self.stats.data_ptr() + self.stats_cursor * 4
+        self.stats_cursor += n
+        f1, f2 = self.lib.ls_groupnorm_stats, self.lib.ls_groupnorm_apply
+        g, b = gamma.data_ptr(), beta.data_ptr()
+        x2p = x2 or None
+        self._emit(lambda: _chk(f1(x1, c1, x2p, c2, rows, rows_per_inst, groups, sp, _stream()), "ls_groupnorm_stats"),
+                   "gn_stats")
+        self._emit(lambda: _chk(f2(x1, c1, x2p, c2, rows, rows_per_inst, groups, sp, g, b, eps, int(silu), out_ptr,
+                                   _stream()), "ls_groupnorm_apply"), "gn_apply")
+
+    def layernorm(self, x: int, rows: int, Cc: int, gamma: torch.Tensor, beta: torch.Tensor, out_ptr: int,
+                  pe: Optional[torch.Tensor] = None, rows_per_frame: int = 1, nframes: int = 1) -> None:
+        fn = self.lib.ls_layernorm
+        g, b = gamma.data_ptr(), beta.data_ptr()
+        pp = pe.data_ptr() if pe is not None else None
+        self._emit(lambda: _chk(fn(x, rows, Cc, g, b, 1e-5, pp, rows_per_frame, nframes, out_ptr, _stream()),
+                                "ls_layernorm"), "layernorm")
+
+    def attention(self, q: int, k: int, v: int, out: int, ldq: int, ldk: int, ldv: int, ldo: int, batch: int,
+                  heads: int, head_dim: int, sq: int, skv: int, q_addr=None, kv_addr=None) -> None:
+        a = L.LsAttnArgs()
+        a.q, a.k, a.v, a.out = q, k, v, out
+        a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
+        a.batch, a.heads, a.head_dim, a.sq, a.skv = batch, heads, head_dim, sq, skv
+        a.q_inner, a.q_outer_stride, a.q_inner_stride, a.q_seq_stride = q_addr or (1, sq, 0, 1)
+        a.kv_inner, a.kv_outer_stride, a.kv_inner_stride, a.kv_seq_stride = kv_addr or (1, skv, 0, 1)
+        a.scale = float(head_dim) ** -0.5
+        fn = self.lib.ls_attention
+        self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_attention"), "attention",
+                   4.0 * batch * heads * sq * skv * head_dim)
+
+    def call(self, name: str, *args) -> None:
+        """any other C-ABI function whose last parameter is the stream"""
+        fn = getattr(self.lib, name)
+        self._emit(lambda: _chk(fn(*args, _stream()), name), name[3:])
+
+
+# ----------------------------------------------------------------------------------------------- weight packing
+def _h(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float16).contiguous()
+
+
+def pack_conv3x3(w: torch.Tensor, splits: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """OIHW -> fp16 [N, sum_seg 9*pad64(c_seg)], K index = (segment, tap=ky*3+kx, channel)"""
+    n, cin = w.shape[0], w.shape[1]
+    splits = list(splits) if splits else [cin]
+    assert sum(splits) == cin
+    parts, c0 = [], 0
+    for cs in splits:
+        cp = (cs + KPAD - 1) // KPAD * KPAD
+        p = torch.zeros(n, w.shape[2], w.shape[3], cp, dtype=torch.float32, device=w.device)
+        p[..., :cs] = w[:, c0:c0 + cs].permute(0, 2, 3, 1)
+        parts.append(p.reshape(n, -1))
+        c0 += cs
+    return _h(torch.cat(parts, dim=1))
+
+
+def pack_1x1(w: torch.Tensor) -> torch.Tensor:
+    n, cin = w.shape[0], w.shape[1]
+    cp = (cin + KPAD - 1) // KPAD * KPAD
+    p = torch.zeros(n, cp, dtype=torch.float32, device=w.device)
+    p[:, :cin] = w.reshape(n, cin)
+    return _h(p)
+
+
+class _Weights:
+    """name -> packed device tensor; everything a plan points at lives here for the life of the engine"""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device):
+        self.sd = sd
+        self.device = torch.device(device)
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def raw(self, key: str) -> torch.Tensor:
+        return self.sd[key].detach().to(self.device, torch.float32)
+
+    def has(self, key: str) -> bool:
+        return key in self.sd
+
+    def put(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        self.t[name] = t.contiguous()
+        return self.t[name]
+
+    def f32(self, key: str) -> torch.Tensor:
+        if key not in self.t:
+            self.put(key, self.raw(key))
+        return self.t[key]
+
+    def lin(self, key: str) -> torch.Tensor:
+        """Linear / 1x1-conv weight -> fp16 [N, K]"""
+        name = key + "#h"
+        if name not in self.t:
+            self.put(name, pack_1x1(self.raw(key)))
+        return self.t[name]
+
+    def conv(self, key: str, splits=None) -> torch.Tensor:
+        name = key + "#c"
+        if name not in self.t:
+            self.put(name, pack_conv3x3(self.raw(key), splits))
+        return self.t[name]
+
+    def bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.t.values())
+
+
+# ------------------------------------------------------------------------------------------------ UNet engine
+class UNetEngine:
+    """UNet3DConditionModel.forward (latentsync/models/unet.py:312-471) as a CUDA-graph plan per input shape."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: dict, device="cuda"):
+        self.cfg = unet_config(cfg)
+        c = self.cfg
+        self.device = torch.device(device)
+        self.w = _Weights(state_dict, self.device)
+        self.plans: Dict[Tuple[int, int, int, int, int], "UNetPlan"] = {}
+        self._pack()
+
+    # reference key helpers
+    def _resnet_names(self) -> List[str]:
+        c = self.cfg
+        names = []
+        for i in range(len(c["down_block_types"])):
+            names += [f"down_blocks.{i}.resnets.{j}" for j in range(c["layers_per_block"])]
+        names += ["mid_block.resnets.0", "mid_block.resnets.1"]
+        for i in range(len(c["up_block_types"])):
+            names += [f"up_blocks.{i}.resnets.{j}" for j in range(c["layers_per_block"] + 1)]
+        return names
+
+    def _attn_names(self) -> List[str]:
+        c = self.cfg
+        names = []
+        for i, t in enumerate(c["down_block_types"]):
+            if t == "CrossAttnDownBlock3D":
+                names += [f"down_blocks.{i}.attentions.{j}" for j in range(c["layers_per_block"])]
+        names += ["mid_block.attentions.0"]
+        for i, t in enumerate(c["up_block_types"]):
+            if t == "CrossAttnUpBlock3D":
+                names += [f"up_blocks.{i}.attentions.{j}" for j in range(c["layers_per_block"] + 1)]
+        return names
+
+    def _pack(self) -> None:
+        """one-time repack of the checkpoint tensors into GEMM operand layouts (fp16, K-major)"""
+        w, c = self.w, self.cfg
+        boc = c["block_out_channels"]
+        # time path (unet.py:95-98,376-382) and all ResnetBlock3D.time_emb_proj (resnet.py:152) as ONE matrix
+        w.put("te1.w", _h(w.raw("time_embedding.linear_1.weight")))
+        w.put("te2.w", _h(w.raw("time_embedding.linear_2.weight")))
+        tw, tb, cb, self.tproj_off = [], [], [], {}
+        off = 0
+        for r in self._resnet_names():
+            tw.append(w.raw(r + ".time_emb_proj.weight"))
+            tb.append(w.raw(r + ".time_emb_proj.bias"))
+            cb.append(w.raw(r + ".conv1.bias"))
+            self.tproj_off[r] = off
+            off += tw[-1].shape[0]
+        self.tproj_total = off
+        w.put("tproj.w", _h(torch.cat(tw)))
+        w.put("tproj.b", torch.cat(tb))
+        w.put("tproj.add", torch.cat(cb))
+        # audio cross-attention K/V projections of every block as ONE matrix (attention.py:231-232)
+        self.kv_off = {}
+        if c["add_audio_layer"]:
+            kw, off = [], 0
+            for a in self._attn_names():
+                t = a + ".transformer_blocks.0.attn2"
+                k, v = w.raw(t + ".to_k.weight"), w.raw(t + ".to_v.weight")
+                self.kv_off[a] = (off, off + k.shape[0])
+                off += k.shape[0] + v.shape[0]
+                kw += [k, v]
+            self.kv_total = off
+            kcat = torch.cat(kw)
+            w.put("kv.w", pack_1x1(kcat))
+        self.cross_k = (c["cross_attention_dim"] + KPAD - 1) // KPAD * KPAD
+
+    # ---- packed-weight accessors used by the plan builder
+    def qkv(self, p: str) -> torch.Tensor:
+        name = p + "#qkv"
+        if name not in self.w.t:
+            self.w.put(name, _h(torch.cat([self.w.raw(p + ".to_q.weight"), self.w.raw(p + ".to_k.weight"),
+                                            self.w.raw(p + ".to_v.weight")])))
+        return self.w.t[name]
+
+    def geglu(self, p: str) -> Tuple[torch.Tensor, torch.Tensor]:
+        name = p + "#geglu"
+        if name + ".w" not in self.w.t:
+            wp, bp = L.pack_geglu(self.w.raw(p + ".weight"), self.w.raw(p + ".bias"), GEGLU_TILE)
+            self.w.put(name + ".w", _h(wp))
+            self.w.put(name + ".b", bp)
+        return self.w.t[name + ".w"], self.w.t[name + ".b"]
+
+    def conv2_with_shortcut(self, r: str, splits: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """conv2 (3x3) and the 1x1 conv_shortcut of a ResnetBlock3D fused into one GEMM along K (resnet.py:215-221)"""
+        name = r + "#c2sc"
+        if name + ".w" not in self.w.t:
+            w2 = pack_conv3x3(self.w.raw(r + ".conv2.weight"))
+            ws = self.w.raw(r + ".conv_shortcut.weight")
+            parts, c0 = [w2], 0
+            for cs in splits:
+                parts.append(pack_1x1(ws[:, c0:c0 + cs]))
+                c0 += cs
+            self.w.put(name + ".w", torch.cat(parts, dim=1))
+            self.w.put(name + ".b", self.w.raw(r + ".conv2.bias") + self.w.raw(r + ".conv_shortcut.bias"))
+        return self.w.t[name + ".w"], self.w.t[name + ".b"]
+
+    def plan(self, B: int, F: int, H: int, W: int, S: int) -> "UNetPlan":
+        key = (B, F, H, W, S)
+        if key not in self.plans:
+            self.plans[key] = UNetPlan(self, B, F, H, W, S)
+        return self.plans[key]
+
+
+class UNetPlan(Plan):
+    def __init__(self, eng: UNetEngine, B: int, F: int, H: int, W: int, S: int):
+        super().__init__(eng.device)
+        self.eng = eng
+        self.B, self.F, self.H, self.W, self.S = B, F, H, W, S
+        self.taps: Dict[str, Tuple[Buf, int]] = {}  # name -> (buffer, level); filled only when LS_DEBUG_TAPS=1
+        self.debug = os.environ.get("LS_DEBUG_TAPS", "0") == "1"
+        c = eng.cfg
+        nlev = len(c["block_out_channels"])
+        assert H % (1 << (nlev - 1)) == 0 and W % (1 << (nlev - 1)) == 0, "latent size must divide by 2^(levels-1)"
+        self._build()
+
+    # -- geometry of level l
+    def _geo(self, lvl: int):
+        return self.H >> lvl, self.W >> lvl
+
+    def _rows(self, lvl: int) -> int:
+        h, w = self._geo(lvl)
+        return self.B * self.F * h * w
+
+    def _tap(self, name: str, x: Buf, lvl: int) -> None:
+        if self.debug:
+            self.taps[name] = (x, lvl)
+
+    def tap_tensor(self, name: str) -> torch.Tensor:
+        """debug: activation `name` as (B, C, F, h, w) fp32"""
+        x, lvl = self.taps[name]
+        h, w = self._geo(lvl)
+        return x.tensor().float().reshape(self.B, self.F, h, w, x.cols).permute(0, 4, 1, 2, 3).contiguous()
+
+    # -- module builders --------------------------------------------------------------------------------------
+    def _resnet(self, r: str, srcs: List[Tuple[Buf, int]], cout: int, lvl: int) -> Buf:
+        """ResnetBlock3D.forward (resnet.py:182-223). srcs = [(hidden, c1)] or [(hidden, c1), (skip, c2)]: the
+        torch.cat of unet_blocks.py:624,745 is never materialised for the convs; GroupNorm statistics span
+        (C/32, F, H, W) of the virtual concatenation per batch element (plain nn.GroupNorm on a 5-D tensor)."""
+        eng, w, c = self.eng, self.eng.w, self.eng.cfg
+        h, wd = self._geo(lvl)
+        rows = self._rows(lvl)
+        per_b = self.F * h * wd
+        cin = sum(ch for _, ch in srcs)
+        x1, c1 = srcs[0]
+        x2p, c2 = (srcs[1][0].ptr, srcs[1][1]) if len(srcs) > 1 else (0, 0)
+        g, eps = c["norm_num_groups"], c["norm_eps"]
+        y1 = self.buf(rows, cin)
+        self.groupnorm(x1.ptr, c1, x2p, c2, rows, per_b, g, w.f32(r + ".norm1.weight"), w.f32(r + ".norm1.bias"), eps,
+                       True, y1.ptr)
+        h1 = self.buf(rows, cout)
+        toff = eng.tproj_off[r]
+        self.gemm([(y1.ptr, cin, cin, 9)], self.B * self.F, h, wd, w.conv(r + ".conv1.weight"), cout, h1.ptr, cout,
+                  bias_ptr=self.tproj.ptr + toff * 4, bias_div=per_b, bias_ld=eng.tproj_total)
+        del y1
+        y2 = self.buf(rows, cout)
+        self.groupnorm(h1.ptr, cout, 0, 0, rows, per_b, g, w.f32(r + ".norm2.weight"), w.f32(r + ".norm2.bias"), eps,
+                       True, y2.ptr)
+        del h1
+        out = self.buf(rows, cout)
+        if w.has(r + ".conv_shortcut.weight"):
+            wp, bp = eng.conv2_with_shortcut(r, [ch for _, ch in srcs])
+            segs = [(y2.ptr, cout, cout, 9)] + [(b.ptr, ch, ch, 1) for b, ch in srcs]
+            self.gemm(segs, self.B * self.F, h, wd, wp, cout, out.ptr, cout, bias_ptr=bp.data_ptr())
+        else:
+            assert len(srcs) == 1 and c1 == cout
+            self.gemm([(y2.ptr, cout, cout, 9)], self.B * self.F, h, wd, w.conv(r + ".conv2.weight"), cout, out.ptr,
+                      cout, bias_ptr=w.f32(r + ".conv2.bias").data_ptr(), residual_ptr=x1.ptr, ldr=cout)
+        return out
+
+    def _linear(self, x: Buf, key: str, n: int, bias: bool = True, residual: Optional[Buf] = None) -> Buf:
+        w = self.eng.w
+        k = w.lin(key + ".weight").shape[1]
+        assert k == x.cols
+        out = self.buf(x.rows, n)
+        self.gemm([(x.ptr, k, k, 1)], 1, 1, x.rows, w.lin(key + ".weight"), n, out.ptr, n,
+                  bias_ptr=w.f32(key + ".bias").data_ptr() if bias else 0,
+                  residual_ptr=residual.ptr if residual is not None else 0, ldr=n)
+        return out
+
+    def _ff(self, ln: str, ff: str, hs: Buf) -> Buf:
+        """x += FF(LN(x)); diffusers FeedForward/GEGLU (attention.py:171,197 ; motion_module.py:200,216)"""
+        w = self.eng.w
+        cc = hs.cols
+        n = self.buf(hs.rows, cc)
+        self.layernorm(hs.ptr, hs.rows, cc, w.f32(ln + ".weight"), w.f32(ln + ".bias"), n.ptr)
+        wp, bp = self.eng.geglu(ff + ".net.0.proj")
+        gg = self.buf(hs.rows, 4 * cc)
+        self.gemm([(n.ptr, cc, cc, 1)], 1, 1, hs.rows, wp, 8 * cc, gg.ptr, 4 * cc, bias_ptr=bp.data_ptr(),
+                  flags=L.EPI_GEGLU, tile_n=GEGLU_TILE)
+        del n
+        return self._linear(gg, ff + ".net.2", cc, residual=hs)
+
+    def _transformer(self, a: str, x: Buf, cc: int, lvl: int) -> Buf:
+        """Transformer3DModel.forward (attention.py:82-124) + BasicTransformerBlock.forward (:174-199)"""
+        eng, w, c = self.eng, self.eng.w, self.eng.cfg
+        h, wd = self._geo(lvl)
+        rows, hw = self._rows(lvl), h * wd
+        heads = c["attention_head_dim"]
+        d = cc // heads
+        nrm = self.buf(rows, cc)
+        self.groupnorm(x.ptr, cc, 0, 0, rows, hw, c["norm_num_groups"], w.f32(a + ".norm.weight"),
+                       w.f32(a + ".norm.bias"), 1e-6, False, nrm.ptr)
+        hs = self._linear(nrm, a + ".proj_in", cc)
+        del nrm
+        t = a + ".transformer_blocks.0"
+        # self-attention over the h*w tokens of each frame
+        n = self.buf(rows, cc)
+        self.layernorm(hs.ptr, rows, cc, w.f32(t + ".norm1.weight"), w.f32(t + ".norm1.bias"), n.ptr)
+        qkv = self.buf(rows, 3 * cc)
+        self.gemm([(n.ptr, cc, cc, 1)], 1, 1, rows, eng.qkv(t + ".attn1"), 3 * cc, qkv.ptr, 3 * cc)
+        o = n  # reuse
+        self.attention(qkv.ptr, qkv.ptr + 2 * cc, qkv.ptr + 4 * cc, o.ptr, 3 * cc, 3 * cc, 3 * cc, cc, self.B * self.F,
+                       heads, d, hw, hw)
+        del qkv
+        hs2 = self._linear(o, t + ".attn1.to_out.0", cc, residual=hs)
+        del o, n, hs
+        hs = hs2
+        if c["add_audio_layer"] and self.audio_kv is not None:
+            # cross-attention: frame f attends to its own S audio tokens (attention.py:183-194)
+            n = self.buf(rows, cc)
+            self.layernorm(hs.ptr, rows, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), n.ptr)
+            q = self._linear(n, t + ".attn2.to_q", cc, bias=False)
+            koff, voff = eng.kv_off[a]
+            ldkv = eng.kv_total
+            self.attention(q.ptr, self.audio_kv.ptr + 2 * koff, self.audio_kv.ptr + 2 * voff, n.ptr, cc, ldkv, ldkv,
+                           cc, self.B * self.F, heads, d, hw, self.S)
+            del q
+            hs2 = self._linear(n, t + ".attn2.to_out.0", cc, residual=hs)
+            del n, hs
+            hs = hs2
+        hs = self._ff(t + ".norm3", t + ".ff", hs)
+        return self._linear(hs, a + ".proj_out", cc, residual=x)
+
+    def _motion(self, m: str, x: Buf, cc: int, lvl: int) -> Buf:
+        """VanillaTemporalModule (motion_module.py:126-151,203-218,262-313).  The "(b f) s c -> (b s) f c" transposes
+        are strides of the attention kernel, not copies; the sinusoid table is added inside the LayerNorm kernel."""
+        eng, w, c = self.eng, self.eng.w, self.eng.cfg
+        kw = c["motion_module_kwargs"]
+        heads = kw.get("num_attention_heads", 8)
+        h, wd = self._geo(lvl)
+        rows, hw = self._rows(lvl), h * wd
+        d = cc // heads
+        t = m + ".temporal_transformer"
+        nrm = self.buf(rows, cc)
+        self.groupnorm(x.ptr, cc, 0, 0, rows, hw, c["norm_num_groups"], w.f32(t + ".norm.weight"),
+                       w.f32(t + ".norm.bias"), 1e-6, False, nrm.ptr)
+        hs = self._linear(nrm, t + ".proj_in", cc)
+        del nrm
+        addr = (hw, self.F * hw, 1, hw)
+        i = 0
+        while w.has(f"{t}.transformer_blocks.{i}.ff_norm.weight"):
+            blk = f"{t}.transformer_blocks.{i}"
+            k = 0
+            while w.has(f"{blk}.attention_blocks.{k}.to_q.weight"):
+                ab = f"{blk}.attention_blocks.{k}"
+                pe = None
+                if w.has(ab + ".pos_encoder.pe"):
+                    name = ab + "#pe"
+                    if name not in w.t:
+                        w.put(name, w.raw(ab + ".pos_encoder.pe")[0, : self.F].contiguous())
+                    pe = w.t[name]
+                    assert pe.shape[0] == self.F, "more frames than temporal_position_encoding_max_len"
+                n = self.buf(rows, cc)
+                self.layernorm(hs.ptr, rows, cc, w.f32(f"{blk}.norms.{k}.weight"), w.f32(f"{blk}.norms.{k}.bias"),
+                               n.ptr, pe=pe, rows_per_frame=hw, nframes=self.F)
+                qkv = self.buf(rows, 3 * cc)
+                self.gemm([(n.ptr, cc, cc, 1)], 1, 1, rows, eng.qkv(ab), 3 * cc, qkv.ptr, 3 * cc)
+                self.attention(qkv.ptr, qkv.ptr + 2 * cc, qkv.ptr + 4 * cc, n.ptr, 3 * cc, 3 * cc, 3 * cc, cc,
+                               self.B * hw, heads, d, self.F, self.F, q_addr=addr, kv_addr=addr)
+                del qkv
+                hs2 = self._linear(n, ab + ".to_out.0", cc, residual=hs)
+                del n, hs
+                hs = hs2
+                k += 1
+            hs = self._ff(blk + ".ff_norm", blk + ".ff", hs)
+            i += 1
+        return self._linear(hs, t + ".proj_out", cc, residual=x)
+
+    def _conv3x3(self, key: str, x: Buf, cin: int, cout: int, lvl: int) -> Buf:
+        h, wd = self._geo(lvl)
+        w = self.eng.w
+        out = self.buf(self._rows(lvl), cout)
+        self.gemm([(x.ptr, cin, cin, 9)], self.B * self.F, h, wd, w.conv(key + ".weight"), cout, out.ptr, cout,
+                  bias_ptr=w.f32(key + ".bias").data_ptr())
+        return out
+
+    # -- whole forward ----------------------------------------------------------------------------------------
+    def _build(self) -> None:
+        eng, w, c = self.eng, self.eng.w, self.eng.cfg
+        B, F = self.B, self.F
+        boc = c["block_out_channels"]
+        nlev = len(boc)
+        rows0 = self._rows(0)
+        cin_pad = (c["in_channels"] + KPAD - 1) // KPAD * KPAD
+        # static I/O
+        self.x_in = self.static(rows0, cin_pad)
+        self.t_in = self.static(1, max(B, 4), torch.float32)
+        self.audio_in = self.static(B * F * self.S, eng.cross_k) if c["add_audio_layer"] else None
+        self.eps_out = self.static(rows0, c["out_channels"], torch.float32)
+        self.x_in.tensor().zero_()
+        if self.audio_in is not None:
+            self.audio_in.tensor().zero_()
+        n_gn = 2 * len(eng._resnet_names()) + len(eng._attn_names()) + 64
+        self.begin_stats(n_gn * B * F * 32 * 2)
+
+        # time embedding: Timesteps -> Linear -> SiLU -> Linear (unet.py:376-382), then every resnet's
+        # time_emb_proj(SiLU(emb)) + conv1.bias in one launch (resnet.py:190-205)
+        te0 = self.static(B, boc[0], torch.float32)
+        te1 = self.static(B, boc[0] * 4, torch.float32)
+        emb = self.static(B, boc[0] * 4, torch.float32)
+        self.tproj = self.static(B, eng.tproj_total, torch.float32)
+        assert c["flip_sin_to_cos"] and c["freq_shift"] == 0
+        self.call("ls_timestep_embedding", self.t_in.ptr, B, boc[0], te0.ptr)
+        self.call("ls_small_linear", te0.ptr, B, boc[0], w.t["te1.w"].data_ptr(),
+                  w.f32("time_embedding.linear_1.bias").data_ptr(), None, boc[0] * 4, 0, 1, te1.ptr)
+        self.call("ls_small_linear", te1.ptr, B, boc[0] * 4, w.t["te2.w"].data_ptr(),
+                  w.f32("time_embedding.linear_2.bias").data_ptr(), None, boc[0] * 4, 0, 0, emb.ptr)
+        self.call("ls_small_linear", emb.ptr, B, boc[0] * 4, w.t["tproj.w"].data_ptr(), w.t["tproj.b"].data_ptr(),
+                  w.t["tproj.add"].data_ptr(), eng.tproj_total, 1, 0, self.tproj.ptr)
+
+        # audio K/V for all 16 cross-attention layers: one GEMM (depends only on the audio => the pipeline runs
+        # this sub-plan once per segment, see UNetPlan.kv_ops)
+        self.audio_kv = None
+        n_before = len(self.ops)
+        if self.audio_in is not None:
+            self.audio_kv = self.static(B * F * self.S, eng.kv_total)
+            self.gemm([(self.audio_in.ptr, eng.cross_k, eng.cross_k, 1)], 1, 1, B * F * self.S, w.t["kv.w"],
+                      eng.kv_total, self.audio_kv.ptr, eng.kv_total)
+        self.kv_ops = (n_before, len(self.ops))
+
+        # conv_in (unet.py:395)
+        x = self.buf(rows0, boc[0])
+        self.gemm([(self.x_in.ptr, cin_pad, cin_pad, 9)], B * F, self.H, self.W,
+                  w.conv("conv_in.weight"), boc[0], x.ptr, boc[0], bias_ptr=w.f32("conv_in.bias").data_ptr())
+        skips: List[Tuple[Buf, int]] = [(x, boc[0])]
+        self._tap("conv_in", x, 0)
+        ch = boc[0]
+        for i, typ in enumerate(c["down_block_types"]):
+            p = f"down_blocks.{i}"
+            cout = boc[i]
+            for j in range(c["layers_per_block"]):
+                x = self._resnet(f"{p}.resnets.{j}", [(x, ch)], cout, i)
+                ch = cout
+                if typ == "CrossAttnDownBlock3D":
+                    x = self._transformer(f"{p}.attentions.{j}", x, ch, i)
+                if w.has(f"{p}.motion_modules.{j}.temporal_transformer.norm.weight"):
+                    x = self._motion(f"{p}.motion_modules.{j}", x, ch, i)
+                self._tap(f"{p}.{j}", x, i)
+                skips.append((x, ch))
+            if i != nlev - 1:
+                # Downsample3D (resnet.py:93-101): 3x3 stride 2 pad 1 via explicit im2col
+                h, wd = self._geo(i)
+                cols = self.buf(self._rows(i + 1), 9 * ch)
+                self.call("ls_im2col_s2", x.ptr, B * F, h, wd, ch, cols.ptr)
+                key = f"{p}.downsamplers.0.conv"
+                y = self.buf(self._rows(i + 1), ch)
+                self.gemm([(cols.ptr, 9 * ch, 9 * ch, 1)], 1, 1, self._rows(i + 1), w.conv(key + ".weight"), ch, y.ptr,
+                          ch, bias_ptr=w.f32(key + ".bias").data_ptr())
+                del cols
+                x = y
+                skips.append((x, ch))
+        lvl = nlev - 1
+        # mid (unet_blocks.py:247-260)
+        x = self._resnet("mid_block.resnets.0", [(x, ch)], ch, lvl)
+        x = self._transformer("mid_block.attentions.0", x, ch, lvl)
+        if w.has("mid_block.motion_modules.0.temporal_transformer.norm.weight"):
+            x = self._motion("mid_block.motion_modules.0", x, ch, lvl)
+        x = self._resnet("mid_block.resnets.1", [(x, ch)], ch, lvl)
+        self._tap("mid", x, lvl)
+        rev = list(reversed(boc))
+        for i, typ in enumerate(c["up_block_types"]):
+            p = f"up_blocks.{i}"
+            cout = rev[i]
+            lvl = nlev - 1 - i
+            for j in range(c["layers_per_block"] + 1):
+                skip, sch = skips.pop()
+                x = self._resnet(f"{p}.resnets.{j}", [(x, ch), (skip, sch)], cout, lvl)
+                del skip
+                ch = cout
+                if typ == "CrossAttnUpBlock3D":
+                    x = self._transformer(f"{p}.attentions.{j}", x, ch, lvl)
+                if w.has(f"{p}.motion_modules.{j}.temporal_transformer.norm.weight"):
+                    x = self._motion(f"{p}.motion_modules.{j}", x, ch, lvl)
+                self._tap(f"{p}.{j}", x, lvl)
+            if i != nlev - 1:
+                # Upsample3D (resnet.py:47-75): nearest x2 on (h, w), then 3x3 conv
+                h, wd = self._geo(lvl)
+                up = self.buf(self._rows(lvl - 1), ch)
+                self.call("ls_upsample2x", x.ptr, B * F, h, wd, ch, up.ptr)
+                x = self._conv3x3(f"{p}.upsamplers.0.conv", up, ch, ch, lvl - 1)
+                del up
+        # conv_norm_out -> SiLU -> conv_out (unet.py:464-466)
+        y = self.buf(rows0, ch)
+        self.groupnorm(x.ptr, ch, 0, 0, rows0, F * self.H * self.W, c["norm_num_groups"], w.f32("conv_norm_out.weight"),
+                       w.f32("conv_norm_out.bias"), c["norm_eps"], True, y.ptr)
+        self.gemm([(y.ptr, ch, ch, 9)], B * F, self.H, self.W, w.conv("conv_out.weight"), c["out_channels"],
+                  self.eps_out.ptr, c["out_channels"], bias_ptr=w.f32("conv_out.bias").data_ptr(), flags=L.EPI_OUT_F32)
+        del x, y
+        assert not skips
+
+
+# ------------------------------------------------------------------------------------------------- VAE engine
+class VAEDecoderEngine:
+    """diffusers AutoencoderKL.decode for the sd-vae-ft-mse layout (lipsync_pipeline.py:145-149)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: dict = SD_VAE_FT_MSE_CONFIG, device="cuda"):
+        self.cfg = dict(cfg)
+        self.device = torch.device(device)
+        self.w = _Weights(state_dict, self.device)
+        self.plans: Dict[Tuple[int, int, int], "VAEPlan"] = {}
+
+    def conv_sc(self, r: str, cin: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        name = r + "#c2sc"
+        w = self.w
+        if name + ".w" not in w.t:
+            w2 = pack_conv3x3(w.raw(r + ".conv2.weight"))
+            ws = pack_1x1(w.raw(r + ".conv_shortcut.weight"))
+            w.put(name + ".w", torch.cat([w2, ws], dim=1))
+            w.put(name + ".b", w.raw(r + ".conv2.bias") + w.raw(r + ".conv_shortcut.bias"))
+        return w.t[name + ".w"], w.t[name + ".b"]
+
+    def plan(self, nimg: int, h: int, w: int) -> "VAEPlan":
+        key = (nimg, h, w)
+        if key not in self.plans:
+            self.plans[key] = VAEPlan(self, nimg, h, w)
+        return self.plans[key]
+
+
+class VAEPlan(Plan):
+    def __init__(self, eng: VAEDecoderEngine, nimg: int, h: int, w: int):
+        super().__init__(eng.device)
+        self.eng, self.nimg, self.h, self.w = eng, nimg, h, w
+        self._build()
+
+    def _gn(self, key: str, x: Buf, cc: int, hw: int, silu: bool) -> Buf:
+        w = self.eng.w
+        y = self.buf(x.rows, cc)
+        self.groupnorm(x.ptr, cc, 0, 0, x.rows, hw, self.eng.cfg["norm_num_groups"], w.f32(key + ".weight"),
+                       w.f32(key + ".bias"), 1e-6, silu, y.ptr)
+        return y
+
+    def _conv(self, key: str, x: Buf, cin: int, cout: int, h: int, wd: int) -> Buf:
+        w = self.eng.w
+        out = self.buf(x.rows, cout)
+        self.gemm([(x.ptr, cin, cin, 9)], self.nimg, h, wd, w.conv(key + ".weight"), cout, out.ptr, cout,
+                  bias_ptr=w.f32(key + ".bias").data_ptr())
+        return out
+
+    def _resnet(self, r: str, x: Buf, cin: int, cout: int, h: int, wd: int) -> Buf:
+        """diffusers ResnetBlock2D without time embedding: GN -> SiLU -> 3x3 -> GN -> SiLU -> 3x3 (+1x1 shortcut)"""
+        w = self.eng.w
+        y1 = self._gn(r + ".norm1", x, cin, h * wd, True)
+        h1 = self._conv(r + ".conv1", y1, cin, cout, h, wd)
+        del y1
+        y2 = self._gn(r + ".norm2", h1, cout, h * wd, True)
+        del h1
+        out = self.buf(x.rows, cout)
+        if w.has(r + ".conv_shortcut.weight"):
+            wp, bp = self.eng.conv_sc(r, cin)
+            self.gemm([(y2.ptr, cout, cout, 9), (x.ptr, cin, cin, 1)], self.nimg, h, wd, wp, cout, out.ptr, cout,
+                      bias_ptr=bp.data_ptr())
+        else:
+            self.gemm([(y2.ptr, cout, cout, 9)], self.nimg, h, wd, w.conv(r + ".conv2.weight"), cout, out.ptr, cout,
+                      bias_ptr=w.f32(r + ".conv2.bias").data_ptr(), residual_ptr=x.ptr, ldr=cout)
+        return out
+
+    def _lin(self, x: Buf, key: str, n: int, residual: Optional[Buf] = None) -> Buf:
+        w = self.eng.w
+        out = self.buf(x.rows, n)
+        self.gemm([(x.ptr, x.cols, x.cols, 1)], 1, 1, x.rows, w.lin(key + ".weight"), n, out.ptr, n,
+                  bias_ptr=w.f32(key + ".bias").data_ptr(), residual_ptr=residual.ptr if residual is not None else 0,
+                  ldr=n)
+        return out
+
+    def _mid_attention(self, a: str, x: Buf, cc: int, h: int, wd: int) -> Buf:
+        """diffusers Attention in UNetMidBlock2D: GN(32, eps 1e-6) -> q,k,v Linear(with bias) -> 1 head, d = C ->
+        softmax(q k^T / sqrt(C)) v -> Linear + residual"""
+        hw = h * wd
+        n = self._gn(a + ".group_norm", x, cc, hw, False)
+        q, k, v = self._lin(n, a + ".to_q", cc), self._lin(n, a + ".to_k", cc), self._lin(n, a + ".to_v", cc)
+        del n
+        sc = self.buf(x.rows, hw, torch.float32)
+        self.gemm([(q.ptr, cc, cc, 1)], self.nimg, 1, hw, None, hw, sc.ptr, hw, flags=L.EPI_OUT_F32,
+                  b_batch_stride=hw * cc, b_ptr=k.ptr)
+        del q, k
+        pr = self.buf(x.rows, hw)
+        self.call("ls_softmax_rows", sc.ptr, x.rows, hw, float(cc) ** -0.5, pr.ptr)
+        del sc
+        vt = self.buf(self.nimg * cc, hw)
+        self.call("ls_transpose", v.ptr, self.nimg, hw, cc, vt.ptr)
+        del v
+        o = self.buf(x.rows, cc)
+        self.gemm([(pr.ptr, hw, hw, 1)], self.nimg, 1, hw, None, cc, o.ptr, cc, b_batch_stride=cc * hw, b_ptr=vt.ptr)
+        del pr, vt
+        return self._lin(o, a + ".to_out.0", cc, residual=x)
+
+    def _build(self) -> None:
+        eng, w, c = self.eng, self.eng.w, self.eng.cfg
+        nimg, h, wd = self.nimg, self.h, self.w
+        boc = list(c["block_out_channels"])
+        lat = c["latent_channels"]
+        rows = nimg * h * wd
+        self.z_in = self.static(rows, KPAD)  # z / scaling_factor + shift, channels-last, zero padded to 64
+        self.z_in.tensor().zero_()
+        nup = len(boc)
+        self.begin_stats((3 * 2 * nup + 12) * nimg * 32 * 2)
+        # post_quant_conv (1x1, 4 -> 4) into a zero-padded 64-channel buffer
+        pq = self.static(rows, KPAD)
+        pq.tensor().zero_()
+        self.gemm([(self.z_in.ptr, KPAD, KPAD, 1)], 1, 1, rows, w.lin("post_quant_conv.weight"), lat, pq.ptr, KPAD,
+                  bias_ptr=w.f32("post_quant_conv.bias").data_ptr())
+        top = boc[-1]
+        x = self._conv("decoder.conv_in", pq, KPAD, top, h, wd)
+        x = self._resnet("decoder.mid_block.resnets.0", x, top, top, h, wd)
+        x = self._mid_attention("decoder.mid_block.attentions.0", x, top, h, wd)
+        x = self._resnet("decoder.mid_block.resnets.1", x, top, top, h, wd)
+        rev = list(reversed(boc))
+        ch = top
+        for i in range(nup):
+            cout = rev[i]
+            for j in range(c["layers_per_block"] + 1):
+                x = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x, ch, cout, h, wd)
+                ch = cout
+            if i != nup - 1:
+                up = self.buf(nimg * 4 * h * wd, ch)
+                self.call("ls_upsample2x", x.ptr, nimg, h, wd, ch, up.ptr)
+                h, wd = 2 * h, 2 * wd
+                x = self._conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", up, ch, ch, h, wd)
+                del up
+        y = self._gn("decoder.conv_norm_out", x, ch, h * wd, True)
+        self.out_h, self.out_w = h, wd
+        nout = c["out_channels"]
+        self.ld_out = 4
+        self.dec_out = self.static(nimg * h * wd, self.ld_out, torch.float32)
+        self.gemm([(y.ptr, ch, ch, 9)], nimg, h, wd, w.conv("decoder.conv_out.weight"), nout, self.dec_out.ptr,
+                  self.ld_out, bias_ptr=w.f32("decoder.conv_out.bias").data_ptr(), flags=L.EPI_OUT_F32)
+        del x, y

@@ -1,0 +1,383 @@
+"""Drop-in for the reference's `LipsyncPipeline` (latentsync/pipelines/lipsync_pipeline.py:46-604).
+
+Only the hot span is re-implemented: the segment loop (:500-575) - CFG duplicate + 13-channel concat,
+UNet forward, CFG combine, DDIM update (x num_inference_steps), VAE decode and paste-back - as `denoise_segment`,
+`decode_latents`, `paste_surrounding_pixels_back` and `run_segments`.  `__call__` keeps the reference signature and
+delegates the untouched pre/post stages (video decode, face alignment, Whisper features, affine restore, ffmpeg mux)
+to the reference's own `latentsync.*` utilities, which must be importable for that entry point.
+
+Multi-GPU (new capability): segments are independent, so `run_segments` takes a contiguous shard of
+the clip per rank and `gather_frames` collects decoded frames on rank 0 with one NCCL gather over NVLink.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Union
+
+import torch
+
+from . import _lib as L
+
+
+def shard_segments(num_segments: int, rank: int, world_size: int) -> range:
+    """contiguous block partition of segment indices (sizes differ by at most one)"""
+    base, rem = divmod(num_segments, world_size)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+class LipsyncPipeline:
+    def __init__(self, vae, audio_encoder, denoising_unet, scheduler):
+        self.vae = vae
+        self.audio_encoder = audio_encoder
+        self.denoising_unet = denoising_unet
+        self.scheduler = scheduler
+        boc = getattr(vae.config, "block_out_channels", (128, 256, 512, 512))
+        self.vae_scale_factor = 2 ** (len(boc) - 1)
+        self.device = torch.device("cpu")
+        self.image_processor = None
+        self._progress_bar_config = {}
+
+    def to(self, device):
+        self.device = torch.device(device)
+        self.denoising_unet = self.denoising_unet.to(device)
+        if hasattr(self.vae, "to"):
+            self.vae = self.vae.to(device)
+        return self
+
+    @property
+    def _execution_device(self):
+        return self.device
+
+    def set_progress_bar_config(self, **kwargs):
+        self._progress_bar_config.update(kwargs)
+
+    def check_inputs(self, height, width, callback_steps):
+        """lipsync_pipeline.py:168-180"""
+        assert height == width, "Height and width must be equal"
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if (callback_steps is None) or (not isinstance(callback_steps, int) or callback_steps <= 0):
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type"
+                             f" {type(callback_steps)}.")
+
+    def prepare_latents(self, batch_size, num_frames, num_channels_latents, height, width, dtype, device, generator):
+        """lipsync_pipeline.py:182-196: ONE (b,4,1,h,w) draw repeated over all frames of the clip"""
+        shape = (batch_size, num_channels_latents, 1, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        latents = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+        latents = latents.repeat(1, 1, num_frames, 1, 1)
+        return latents * self.scheduler.init_noise_sigma
+
+    # ------------------------------------------------------------------------------------------------ hot loop
+    @torch.no_grad()
+    def denoise_segment(self, latents: torch.Tensor, audio_embeds: Optional[torch.Tensor], mask_latents: torch.Tensor,
+                        masked_image_latents: torch.Tensor, ref_latents: torch.Tensor, num_inference_steps: int = 20,
+                        guidance_scale: float = 1.5, callback: Optional[Callable] = None, callback_steps: int = 1,
+                        trace: Optional[Dict[str, list]] = None, teacher_latents: Optional[Sequence] = None):
+        """Denoising loop of one segment (lipsync_pipeline.py:537-568).
+
+        latents (1,4,f,h,w); audio_embeds (f,S,D) = the conditional half only (the uncond half is zeros, :503-507);
+        mask_latents (1|2,1,f,h,w), masked_image_latents / ref_latents (1|2,4,f,h,w) - if the CFG-duplicated (2,...)
+        form of prepare_mask_latents (:308-311) is passed, the first half is used (both halves are identical).
+        Returns the final latents (1,4,f,h,w) fp32.  `trace`, if a dict, receives per-step "noise_pred" (guided) and
+        "latents" tensors; `teacher_latents[j]`, if given, replaces the loop state before step j (per-step parity)."""
+        unet, sch = self.denoising_unet, self.scheduler
+        dev = unet.device
+        do_cfg = guidance_scale > 1.0
+        nb = 2 if do_cfg else 1
+        lat = latents.to(dev, torch.float32).contiguous().clone()
+        assert lat.shape[0] == 1 and lat.shape[1] == 4, "one segment per call (batch_size is 1, lipsync_pipeline.py:392)"
+        _, _, F, h, w = lat.shape
+        mask = mask_latents[:1].to(dev, torch.float32).contiguous()
+        masked = masked_image_latents[:1].to(dev, torch.float32).contiguous()
+        ref = ref_latents[:1].to(dev, torch.float32).contiguous()
+        S = 0
+        if unet.add_audio_layer:
+            assert audio_embeds is not None
+            S = audio_embeds.shape[-2]
+        plan = unet.plan(nb, F, h, w, S)
+        if S:
+            a = audio_embeds.to(dev, torch.float16).reshape(F * S, -1)
+            buf = plan.audio_in.tensor()
+            buf.zero_()  # uncond half: null audio embeds (:505-507)
+            buf[(nb - 1) * F * S:, : a.shape[1]].copy_(a)
+        sch.set_timesteps(num_inference_steps)
+        timesteps = sch._host_timesteps
+        lib = L.lib()
+        eps_dbg = torch.empty_like(lat) if trace is not None else None
+        t_view = plan.t_in.tensor().view(-1)
+        for j, t in enumerate(timesteps):
+            if teacher_latents is not None:
+                lat.copy_(teacher_latents[j].to(dev, torch.float32))
+            st = torch.cuda.current_stream().cuda_stream
+            # cat([latents]*2) ; cat([x, mask, masked, ref], dim=1)  -> channels-last fp16 UNet input (:542-549)
+            L._check(lib.ls_concat13(lat.data_ptr(), mask.data_ptr(), masked.data_ptr(), ref.data_ptr(), nb, F, h * w,
+                                     plan.x_in.ptr, st), "ls_concat13")
+            t_view.fill_(float(t))
+            plan.replay()  # noise_pred (:552-554)
+            a_t, a_p = sch.step_coefficients(t)
+            # CFG combine (:557-559) + DDIM step (:562) in one pass, latents updated in place
+            L._check(lib.ls_cfg_ddim_step(plan.eps_out.ptr, plan.eps_out.cols, nb, F, h * w, float(guidance_scale), a_t,
+                                          a_p, lat.data_ptr(), eps_dbg.data_ptr() if eps_dbg is not None else None, st),
+                     "ls_cfg_ddim_step")
+            if trace is not None:
+                trace.setdefault("noise_pred", []).append(eps_dbg.clone())
+                trace.setdefault("latents", []).append(lat.clone())
+            if callback is not None and j % callback_steps == 0:
+                callback(j, t, lat)
+        return lat
+
+    @torch.no_grad()
+    def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
+        """lipsync_pipeline.py:145-149: z / scaling_factor + shift -> "(b f) c h w" -> vae.decode(...).sample"""
+        sf, sh = self.vae.config.scaling_factor, self.vae.config.shift_factor
+        b, c, f, h, w = latents.shape
+        if hasattr(self.vae, "plan") and sh == 0.0 and b == 1 and latents.dtype == torch.float32 and latents.is_cuda:
+            plan = self.vae.plan(f, h, w)
+            st = torch.cuda.current_stream().cuda_stream
+            lib = L.lib()
+            lat = latents.contiguous()
+            L._check(lib.ls_ncfhw_to_cl(lat.data_ptr(), 1, c, f, h * w, plan.z_in.cols, 1.0 / sf, plan.z_in.ptr, st),
+                     "ls_ncfhw_to_cl")
+            plan.replay()
+            H, W = plan.out_h, plan.out_w
+            out = torch.empty(f, 3, H, W, dtype=torch.float32, device=latents.device)
+            L._check(lib.ls_cl_to_ncfhw(plan.dec_out.ptr, plan.ld_out, f, 3, 1, H * W, out.data_ptr(), st),
+                     "ls_cl_to_ncfhw")
+            return out
+        z = latents / sf + sh
+        z = z.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+        return self.vae.decode(z).sample
+
+    @torch.no_grad()
+    def decode_and_paste(self, latents: torch.Tensor, ref_pixel_values: torch.Tensor, masks: torch.Tensor):
+        """decode_latents + paste_surrounding_pixels_back(decoded, ref, 1 - masks) (:571-574) without materialising the
+        decoded frames in NCHW: out = decoded * (1 - m) + ref * m, m = `masks` (1 = keep the original pixel)."""
+        sf = self.vae.config.scaling_factor
+        _, c, f, h, w = latents.shape
+        plan = self.vae.plan(f, h, w)
+        st = torch.cuda.current_stream().cuda_stream
+        lib = L.lib()
+        lat = latents.to(torch.float32).contiguous()
+        dev = lat.device
+        L._check(lib.ls_ncfhw_to_cl(lat.data_ptr(), 1, c, f, h * w, plan.z_in.cols, 1.0 / sf, plan.z_in.ptr, st),
+                 "ls_ncfhw_to_cl")
+        plan.replay()
+        H, W = plan.out_h, plan.out_w
+        ref = ref_pixel_values.to(dev, torch.float32).contiguous()
+        m = masks.to(dev, torch.float32).contiguous()
+        out = torch.empty(f, 3, H, W, dtype=torch.float32, device=dev)
+        L._check(lib.ls_paste_back(plan.dec_out.ptr, plan.ld_out, ref.data_ptr(), m.data_ptr(), f, H * W,
+                                   out.data_ptr(), st), "ls_paste_back")
+        return out
+
+    @staticmethod
+    def paste_surrounding_pixels_back(decoded_latents, pixel_values, masks, device, weight_dtype):
+        """lipsync_pipeline.py:328-333 (called with `1 - masks` at :572-574): decoded * masks + pixel * (1 - masks)"""
+        d = decoded_latents.to(device, torch.float32).contiguous()
+        n, c, H, W = d.shape
+        ref = pixel_values.to(device, torch.float32).contiguous()
+        keep = (1 - masks.to(device, torch.float32)).contiguous()  # kernel takes m with out = d*(1-m) + ref*m
+        out = torch.empty_like(d)
+        d_cl = d.permute(0, 2, 3, 1).reshape(n * H * W, c).contiguous()
+        L.paste_back(d_cl, c, ref, keep, n, H * W, out)
+        return out.to(weight_dtype)
+
+    @torch.no_grad()
+    def run_segments(self, segments: Sequence[Dict[str, torch.Tensor]], num_inference_steps: int = 20,
+                     guidance_scale: float = 1.5) -> List[torch.Tensor]:
+        """HOT LOOP 1 (lipsync_pipeline.py:500-575) over already-prepared segment inputs (keys as produced by
+        synthetic.segment_inputs / the reference's prepare_* helpers).  Returns one (f,3,H,W) fp32 tensor each."""
+        frames = []
+        for seg in segments:
+            lat = self.denoise_segment(seg["latents"], seg.get("audio_embeds"), seg["mask_latents"],
+                                       seg["masked_image_latents"], seg["ref_latents"], num_inference_steps,
+                                       guidance_scale)
+            frames.append(self.decode_and_paste(lat, seg["ref_pixel_values"], seg["masks"]))
+        return frames
+
+    @staticmethod
+    def gather_frames(frames: torch.Tensor, seg_counts: Sequence[int], dst: int = 0) -> Optional[torch.Tensor]:
+        """NCCL gather of the per-rank decoded frames to `dst` (ranks hold contiguous blocks of `seg_counts[r]`
+        segments).  frames: (n_local_frames, 3, H, W).  Returns the whole clip on `dst`, None elsewhere."""
+        import torch.distributed as dist
+
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+            return frames
+        world, rank = dist.get_world_size(), dist.get_rank()
+        per_seg = frames.shape[0] // max(seg_counts[rank], 1) if seg_counts[rank] else 0
+        per_seg = torch.tensor([per_seg], device=frames.device)
+        dist.all_reduce(per_seg, op=dist.ReduceOp.MAX)
+        f = int(per_seg.item())
+        shape = tuple(frames.shape[1:])
+        outs = None
+        if rank == dst:
+            outs = [torch.empty((seg_counts[r] * f,) + shape, dtype=frames.dtype, device=frames.device)
+                    for r in range(world)]
+        # ragged gather as point-to-point sends: the payload is ~6 MB per segment, NVLink-trivial
+        if rank == dst:
+            reqs = []
+            for r in range(world):
+                if r == dst:
+                    outs[r].copy_(frames)
+                elif seg_counts[r] > 0:
+                    reqs.append(dist.irecv(outs[r], src=r))
+            for q in reqs:
+                q.wait()
+            return torch.cat(outs, dim=0)
+        if seg_counts[rank] > 0:
+            dist.send(frames.contiguous(), dst=dst)
+        return None
+
+    # ------------------------------------------------------------------------------------------- full entry point
+    @torch.no_grad()
+    def __call__(
+        self,
+        video_path: str,
+        audio_path: str,
+        video_out_path: str,
+        video_mask_path: str = None,
+        num_frames: int = 16,
+        video_fps: int = 25,
+        audio_sample_rate: int = 16000,
+        height: Optional[int] = None,
+        width: Optional[int] = None,
+        num_inference_steps: int = 20,
+        guidance_scale: float = 1.5,
+        weight_dtype: Optional[torch.dtype] = torch.float16,
+        eta: float = 0.0,
+        mask: str = "fix_mask",
+        mask_image_path: str = "latentsync/utils/mask.png",
+        generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+        callback: Optional[Callable[[int, int, torch.FloatTensor], None]] = None,
+        callback_steps: Optional[int] = 1,
+        data_path: Optional[str] = None,
+        start_from_backwards: Optional[bool] = False,
+        force_video_length: Optional[bool] = False,
+        use_darken: Optional[bool] = False,
+        brightness_factor: Optional[float] = 1.0,
+        **kwargs,
+    ):
+        """Same signature and side effect (an mp4 at `video_out_path`) as lipsync_pipeline.py:361-604.  Stages outside
+        the hot path run the reference's own code, imported from its `latentsync` package."""
+        try:  # untouched stages
+            import numpy as np
+            import soundfile as sf
+            from latentsync.pipelines.affine_transform_video import affine_transform_video
+            from latentsync.utils.image_processor import ImageProcessor, load_fixed_mask
+            from latentsync.utils.repeat import (pad_whisper_chunks, pad_whisper_chunks_end,
+                                                 pad_whisper_chunks_to_target, repeat_to_length, truncate_to_length)
+            from latentsync.utils.util import read_audio, read_video, write_video
+        except ImportError as e:
+            raise ImportError("LipsyncPipeline.__call__ needs the reference's untouched pre/post-processing package "
+                              "`latentsync` (face alignment, Whisper front end, ffmpeg I/O) on sys.path; the "
+                              f"accelerated span is available as run_segments(): {e}") from e
+        import os
+        import shutil
+        import subprocess
+
+        if eta != 0.0:
+            raise NotImplementedError("eta > 0 is not supported (the reference always passes eta=0.0)")
+        is_train = self.denoising_unet.training
+        self.denoising_unet.eval()
+        device = self._execution_device
+        mask_image = load_fixed_mask(height, mask_image_path)
+        self.image_processor = ImageProcessor(height, mask=mask, device="cuda", mask_image=mask_image)
+        if data_path:
+            loaded = torch.load(data_path)
+            faces, boxes, affine_matrices = loaded["faces"], loaded["boxes"], loaded["affine_matrices"]
+            original_video_frames = read_video(video_path, use_decord=False)
+        else:
+            faces, original_video_frames, boxes, affine_matrices = affine_transform_video(self.image_processor,
+                                                                                          video_path)
+        height = height or self.denoising_unet.config.sample_size * self.vae_scale_factor
+        width = width or self.denoising_unet.config.sample_size * self.vae_scale_factor
+        self.check_inputs(height, width, callback_steps)
+        self.video_fps = video_fps
+        do_cfg = guidance_scale > 1.0
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        audio_samples = read_audio(audio_path)
+        whisper_feature = self.audio_encoder.audio2feat(audio_path)
+        whisper_chunks = self.audio_encoder.feature2chunks(feature_array=whisper_feature, fps=video_fps)
+        padding_duration = 0
+        if not force_video_length:
+            if start_from_backwards:
+                whisper_chunks, audio_samples, padding_duration, _ = pad_whisper_chunks(
+                    whisper_chunks, whisper_chunks[0].shape, audio_samples, audio_sample_rate, self.video_fps)
+            else:
+                whisper_chunks, audio_samples, padding_duration = pad_whisper_chunks_end(
+                    whisper_chunks, whisper_chunks[0].shape, audio_samples, audio_sample_rate, self.video_fps)
+            if len(whisper_chunks) > len(faces):
+                n = len(whisper_chunks)
+                faces, boxes = repeat_to_length(faces, n), repeat_to_length(boxes, n)
+                original_video_frames = repeat_to_length(original_video_frames, n)
+                affine_matrices = repeat_to_length(affine_matrices, n)
+        else:
+            whisper_chunks, audio_samples, padding_duration = pad_whisper_chunks_to_target(
+                whisper_chunks, whisper_chunks[0].shape, audio_samples, audio_sample_rate, len(faces), fps=self.video_fps)
+        if len(faces) != len(whisper_chunks) and start_from_backwards:
+            n = len(whisper_chunks)
+            faces, boxes = truncate_to_length(faces, n), truncate_to_length(boxes, n)
+            original_video_frames = truncate_to_length(original_video_frames, n)
+            affine_matrices = truncate_to_length(affine_matrices, n)
+
+        all_latents = self.prepare_latents(1, len(whisper_chunks), self.vae.config.latent_channels, height, width,
+                                           torch.float32, device, generator)
+        synced = []
+        for i in range(math.ceil(len(whisper_chunks) / num_frames)):
+            audio_embeds = None
+            if self.denoising_unet.add_audio_layer:
+                audio_embeds = torch.stack(whisper_chunks[i * num_frames:(i + 1) * num_frames]).to(device)
+            inference_faces = faces[i * num_frames:(i + 1) * num_frames]
+            latents = all_latents[:, :, i * num_frames:(i + 1) * num_frames]
+            ref_px, masked_px, masks = self.image_processor.prepare_masks_and_masked_images(inference_faces,
+                                                                                            affine_transform=False)
+            # VAE *encode* of masked/reference frames is upstream of the accelerated span
+            m = torch.nn.functional.interpolate(masks, size=(height // self.vae_scale_factor,
+                                                             width // self.vae_scale_factor))
+            sfac, shf = self.vae.config.scaling_factor, self.vae.config.shift_factor
+            enc = lambda x: (self.vae.encode(x.to(device, weight_dtype)).latent_dist.sample(generator=generator)
+                             - shf) * sfac
+            masked_lat = enc(masked_px).permute(1, 0, 2, 3).unsqueeze(0)
+            ref_lat = enc(ref_px).permute(1, 0, 2, 3).unsqueeze(0)
+            mask_lat = m.permute(1, 0, 2, 3).unsqueeze(0)
+            lat = self.denoise_segment(latents, audio_embeds, mask_lat, masked_lat, ref_lat, num_inference_steps,
+                                       guidance_scale if do_cfg else 1.0, callback, callback_steps)
+            synced.append(self.decode_and_paste(lat, ref_px, masks).to(weight_dtype))
+        self.image_processor_restore = self.image_processor.restorer
+        frames = self._restore_video(torch.cat(synced), original_video_frames, boxes, affine_matrices)
+        remain = int(frames.shape[0] / video_fps * audio_sample_rate)
+        audio_samples = audio_samples[:remain].cpu().numpy()
+        if is_train:
+            self.denoising_unet.train()
+        temp_dir = "temp"
+        if os.path.exists(temp_dir):
+            shutil.rmtree(temp_dir)
+        os.makedirs(temp_dir, exist_ok=True)
+        write_video(os.path.join(temp_dir, "video.mp4"), frames, fps=25, use_darken=use_darken,
+                    brightness_factor=brightness_factor)
+        sf.write(os.path.join(temp_dir, "audio.wav"), audio_samples, audio_sample_rate)
+        v, a = os.path.join(temp_dir, "video.mp4"), os.path.join(temp_dir, "audio.wav")
+        if start_from_backwards or force_video_length:
+            command = f"ffmpeg -y -loglevel error -nostdin -i {v} -i {a} -c:v libx264 -c:a aac -q:v 0 -q:a 0 {video_out_path}"
+        else:
+            command = (f"ffmpeg -y -loglevel error -nostdin -i {v} -i {a} -c:v libx264 -c:a aac -q:v 0 -q:a 0 -t "
+                       f"$(ffprobe -v error -show_entries format=duration -of default=noprint_wrappers=1:nokey=1 {v} | "
+                       f"awk '{{print $1-{padding_duration}}}') {video_out_path}")
+        subprocess.run(command, shell=True)
+
+    def _restore_video(self, faces, video_frames, boxes, affine_matrices):
+        """lipsync_pipeline.py:343-358 (untouched stage: per-frame resize -> uint8 -> cv2 inverse affine paste)"""
+        import numpy as np
+        import torchvision
+
+        video_frames = video_frames[: len(faces)]
+        out_frames = []
+        for index, face in enumerate(faces):
+            x1, y1, x2, y2 = boxes[index]
+            face = torchvision.transforms.functional.resize(face, size=(int(y2 - y1), int(x2 - x1)), antialias=True)
+            face = (face.permute(1, 2, 0) / 2 + 0.5).clamp(0, 1)
+            face = (face * 255).to(torch.uint8).cpu().numpy()
+            out_frames.append(self.image_processor.restorer.restore_img(video_frames[index], face,
+                                                                        affine_matrices[index]))
+        return np.stack(out_frames, axis=0)
