@@ -266,6 +266,10 @@ def main():
         tot = sum(ms for _, ms in vtable.values())
         for k, (n, ms) in sorted(vtable.items(), key=lambda kv: -kv[1][1]):
             print(f"vae   {k:20s} {n:4d} launches {ms:8.3f} ms {100 * ms / tot:5.1f} %", file=sys.stderr)
+        for name, pl in (("unet", uplan), ("vae", vplan)):
+            for kind in ("gemm", "attention"):
+                for d, n, ms, tf in pl.shape_table(kind):
+                    print(f"{name} {kind} x{n:3d} {ms:8.3f} ms {tf:7.1f} TF/s  {d}", file=sys.stderr)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

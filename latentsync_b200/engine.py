@@ -94,6 +94,7 @@ class Plan:
         self.stats: Optional[torch.Tensor] = None
         self.launches = 0
         self.kinds: List[str] = []  # one tag per recorded launch (bench.py times kernels by kind)
+        self.descs: List[str] = []
         self.op_flops: List[float] = []  # algorithmic FLOPs of each launch (2*M*N*K for GEMM/conv, 4*B*h*Sq*Sk*d for SDPA)
 
     # ---- buffers
@@ -121,10 +122,23 @@ class Plan:
             evs.append((a, b))
         torch.cuda.synchronize(self.device)
         out: Dict[str, Tuple[int, float]] = {}
-        for kind, (a, b) in zip(self.kinds, evs):
+        self.last_times = [a.elapsed_time(b) for a, b in evs]
+        for kind, ms1 in zip(self.kinds, self.last_times):
             n, ms = out.get(kind, (0, 0.0))
-            out[kind] = (n + 1, ms + a.elapsed_time(b))
+            out[kind] = (n + 1, ms + ms1)
         return out
+
+    def shape_table(self, kind: str = "gemm"):
+        """after run_timed(): [(desc, launches, total ms, TFLOP/s)] aggregated over identical launches"""
+        agg: Dict[str, List[float]] = {}
+        for k, d, f, ms in zip(self.kinds, self.descs, self.op_flops, self.last_times):
+            if k == kind:
+                e = agg.setdefault(d, [0, 0.0, 0.0])
+                e[0] += 1
+                e[1] += ms
+                e[2] += f
+        rows = [(d, int(n), ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0) for d, (n, ms, fl) in agg.items()]
+        return sorted(rows, key=lambda r: -r[2])
 
     def capture(self) -> None:
         """warm up eagerly (sets function attributes, validates every launch), then record the CUDA graph"""
@@ -147,10 +161,11 @@ class Plan:
             self.graph.replay()
 
     # ---- emitters (each records ONE launch)
-    def _emit(self, fn, kind: str = "other", flops: float = 0.0) -> None:
+    def _emit(self, fn, kind: str = "other", flops: float = 0.0, desc: str = "") -> None:
         self.ops.append(fn)
         self.kinds.append(kind)
         self.op_flops.append(flops)
+        self.descs.append(desc)
         self.launches += 1
 
     def flops(self, kind: Optional[str] = None) -> float:
@@ -180,7 +195,9 @@ class Plan:
         a.ldr = ldr
         a.out, a.ldo, a.flags, a.tile_n = out_ptr, ldo, flags, tile_n
         fn = self.lib.ls_gemm
-        self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_gemm"), "gemm", 2.0 * nimg * H * W * N * ktot)
+        taps = "+".join(f"{ch}x{tp}" for _, ch, _, tp in segs)
+        self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_gemm"), "gemm", 2.0 * nimg * H * W * N * ktot,
+                   f"M={nimg * H * W} N={N} K={ktot} img={nimg}x{H}x{W} segs={taps} flags={flags} batched={int(b_batch_stride != 0)}")
 
     def begin_stats(self, nfloats: int) -> None:
         """one fp32 arena for the (sum, sumsq) results of every GroupNorm of the plan"""
@@ -220,7 +237,7 @@ class Plan:
         a.scale = float(head_dim) ** -0.5
         fn = self.lib.ls_attention
         self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_attention"), "attention",
-                   4.0 * batch * heads * sq * skv * head_dim)
+                   4.0 * batch * heads * sq * skv * head_dim, f"batch={batch} heads={heads} d={head_dim} sq={sq} skv={skv}")
 
     def call(self, name: str, *args) -> None:
         """any other C-ABI function whose last parameter is the stream"""
