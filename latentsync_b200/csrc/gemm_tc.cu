@@ -2,7 +2,8 @@
 //
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp16 x fp16 -> fp32 in TMEM)
-//   warps 2..5  : epilogue       (tcgen05.ld -> bias / time-embedding / residual / GEGLU / SiLU -> global)
+//   warps 2..9  : epilogue       (tcgen05.ld -> bias / time-embedding / residual / GEGLU / SiLU -> 64B-swizzled smem
+//                                 slab -> TMA bulk store; two groups of 4 warps take alternate 32-column slabs)
 //
 // Two TMEM accumulators (double buffered) let the epilogue of tile i overlap the main loop of tile i+1.
 // The A operand of a 3x3 convolution is never materialised: for filter tap (dy, dx) the producer issues a 4-D
@@ -25,7 +26,9 @@ extern std::atomic<int64_t> g_launch_count;
 constexpr int BM = 128;
 constexpr int BK = 64;  // fp16 elements: one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
+constexpr int SLAB_BYTES = BM * 64;      // 128 rows x 32 fp16 columns, SWIZZLE_64B
+constexpr int STAGING_BYTES = 4 * SLAB_BYTES;  // 2 epilogue groups x 2 slabs (ping-pong)
 constexpr int MAX_STAGES = 8;
 
 struct GemmKParams {
@@ -49,6 +52,9 @@ struct GemmKParams {
   void* out;
   int ldo;
   int flags;
+  CUtensorMap mapOut;  // fp16 [M][N_out] output, box 32 columns x 128 rows, SWIZZLE_64B (valid iff tma_store)
+  int tma_store;
+  int64_t M;           // total output rows
 };
 
 __device__ __forceinline__ void decode_m_tile(const GemmKParams& p, int mt, int& x0, int& y0, int& i0) {
@@ -147,7 +153,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const int stages = p.stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * STAGE_BYTES);
+  uint8_t* staging = smem + stages * STAGE_BYTES;  // 1024-byte aligned (STAGE_BYTES % 1024 == 0)
+  float* bias_sm = reinterpret_cast<float*>(staging + STAGING_BYTES);  // 2 groups x 256 floats
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + 2048);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], GEMM_THREADS / 32 - 2);
     }
     fence_barrier_init();
   }
@@ -247,9 +255,155 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int group = (warp - 2) >> 2; // 0: even slabs, 1: odd slabs
+    const int r = q * 32 + lane;       // row of the tile == TMEM lane
+    const bool geglu = (p.flags & LS_EPI_GEGLU) != 0;
+    if (p.tma_store) {
+      // Latency-tolerant epilogue: the tile's bias row goes to smem and ALL residual fragments of the group's slabs
+      // are requested before waiting for the accumulator, so global-load latency hides behind the main loop.
+      const bool issuer = (warp == 2 + 4 * group) && lane == 0;
+      uint8_t* my_stage = staging + group * 2 * SLAB_BYTES;
+      float* my_bias = bias_sm + group * 256;
+      constexpr int NSLAB_MAX = (BN / 32 + 1) / 2;  // slabs per group
+      const int nslab = geglu ? BN / 64 : BN / 32;
+      const int n_out_total = geglu ? p.N / 2 : p.N;
+      const int gtid = (warp - 2 - 4 * group) * 32 + lane;  // 0..127 inside the group
+      uint32_t slab_count = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (lt >> 1) & 1u;
+        const int mt = tile / p.n_tiles;
+        const int nt = tile - mt * p.n_tiles;
+        int x0, y0, i0;
+        decode_m_tile(p, mt, x0, y0, i0);
+        const int64_t m0 = ((int64_t)i0 * p.H + y0) * p.W + x0;  // tile rows are contiguous (checked on the host)
+        const int64_t m = m0 + r;
+        const bool row_ok = m < p.M;
+        const int last_j = group + ((nslab - 1 - group) / 2) * 2;  // last slab this group handles
+        // (1) bias row of this tile -> smem (host guarantees one bias row per tile: bias_div % 128 == 0)
+        {
+          const float* brow = p.bias + (p.bias_div > 0 ? (m0 / p.bias_div) * (int64_t)p.bias_ld : 0) + nt * BN;
+          for (int c = gtid; c < BN; c += 128)
+            my_bias[c] = (p.bias != nullptr && nt * BN + c < p.N) ? __ldg(brow + c) : 0.f;
+        }
+        // (2) residual fragments of every slab this group owns
+        uint4 res[NSLAB_MAX][4];
+        if (p.residual != nullptr) {
+#pragma unroll
+          for (int s = 0; s < NSLAB_MAX; ++s) {
+            const int j = group + 2 * s;
+            const int ncol0 = nt * BN + j * 32;
+            if (j < nslab && row_ok && ncol0 + 32 <= n_out_total) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * (int64_t)p.ldr + ncol0);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) res[s][e] = __ldg(rp + e);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) res[s][e] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        }
+        named_bar_sync(1 + group, 128);  // bias row visible to the group
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
+        bool released = false;
+#pragma unroll
+        for (int s = 0; s < NSLAB_MAX; ++s) {
+          const int j = group + 2 * s;
+          if (j >= nslab) break;
+          const int ncol0 = geglu ? nt * (BN / 2) + j * 32 : nt * BN + j * 32;  // first output column of the slab
+          if (ncol0 >= n_out_total) break;  // this and all later slabs lie beyond N (uniform over the group)
+          uint32_t v[32];
+          float f[32];
+          tmem_ld_32x32(tbase + j * 32, v);
+          if (!geglu) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int e4 = 0; e4 < 8; ++e4) {
+                const float4 t = *reinterpret_cast<const float4*>(my_bias + j * 32 + e4 * 4);
+                f[e4 * 4] += t.x;
+                f[e4 * 4 + 1] += t.y;
+                f[e4 * 4 + 2] += t.z;
+                f[e4 * 4 + 3] += t.w;
+              }
+            }
+          } else {
+            uint32_t g[32];
+            tmem_ld_32x32(tbase + BN / 2 + j * 32, g);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float fv = __uint_as_float(v[e]) + my_bias[j * 32 + e];
+              const float fg = __uint_as_float(g[e]) + my_bias[BN / 2 + j * 32 + e];
+              f[e] = fv * gelu_erf_f(fg);
+            }
+          }
+          if (j == last_j) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            released = true;
+          }
+          if (p.residual != nullptr) {
+            if (ncol0 + 32 <= n_out_total) {
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&res[s][e4]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(h2[e]);
+                  f[e4 * 8 + e * 2] += t.x;
+                  f[e4 * 8 + e * 2 + 1] += t.y;
+                }
+              }
+            } else if (row_ok) {  // ragged last slab: scalar, in-bounds columns only
+              const __half* rr = p.residual + m * (int64_t)p.ldr + ncol0;
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (ncol0 + e < n_out_total) f[e] += __half2float(rr[e]);
+            }
+          }
+          if (p.flags & LS_EPI_SILU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = silu_f(f[e]);
+          }
+          // stage the slab: row r is 64 bytes, 16-byte chunk c lives at position c ^ ((r >> 1) & 3)  (SWIZZLE_64B)
+          uint8_t* slab = my_stage + (slab_count & 1u) * SLAB_BYTES;
+          ++slab_count;
+          const int sw = (r >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1]);
+            *reinterpret_cast<uint4*>(slab + r * 64 + ((c ^ sw) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          // every store issued before this slab has finished READING its smem => the other slab may be overwritten
+          // once the group passes the barrier below
+          if (issuer) bulk_wait_group_read<0>();
+          named_bar_sync(1 + group, 128);
+          if (issuer) {
+            tma_store_2d(&p.mapOut, slab, ncol0, (int)m0);
+            bulk_commit_group();
+          }
+        }
+        if (!released) {  // group had no slab inside N for this tile: still hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+      if (issuer) bulk_wait_group_read<0>();
+    } else if (group == 0) {
     const int ix = r % p.bw;
     const int iy = (r / p.bw) % p.bh;
     const int in = r / (p.bw * p.bh);
@@ -321,6 +475,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
       }
     }
+  } else {
+      // legacy direct-store path uses the first 4 epilogue warps only; the others just release the accumulators
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (lt >> 1) & 1u;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+    }
   }
 
   tc_fence_before();
@@ -381,7 +545,7 @@ static int pick_tile_n(int m_tiles, int N, int sms) {
 template <int BN>
 static int launch_gemm(const GemmKParams& p, int grid, cudaStream_t stream) {
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
-  const size_t smem = (size_t)p.stages * STAGE_BYTES + 1024 + 256;
+  const size_t smem = (size_t)p.stages * STAGE_BYTES + STAGING_BYTES + 2048 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -489,6 +653,27 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     LS_CHECK(r == CUDA_SUCCESS, "ls_gemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
 
+  // output path: smem-staged TMA bulk stores when the tile's 128 rows are contiguous output rows and the row pitch
+  // is 16-byte aligned; otherwise (fp32 output, ragged geometry, narrow ld) per-thread direct stores
+  const int64_t M = (int64_t)a->nimg * a->H * a->W;
+  p.M = M;
+  const int n_out = (a->flags & LS_EPI_GEGLU) ? a->N / 2 : a->N;
+  const bool rows_contig = (a->W < BM) || (a->W % BM == 0) || (a->H == 1 && a->nimg == 1);
+  p.tma_store = (!(a->flags & LS_EPI_OUT_F32) && (a->ldo % 8 == 0) && rows_contig && M < (1ll << 31) &&
+                 (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->bias_div == 0 || a->bias_div % BM == 0) &&
+                 (a->residual == nullptr || ((a->ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0)))
+                    ? 1
+                    : 0;
+  if (p.tma_store) {
+    cuuint64_t gdim[2] = {(cuuint64_t)n_out, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)a->ldo * 2};
+    cuuint32_t box[2] = {32, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&p.mapOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->out, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LS_CHECK(r == CUDA_SUCCESS, "ls_gemm: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+  }
   p.bias = a->bias;
   p.bias_div = a->bias_div;
   p.bias_ld = a->bias_ld > 0 ? a->bias_ld : a->N;
@@ -499,7 +684,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.flags = a->flags;
 
   const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
-  int stages = (227 * 1024 - 1024 - 256) / stage_bytes;
+  int stages = (227 * 1024 - 1024 - 256 - 2048 - STAGING_BYTES) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.num_kb && p.num_kb >= 2) stages = p.num_kb;
   if (stages < 2) stages = 2;
