@@ -75,7 +75,8 @@ typedef struct LsGemmArgs {
   void* out; /* fp16 (or fp32 with LS_EPI_OUT_F32) [M][ldo]; with LS_EPI_GEGLU N_out = N/2 */
   int32_t ldo;
   int32_t flags;
-  int32_t tile_n; /* 0 = auto; else one of 32, 64, 128, 160, 256 */
+  int32_t tile_n; /* 0 = auto (wave-quantisation cost model); else a multiple of 32 (64 with GEGLU) up to 256 */
+  int32_t cta_pair; /* 0 = auto; 1 = single-CTA 128 x tile_n tiles; 2 = CTA pairs (cta_group::2), 256 x tile_n tiles */
 } LsGemmArgs;
 
 int ls_gemm(const LsGemmArgs* args, void* stream);

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_C.so")
+_SO = os.path.join(_HERE, os.environ.get("LS_SO_NAME", "_C.so"))  # LS_SO_NAME: instrumented debug builds
 _CSRC = os.path.join(_HERE, "csrc")
 
 EPI_GEGLU = 1
@@ -45,6 +45,7 @@ class LsGemmArgs(C.Structure):
         ("ldo", C.c_int32),
         ("flags", C.c_int32),
         ("tile_n", C.c_int32),
+        ("cta_pair", C.c_int32),
     ]
 
 
@@ -183,6 +184,7 @@ def gemm(
     flags: int = 0,
     tile_n: int = 0,
     b_batch_stride: int = 0,
+    cta_pair: int = 0,
 ) -> None:
     a = LsGemmArgs()
     a.nseg = len(segs)
@@ -210,6 +212,7 @@ def gemm(
     a.ldo = ldo
     a.flags = flags
     a.tile_n = tile_n
+    a.cta_pair = cta_pair
     _check(lib().ls_gemm(C.byref(a), _stream()), "ls_gemm")
 
 

@@ -73,6 +73,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Polite wait for warps that are NOT on the critical path (epilogue warps waiting for an accumulator): back off with
+// nanosleep so their polling does not steal issue slots from the TMA-producer / MMA-issuer warps of the same SM
+// sub-partition (the warp arbiter favours them otherwise).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(spins < 8 ? 32 : 128);
+    if (++spins > (1u << 24)) {
+      printf("latentsync_b200: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // TMA tiled loads, completion signalled on an mbarrier (complete_tx::bytes).
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {

@@ -1,11 +1,24 @@
 // Persistent warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
 //
-//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp16 x fp16 -> fp32 in TMEM)
-//   warps 2..9  : epilogue       (tcgen05.ld -> bias / time-embedding / residual / GEGLU / SiLU -> 64B-swizzled smem
+//   warps 0..7  : epilogue       (tcgen05.ld -> bias / time-embedding / residual / GEGLU / SiLU -> 64B-swizzled smem
 //                                 slab -> TMA bulk store; two groups of 4 warps take alternate 32-column slabs)
+//   warp 8      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx), one lane
+//   warp 9      : TMEM allocator + tcgen05.mma issuer (fp16 x fp16 -> fp32 in TMEM), one lane
 //
 // Two TMEM accumulators (double buffered) let the epilogue of tile i overlap the main loop of tile i+1.
+//
+// What bounds the main loop (measured with in-kernel clock64 probes, profiles/r1_gemm_issue_loop.txt): not HBM, L2 or
+// shared memory but the two single-thread loops - one mbarrier round trip plus four MMA issues per 64-wide k-block
+// cost ~650 cycles in the first version against 512 cycles of tensor work at N = 256.  Hence:
+//   * both loops run on ONE lane of the two HIGHEST warp ids (the sub-partition arbiter prefers high warp ids and the
+//     epilogue warps poll with nanosleep back-off, so they cannot steal issue slots),
+//   * each iteration is one asm block that first probes the NEXT stage's mbarrier (try_wait) and only then issues the
+//     TMA loads / MMAs + commit of the current stage, so the probe's latency hides behind the issue work.
+//
+// CTA pairs (cta_group::2): a cluster of two CTAs computes a 256 x N tile; each CTA stages its own 128 rows of A and
+// HALF of the B rows, the leader's tcgen05.mma.cta_group::2 reads both halves.  Halves the B traffic per MMA.  The
+// tile width N (any multiple of 32 up to 256) and the pairing are chosen per launch by a cost model on the host.
+//
 // The A operand of a 3x3 convolution is never materialised: for filter tap (dy, dx) the producer issues a 4-D
 // TMA box load of the channels-last activation shifted by (dy, dx); out-of-bounds coordinates are zero-filled by
 // the TMA unit, which is exactly the conv's zero padding.  Extra K segments implement the ResnetBlock3D 1x1
@@ -18,6 +31,7 @@
 #include "../../include/latentsync_b200.h"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace ls {
 
@@ -27,13 +41,21 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // fp16 elements: one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int GEMM_THREADS = 320;
-constexpr int SLAB_BYTES = BM * 64;      // 128 rows x 32 fp16 columns, SWIZZLE_64B
-constexpr int STAGING_BYTES = 4 * SLAB_BYTES;  // 2 epilogue groups x 2 slabs (ping-pong)
 constexpr int MAX_STAGES = 8;
+constexpr int PRODUCER_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int SLAB_BYTES = BM * 64;            // 128 rows x 32 fp16 columns, SWIZZLE_64B
+constexpr int STAGING_BYTES = 4 * SLAB_BYTES;  // 2 epilogue groups x 2 slabs (ping-pong)
+constexpr int BIAS_BYTES = 2 * 256 * 4;        // 2 epilogue groups x 256 floats
+constexpr int ACC_COLS = 256;                  // TMEM columns per accumulator
+constexpr int TMEM_COLS = 512;                 // two accumulators: the whole TMEM (one CTA per SM anyway)
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address (-> pair leader)
 
 struct GemmKParams {
   CUtensorMap mapA[LS_GEMM_MAX_SEG];
   CUtensorMap mapB;
+  CUtensorMap mapOut;  // fp16 [M][N_out] output, box 32 columns x 128 rows, SWIZZLE_64B (valid iff tma_store)
   int nseg;
   int seg_taps[LS_GEMM_MAX_SEG];
   int seg_cblk[LS_GEMM_MAX_SEG];
@@ -42,6 +64,7 @@ struct GemmKParams {
   int tiles_x, tiles_y;
   int m_tiles, n_tiles, num_kb;
   int N;
+  int BN;  // tile width (multiple of 32, <= 256)
   int b_batched;
   int stages;
   const float* bias;
@@ -52,10 +75,168 @@ struct GemmKParams {
   void* out;
   int ldo;
   int flags;
-  CUtensorMap mapOut;  // fp16 [M][N_out] output, box 32 columns x 128 rows, SWIZZLE_64B (valid iff tma_store)
   int tma_store;
-  int64_t M;           // total output rows
+  int64_t M;  // total output rows
 };
+
+// ----------------------------------------------------------------------------------------- pair-mode PTX wrappers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void tmem_alloc_g(uint32_t* dst_smem, uint32_t ncols) {
+  if constexpr (CTAS == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void tmem_dealloc_g(uint32_t taddr, uint32_t ncols) {
+  if constexpr (CTAS == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this smem offset in every CTA of the pair
+template <int CTAS>
+__device__ __forceinline__ void umma_commit_g(uint64_t* bar) {
+  if constexpr (CTAS == 1) {
+    umma_commit(bar);
+  } else {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+  }
+}
+// arrive on the pair leader's copy of `bar` (for the leader itself this is its own barrier)
+template <int CTAS>
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  if constexpr (CTAS == 1) {
+    mbar_arrive(bar);
+  } else {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK)
+                 : "memory");
+  }
+}
+
+// One k-block of the MMA issuer as ONE asm block: probe the next stage's `full` barrier, issue the four K=16 MMAs of
+// this stage (smem descriptors advance by 32 bytes = +2 in the 16-byte-unit address field), commit to this stage's
+// `empty` barrier, and only then consume the probe result.  Returns 1 if the next stage has already landed.
+template <int CTAS>
+__device__ __forceinline__ uint32_t mma_kblock(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t empty_bar, uint32_t next_full_bar,
+                                               uint32_t next_parity) {
+  uint32_t ready;
+  if constexpr (CTAS == 1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P, ACC, T;\n"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%7], %8;\n"
+        "setp.ne.b32 ACC, %5, 0;\n"
+        "setp.eq.b32 T, %4, %4;\n"
+        "add.s64 a1, %2, 2;\n add.s64 b1, %3, 2;\n"
+        "add.s64 a2, %2, 4;\n add.s64 b2, %3, 4;\n"
+        "add.s64 a3, %2, 6;\n add.s64 b3, %3, 6;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, ACC;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %4, T;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %4, T;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %4, T;\n"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(empty_bar), "r"(next_full_bar),
+          "r"(next_parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred P, ACC, T;\n"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+        ".reg .b16 m;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%7], %8;\n"
+        "setp.ne.b32 ACC, %5, 0;\n"
+        "setp.eq.b32 T, %4, %4;\n"
+        "mov.b16 m, 3;\n"
+        "add.s64 a1, %2, 2;\n add.s64 b1, %3, 2;\n"
+        "add.s64 a2, %2, 4;\n add.s64 b2, %3, 4;\n"
+        "add.s64 a3, %2, 6;\n add.s64 b3, %3, 6;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %4, ACC;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %4, T;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a2, b2, %4, T;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a3, b3, %4, T;\n"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], m;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(empty_bar), "r"(next_full_bar),
+          "r"(next_parity)
+        : "memory");
+  }
+  return ready;
+}
+
+// One k-block of the TMA producer as ONE asm block: probe the next stage's `empty` barrier, arm this stage's `full`
+// barrier (pair leader only) and issue the A (4-D box) and B (3-D box) loads.  In pair mode the data lands in THIS
+// CTA's smem while the transaction bytes are counted on the LEADER's barrier (address with the CTA-rank bit cleared).
+template <int CTAS>
+__device__ __forceinline__ uint32_t produce_kblock(uint32_t sa, uint32_t sb, const CUtensorMap* mapA,
+                                                   const CUtensorMap* mapB, uint32_t full_bar, uint32_t tx_bytes,
+                                                   int a0, int a1, int a2, int a3, int b0, int b1, int b2,
+                                                   uint32_t next_empty_bar, uint32_t next_parity) {
+  uint32_t ready;
+  if constexpr (CTAS == 1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%14], %15;\n"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%5], %6;\n"
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%3, {%7, %8, %9, %10}], [%5];\n"
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4, {%11, %12, %13}], [%5];\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}"
+        : "=r"(ready)
+        : "r"(sa), "r"(sb), "l"(reinterpret_cast<uint64_t>(mapA)), "l"(reinterpret_cast<uint64_t>(mapB)),
+          "r"(full_bar), "r"(tx_bytes), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2),
+          "r"(next_empty_bar), "r"(next_parity)
+        : "memory");
+  } else {
+    // tx_bytes == 0 on the non-leader CTA: it only issues its loads
+    asm volatile(
+        "{\n"
+        ".reg .pred P, L;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%14], %15;\n"
+        "setp.ne.b32 L, %6, 0;\n"
+        "@L mbarrier.arrive.expect_tx.shared::cta.b64 _, [%5], %6;\n"
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%3, {%7, %8, %9, %10}], [%16];\n"
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4, {%11, %12, %13}], [%16];\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}"
+        : "=r"(ready)
+        : "r"(sa), "r"(sb), "l"(reinterpret_cast<uint64_t>(mapA)), "l"(reinterpret_cast<uint64_t>(mapB)),
+          "r"(full_bar), "r"(tx_bytes), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2),
+          "r"(next_empty_bar), "r"(next_parity), "r"(full_bar & PEER_MASK)
+        : "memory");
+  }
+  return ready;
+}
 
 __device__ __forceinline__ void decode_m_tile(const GemmKParams& p, int mt, int& x0, int& y0, int& i0) {
   const int tx = mt % p.tiles_x;
@@ -67,6 +248,7 @@ __device__ __forceinline__ void decode_m_tile(const GemmKParams& p, int mt, int&
   i0 = tn * p.bn;
 }
 
+// ------------------------------------------------------------------------- legacy (direct global store) epilogue
 // bias / residual / activation / store for 32 consecutive output columns of one row
 __device__ __forceinline__ void epilogue_store32(const GemmKParams& p, int64_t m, int n_base, int n_total,
                                                  float (&f)[32]) {
@@ -87,7 +269,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmKParams& p, int64_t m
         }
       }
     } else {
-      for (int j = 0; j < nvalid; ++j) f[j] += __half2float(rr[j]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) f[j] += __half2float(rr[j]);
     }
   }
   if (p.flags & LS_EPI_SILU) {
@@ -101,7 +285,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmKParams& p, int64_t m
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(o + j * 4) = make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
     } else {
-      for (int j = 0; j < nvalid; ++j) o[j] = f[j];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) o[j] = f[j];
     }
   } else {
     __half* o = reinterpret_cast<__half*>(p.out) + m * (int64_t)p.ldo + n_base;
@@ -115,7 +301,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmKParams& p, int64_t m
         *reinterpret_cast<uint4*>(o + j * 8) = u;
       }
     } else {
-      for (int j = 0; j < nvalid; ++j) o[j] = __float2half_rn(f[j]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) o[j] = __float2half_rn(f[j]);
     }
   }
 }
@@ -134,28 +322,26 @@ __device__ __forceinline__ void add_bias32(const GemmKParams& p, int64_t m, int 
       f[j * 4 + 3] += t.w;
     }
   } else {
-    for (int j = 0; j < nvalid; ++j) f[j] += __ldg(b + j);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) f[j] += __ldg(b + j);
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-  constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr int ACC_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
-  constexpr int TMEM_COLS = 2 * ACC_COLS;
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "tile N");
-  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
-  // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-  constexpr uint32_t IDESC = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+// ----------------------------------------------------------------------------------------------------- kernel body
+template <int CTAS>
+__device__ __forceinline__ void gemm_body(const GemmKParams& p) {
+  const int BN = p.BN;
+  const int b_rows = BN / CTAS;  // B rows staged by each CTA
+  const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
+  // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
+  const uint32_t idesc = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t((BM * CTAS) >> 4) << 24);
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const int stages = p.stages;
-  uint8_t* staging = smem + stages * STAGE_BYTES;  // 1024-byte aligned (STAGE_BYTES % 1024 == 0)
-  float* bias_sm = reinterpret_cast<float*>(staging + STAGING_BYTES);  // 2 groups x 256 floats
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + 2048);
+  uint8_t* staging = smem + stages * stage_bytes;  // 1024-byte aligned (stage_bytes % 1024 == 0)
+  float* bias_sm = reinterpret_cast<float*>(staging + STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + BIAS_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -163,129 +349,175 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int rank = (CTAS == 2) ? (int)cluster_ctarank() : 0;
+  const bool leader = (rank == 0);
+  const int unit = blockIdx.x / CTAS;  // CTA (or CTA pair) index
+  const int nunits = gridDim.x / CTAS;
+  const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
+  const int total_tiles = m_units * p.n_tiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.mapA[s]);
     tma_prefetch_desc(&p.mapB);
+    if (p.tma_store) tma_prefetch_desc(&p.mapOut);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], GEMM_THREADS / 32 - 2);
+      mbar_init(&tmem_empty[a], 8 * CTAS);  // one arrival per epilogue warp of every CTA of the pair
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
+  if (warp == MMA_WARP) tmem_alloc_g<CTAS>(tmem_slot, TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == PRODUCER_WARP) {
+    // ------------------------------------------------------------------ TMA producer (one lane, every CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int nt = tile - mt * p.n_tiles;
+      uint32_t ready = 0;  // probe result for the current stage's `empty` barrier
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const uint32_t tx = leader ? (uint32_t)(stage_bytes * CTAS) : 0u;
+#ifdef LS_GEMM_PROBE
+      long long pr_wait = 0, pr_miss = 0;
+      const long long pr_t0 = clock64();
+#endif
+      for (int tile = unit; tile < total_tiles; tile += nunits) {
+        const int mu = tile / p.n_tiles;
+        const int nt = tile - mu * p.n_tiles;
+        const int mt = mu * CTAS + rank;  // may run past m_tiles for the odd last pair: TMA zero-fills, stores clip
         int x0, y0, i0;
         decode_m_tile(p, mt, x0, y0, i0);
         const int bz = p.b_batched ? i0 : 0;
+        const int brow = nt * BN + rank * b_rows;
         int kcol = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
           const int cblk = p.seg_cblk[s];
+          const CUtensorMap* mapA = &p.mapA[s];
           for (int tap = 0; tap < taps; ++tap) {
             const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
             const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
             for (int cb = 0; cb < cblk; ++cb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
-              uint8_t* sa = smem + stage * STAGE_BYTES;
-              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-              tma_load_4d(sa, &p.mapA[s], &full_bar[stage], cb * BK, x0 + dx, y0 + dy, i0);
-              tma_load_3d(sa + A_STAGE_BYTES, &p.mapB, &full_bar[stage], kcol, nt * BN, bz);
+#ifdef LS_GEMM_PROBE
+              const long long pc0 = clock64();
+              pr_miss += ready ? 0 : 1;
+#endif
+              if (!ready) mbar_wait(&empty_bar[stage], phase ^ 1u);
+#ifdef LS_GEMM_PROBE
+              pr_wait += clock64() - pc0;
+#endif
+              const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
+              const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              ready = produce_kblock<CTAS>(sa, sa + A_STAGE_BYTES, mapA, &p.mapB, full0 + stage * 8, tx, cb * BK,
+                                           x0 + dx, y0 + dy, i0, kcol, brow, bz, empty0 + nstage * 8, nphase ^ 1u);
               kcol += BK;
-              if (++stage == stages) {
-                stage = 0;
-                phase ^= 1u;
-              }
+              stage = nstage;
+              phase = nphase;
             }
           }
         }
       }
+#ifdef LS_GEMM_PROBE
+      if (blockIdx.x == 0)
+        printf("gemm probe: producer total %lld clk, in wait(empty) %lld clk, probe misses %lld, kblocks/tile %d\n",
+               clock64() - pr_t0, pr_wait, pr_miss, p.num_kb);
+#endif
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    int stage = 0;
-    uint32_t phase = 0;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int acc = lt & 1;
-      const uint32_t acc_phase = (lt >> 1) & 1u;
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------------ MMA issuer (one lane, pair leader only)
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t ready = 0;  // probe result for the current stage's `full` barrier
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      int lt = 0;
+#ifdef LS_GEMM_PROBE
+      long long mm_wait = 0, mm_miss = 0, mm_acc = 0;
+      const long long mm_t0 = clock64();
+#endif
+      for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (lt >> 1) & 1u;
+#ifdef LS_GEMM_PROBE
+        const long long ma0 = clock64();
+#endif
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+#ifdef LS_GEMM_PROBE
+        mm_acc += clock64() - ma0;
+#endif
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes along K inside the 128B swizzle atom == +2 in the 16-byte-unit address field
-            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+#ifdef LS_GEMM_PROBE
+          const long long mc0 = clock64();
+          mm_miss += ready ? 0 : 1;
+#endif
+          if (!ready) mbar_wait(&full_bar[stage], phase);
+#ifdef LS_GEMM_PROBE
+          mm_wait += clock64() - mc0;
+#endif
+          tc_fence_after();
+          const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
+          const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          ready = mma_kblock<CTAS>(d_tmem, umma_desc_sw128(sa), umma_desc_sw128(sa + A_STAGE_BYTES), idesc,
+                                   kb != 0 ? 1u : 0u, empty0 + stage * 8, full0 + nstage * 8, nphase);
+          stage = nstage;
+          phase = nphase;
         }
-        __syncwarp();
-        if (++stage == stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        umma_commit_g<CTAS>(&tmem_full[acc]);  // accumulator complete once every MMA issued so far has retired
       }
+#ifdef LS_GEMM_PROBE
+      if (blockIdx.x == 0)
+        printf("gemm probe: issuer total %lld clk (%d tiles), in wait(full) %lld clk, probe misses %lld, "
+               "wait(tmem_empty) %lld clk\n", clock64() - mm_t0, lt, mm_wait, mm_miss, mm_acc);
+#endif
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int group = (warp - 2) >> 2; // 0: even slabs, 1: odd slabs
-    const int r = q * 32 + lane;       // row of the tile == TMEM lane
+    // ------------------------------------------------------------------ epilogue (warps 0..7, every CTA)
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int group = warp >> 2;  // 0: even slabs, 1: odd slabs
+    const int r = q * 32 + lane;  // row of the tile == TMEM lane
     const bool geglu = (p.flags & LS_EPI_GEGLU) != 0;
     if (p.tma_store) {
       // Latency-tolerant epilogue: the tile's bias row goes to smem and ALL residual fragments of the group's slabs
       // are requested before waiting for the accumulator, so global-load latency hides behind the main loop.
-      const bool issuer = (warp == 2 + 4 * group) && lane == 0;
+      const bool issuer = (warp == 4 * group) && lane == 0;
       uint8_t* my_stage = staging + group * 2 * SLAB_BYTES;
       float* my_bias = bias_sm + group * 256;
-      constexpr int NSLAB_MAX = (BN / 32 + 1) / 2;  // slabs per group
+      constexpr int NSLAB_MAX = 4;  // slabs per group at BN = 256
       const int nslab = geglu ? BN / 64 : BN / 32;
       const int n_out_total = geglu ? p.N / 2 : p.N;
-      const int gtid = (warp - 2 - 4 * group) * 32 + lane;  // 0..127 inside the group
+      const int gtid = (warp - 4 * group) * 32 + lane;  // 0..127 inside the group
       uint32_t slab_count = 0;
       int lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1u;
-        const int mt = tile / p.n_tiles;
-        const int nt = tile - mt * p.n_tiles;
+        const int mu = tile / p.n_tiles;
+        const int nt = tile - mu * p.n_tiles;
+        const int mt = mu * CTAS + rank;
         int x0, y0, i0;
         decode_m_tile(p, mt, x0, y0, i0);
         const int64_t m0 = ((int64_t)i0 * p.H + y0) * p.W + x0;  // tile rows are contiguous (checked on the host)
         const int64_t m = m0 + r;
         const bool row_ok = m < p.M;
+        const bool tile_ok = m0 < p.M;
         const int last_j = group + ((nslab - 1 - group) / 2) * 2;  // last slab this group handles
         // (1) bias row of this tile -> smem (host guarantees one bias row per tile: bias_div % 128 == 0)
         {
-          const float* brow = p.bias + (p.bias_div > 0 ? (m0 / p.bias_div) * (int64_t)p.bias_ld : 0) + nt * BN;
+          const int64_t brow_i = (p.bias_div > 0 && tile_ok) ? (m0 / p.bias_div) : 0;
+          const float* brow = p.bias + brow_i * (int64_t)p.bias_ld + nt * BN;
           for (int c = gtid; c < BN; c += 128)
             my_bias[c] = (p.bias != nullptr && nt * BN + c < p.N) ? __ldg(brow + c) : 0.f;
         }
@@ -307,7 +539,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
         }
         named_bar_sync(1 + group, 128);  // bias row visible to the group
-        mbar_wait(&tmem_full[acc], acc_phase);
+        mbar_wait_relaxed(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
         bool released = false;
@@ -323,16 +555,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           if (!geglu) {
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int e4 = 0; e4 < 8; ++e4) {
-                const float4 t = *reinterpret_cast<const float4*>(my_bias + j * 32 + e4 * 4);
-                f[e4 * 4] += t.x;
-                f[e4 * 4 + 1] += t.y;
-                f[e4 * 4 + 2] += t.z;
-                f[e4 * 4 + 3] += t.w;
-              }
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 t = *reinterpret_cast<const float4*>(my_bias + j * 32 + e4 * 4);
+              f[e4 * 4] = __uint_as_float(v[e4 * 4]) + t.x;
+              f[e4 * 4 + 1] = __uint_as_float(v[e4 * 4 + 1]) + t.y;
+              f[e4 * 4 + 2] = __uint_as_float(v[e4 * 4 + 2]) + t.z;
+              f[e4 * 4 + 3] = __uint_as_float(v[e4 * 4 + 3]) + t.w;
             }
           } else {
             uint32_t g[32];
@@ -348,7 +576,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           if (j == last_j) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
             released = true;
           }
           if (p.residual != nullptr) {
@@ -391,7 +619,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           // once the group passes the barrier below
           if (issuer) bulk_wait_group_read<0>();
           named_bar_sync(1 + group, 128);
-          if (issuer) {
+          if (issuer && tile_ok) {
             tma_store_2d(&p.mapOut, slab, ncol0, (int)m0);
             bulk_commit_group();
           }
@@ -399,63 +627,65 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (!released) {  // group had no slab inside N for this tile: still hand the accumulator back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
         }
       }
       if (issuer) bulk_wait_group_read<0>();
     } else if (group == 0) {
-    const int ix = r % p.bw;
-    const int iy = (r / p.bw) % p.bh;
-    const int in = r / (p.bw * p.bh);
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int acc = lt & 1;
-      const uint32_t acc_phase = (lt >> 1) & 1u;
-      const int mt = tile / p.n_tiles;
-      const int nt = tile - mt * p.n_tiles;
-      int x0, y0, i0;
-      decode_m_tile(p, mt, x0, y0, i0);
-      const int x = x0 + ix, y = y0 + iy, img = i0 + in;
-      const bool row_ok = (x < p.W) && (y < p.H) && (img < p.nimg);
-      const int64_t m = ((int64_t)img * p.H + y) * p.W + x;
+      // legacy path (fp32 output / ragged geometry / narrow leading dimension): per-thread direct global stores
+      const int ix = r % p.bw;
+      const int iy = (r / p.bw) % p.bh;
+      const int in = r / (p.bw * p.bh);
+      int lt = 0;
+      for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (lt >> 1) & 1u;
+        const int mu = tile / p.n_tiles;
+        const int nt = tile - mu * p.n_tiles;
+        const int mt = mu * CTAS + rank;
+        int x0, y0, i0;
+        decode_m_tile(p, mt, x0, y0, i0);
+        const int x = x0 + ix, y = y0 + iy, img = i0 + in;
+        const bool row_ok = (x < p.W) && (y < p.H) && (img < p.nimg);
+        const int64_t m = ((int64_t)img * p.H + y) * p.W + x;
 
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
-
-      if (!(p.flags & LS_EPI_GEGLU)) {
+        mbar_wait_relaxed(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
+        if (!geglu) {
+          const int nchunk = BN / 32;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tbase + c * 32, v);
-          tmem_ld_wait();
-          if (c == BN / 32 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          const int n_base = nt * BN + c * 32;
-          if (row_ok && n_base < p.N) {
-            float f[32];
+          for (int c = 0; c < nchunk; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tbase + c * 32, v);
+            tmem_ld_wait();
+            if (c == nchunk - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
+            }
+            const int n_base = nt * BN + c * 32;
+            if (row_ok && n_base < p.N) {
+              float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            add_bias32(p, m, n_base, f);
-            epilogue_store32(p, m, n_base, p.N, f);
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              add_bias32(p, m, n_base, f);
+              epilogue_store32(p, m, n_base, p.N, f);
+            }
           }
-        }
-      } else {
-        // W rows of this tile are [BN/2 value rows | BN/2 gate rows]
-        if constexpr (BN >= 64) {
+        } else {
+          // W rows of this tile are [BN/2 value rows | BN/2 gate rows]
+          const int nchunk = BN / 64;
 #pragma unroll 1
-          for (int c = 0; c < BN / 64; ++c) {
+          for (int c = 0; c < nchunk; ++c) {
             uint32_t v[32], g[32];
             tmem_ld_32x32(tbase + c * 32, v);
             tmem_ld_32x32(tbase + BN / 2 + c * 32, g);
             tmem_ld_wait();
-            if (c == BN / 64 - 1) {
+            if (c == nchunk - 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+              if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
             }
             const int nv_base = nt * BN + c * 32;  // packed column of the value half
             if (row_ok && nv_base < p.N) {
@@ -474,23 +704,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
         }
       }
-    }
-  } else {
-      // legacy direct-store path uses the first 4 epilogue warps only; the others just release the accumulators
+    } else {
+      // the legacy path uses the first 4 epilogue warps only; the others just hand the accumulators back
       int lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1u;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        mbar_wait_relaxed(&tmem_full[acc], acc_phase);
+        if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == MMA_WARP) tmem_dealloc_g<CTAS>(tmem_base, TMEM_COLS);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
+  gemm_body<1>(p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc_pair_kernel(const __grid_constant__ GemmKParams p) {
+  gemm_body<2>(p);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -521,40 +758,22 @@ static int num_sms() {
   return n;
 }
 
-static int pick_tile_n(int m_tiles, int N, int sms) {
-  if (N <= 32) return 32;
-  if (N <= 64) return 64;
-  const int cands[5] = {256, 160, 128, 64, 32};
-  int best = 128;
-  long best_cost = -1;
-  for (int i = 0; i < 5; ++i) {
-    const int c = cands[i];
-    const long n_tiles = (N + c - 1) / c;
-    const long tiles = n_tiles * m_tiles;
-    const long waves = (tiles + sms - 1) / sms;
-    // per-tile time ~ BN MMA columns (+ fixed overhead); tiles narrower than 64 are operand-bandwidth bound
-    const long cost = waves * ((c < 64 ? 64 : c) + 24);
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = c;
-    }
-  }
-  return best;
-}
-
-template <int BN>
-static int launch_gemm(const GemmKParams& p, int grid, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
-  const size_t smem = (size_t)p.stages * STAGE_BYTES + STAGING_BYTES + 2048 + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(p);
-  LS_CUDA(cudaGetLastError());
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return 0;
+// Estimated cycles of one launch: waves x max(main loop, epilogue) + tail.  Per 64-wide k-block the main loop is bound
+// by the SM's shared-memory port, which TMA writes and tcgen05 operand reads share: measured with the clock64 probes
+// (profiles/r1_gemm_issue_loop.txt) ~ 330 + BN cycles for a single CTA (128 x BN tile) and ~ 560 + 0.15 BN for a CTA pair
+// (256 x BN tile), against 2 BN cycles of tensor work - so pairs only tie, and wide tiles win unless they waste columns.
+static double tile_cost(int ctas, int bn, int m_tiles, int N, int num_kb, int sms) {
+  const int n_tiles = (N + bn - 1) / bn;
+  const int m_units = (m_tiles + ctas - 1) / ctas;
+  const long tiles = (long)m_units * n_tiles;
+  const int units = sms / ctas;
+  const long waves = (tiles + units - 1) / units;
+  const double port = (ctas == 1) ? 330.0 + bn : 1.05 * (560.0 + 0.15 * bn);
+  const double t_kb = (2.0 * bn > port) ? 2.0 * bn : port;
+  const double t_epi = 400.0 + 300.0 * ((bn / 32 + 1) / 2);
+  const double t_main = num_kb * t_kb;
+  const double t_tile = (t_main > t_epi ? t_main : t_epi);
+  return waves * t_tile + t_epi + 2000.0;
 }
 
 static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
@@ -609,22 +828,44 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.tiles_y = (a->H + p.bh - 1) / p.bh;
   const int tiles_n = (a->nimg + p.bn - 1) / p.bn;
   p.m_tiles = p.tiles_x * p.tiles_y * tiles_n;
-  if (any_conv) {
-    // a 3x3 tap shift must stay inside one image row/column block: the box spans whole rows (or W >= 128)
-    LS_CHECK(a->b_batch_stride == 0, "ls_gemm: batched conv unsupported");
-  }
+  if (any_conv) LS_CHECK(a->b_batch_stride == 0, "ls_gemm: batched conv unsupported");
   p.N = a->N;
   p.b_batched = a->b_batch_stride != 0 ? 1 : 0;
   if (p.b_batched) LS_CHECK(p.bn == 1, "ls_gemm: batched GEMM needs >= 128 rows per problem or H == 1");
 
-  int BN = a->tile_n;
+  // ---- tile width and CTA pairing
   const int sms = num_sms();
-  if (a->flags & LS_EPI_GEGLU) {
-    LS_CHECK(BN == 64 || BN == 128 || BN == 256, "ls_gemm: GEGLU needs explicit tile_n in {64,128,256}");
-    LS_CHECK(a->N % BN == 0, "ls_gemm: GEGLU needs N %% tile_n == 0");
+  const bool geglu = (a->flags & LS_EPI_GEGLU) != 0;
+  static int env_ctas = -1;
+  if (env_ctas < 0) {
+    const char* e = getenv("LS_GEMM_CTAS");
+    env_ctas = e ? atoi(e) : 0;
   }
-  if (BN == 0) BN = pick_tile_n(p.m_tiles, a->N, sms);
-  LS_CHECK(BN == 32 || BN == 64 || BN == 128 || BN == 160 || BN == 256, "ls_gemm: unsupported tile_n %d", BN);
+  const int force_ctas = a->cta_pair != 0 ? a->cta_pair : env_ctas;
+  // a pair shares one B tile: both 128-row halves must belong to the same batched problem
+  const bool pair_ok = (p.m_tiles >= 2) && (!p.b_batched || ((p.tiles_x * p.tiles_y) % 2 == 0)) && (sms % 2 == 0);
+  int best_bn = 0, best_ctas = 1;
+  double best_cost = -1.0;
+  const int step = geglu ? 64 : 32;
+  for (int ctas = 1; ctas <= 2; ++ctas) {
+    if (ctas == 2 && !pair_ok) continue;
+    if (force_ctas == 1 && ctas == 2) continue;
+    if (force_ctas == 2 && ctas == 1 && pair_ok) continue;
+    for (int bn = step; bn <= 256; bn += step) {
+      if (a->tile_n != 0 && bn != a->tile_n) continue;
+      if (geglu && (a->N % bn != 0)) continue;
+      if (bn > 32 && bn - 32 >= a->N && a->tile_n == 0) continue;  // wider than the problem
+      const double c = tile_cost(ctas, bn, p.m_tiles, a->N, p.num_kb, sms);
+      if (best_cost < 0 || c < best_cost) {
+        best_cost = c;
+        best_bn = bn;
+        best_ctas = ctas;
+      }
+    }
+  }
+  LS_CHECK(best_bn > 0, "ls_gemm: no valid tile width for N=%d tile_n=%d flags=%d", a->N, a->tile_n, a->flags);
+  const int BN = best_bn, CTAS = best_ctas;
+  p.BN = BN;
   p.n_tiles = (a->N + BN - 1) / BN;
 
   // tensor maps
@@ -645,7 +886,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     LS_CHECK((reinterpret_cast<uintptr_t>(a->b_ptr) & 15) == 0 && (bstride & 15) == 0, "ls_gemm: B alignment");
     cuuint64_t gdim[3] = {(cuuint64_t)ktot, (cuuint64_t)a->N, nb};
     cuuint64_t gstr[2] = {(cuuint64_t)ktot * 2, bstride};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BN / CTAS), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(a->b_ptr), gdim, gstr, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -657,7 +898,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   // is 16-byte aligned; otherwise (fp32 output, ragged geometry, narrow ld) per-thread direct stores
   const int64_t M = (int64_t)a->nimg * a->H * a->W;
   p.M = M;
-  const int n_out = (a->flags & LS_EPI_GEGLU) ? a->N / 2 : a->N;
+  const int n_out = geglu ? a->N / 2 : a->N;
   const bool rows_contig = (a->W < BM) || (a->W % BM == 0) || (a->H == 1 && a->nimg == 1);
   p.tma_store = (!(a->flags & LS_EPI_OUT_F32) && (a->ldo % 8 == 0) && rows_contig && M < (1ll << 31) &&
                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->bias_div == 0 || a->bias_div % BM == 0) &&
@@ -683,23 +924,31 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.ldo = a->ldo;
   p.flags = a->flags;
 
-  const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
-  int stages = (227 * 1024 - 1024 - 256 - 2048 - STAGING_BYTES) / stage_bytes;
+  const int stage_bytes = A_STAGE_BYTES + (BN / CTAS) * 128;
+  const int fixed = STAGING_BYTES + BIAS_BYTES + 192;  // + 20 mbarriers and the TMEM slot
+  int stages = (SMEM_BUDGET - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > p.num_kb && p.num_kb >= 2) stages = p.num_kb;
   if (stages < 2) stages = 2;
   p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
 
-  const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < sms ? total : sms;
-  switch (BN) {
-    case 32: return launch_gemm<32>(p, grid, stream);
-    case 64: return launch_gemm<64>(p, grid, stream);
-    case 128: return launch_gemm<128>(p, grid, stream);
-    case 160: return launch_gemm<160>(p, grid, stream);
-    case 256: return launch_gemm<256>(p, grid, stream);
+  const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
+  const long total = (long)m_units * p.n_tiles;
+  const int units = sms / CTAS;
+  const int grid = (int)(total < units ? total : units) * CTAS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    LS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    attr_set = true;
   }
-  return 1;
+  if (CTAS == 1)
+    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, stream>>>(p);
+  else
+    gemm_tc_pair_kernel<<<grid, GEMM_THREADS, smem, stream>>>(p);
+  LS_CUDA(cudaGetLastError());
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 }  // namespace ls
