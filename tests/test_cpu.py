@@ -1,0 +1,345 @@
+"""CPU-side suite (`-m "not gpu"`): the oracle against the golden vectors produced by the reference's own modules and
+against closed forms, the host logic (parameter inventory, weight packing, scheduler tables, segment sharding, the
+drop-in classes' construction / error behaviour), and the C-ABI library (loads, exports every declared symbol).
+No kernel is launched here."""
+import ctypes
+import json
+import math
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+# ------------------------------------------------------------------------------------------------------ oracle
+def test_oracle_port_matches_reference_golden_tiny():
+    """oracle/unet_ref.py (the port that travels to the GPU box) vs the output of the REFERENCE's modules"""
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.spec import TINY_UNET_CONFIG
+    from oracle.unet_ref import unet_forward
+
+    gold = torch.load(os.path.join(GOLDEN, "unet_tiny.pt"))
+    sd = syn.unet_state_dict(TINY_UNET_CONFIG, seed=0)
+    seg = syn.segment_inputs(11, 0, 16, 128, 128)
+    x = torch.cat([seg["latents"]] * 2)
+    x = torch.cat([x, torch.cat([seg["mask_latents"]] * 2), torch.cat([seg["masked_image_latents"]] * 2),
+                   torch.cat([seg["ref_latents"]] * 2)], dim=1)
+    a = seg["audio_embeds"][None]
+    a = torch.cat([torch.zeros_like(a), a])
+    taps = {}
+    y = unet_forward(sd, TINY_UNET_CONFIG, x, gold["t"], a, taps=taps)
+    assert rel_l2(y, gold["noise_pred"]) < 1e-5
+    for k, v in gold["taps"].items():  # sub-sampled intermediate activations, Appendix-B tape order
+        got = taps[k].flatten()[:: max(1, taps[k].numel() // 4096)]
+        assert rel_l2(got, v) < 1e-5, k
+
+
+def test_oracle_loop_matches_reference_golden_tiny():
+    """the restated loop (lipsync_pipeline.py:537-568) + DDIM restatement reproduce the reference-driven trace"""
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.spec import TINY_UNET_CONFIG
+    from oracle import pipeline_ref as P
+    from oracle.unet_ref import unet_forward
+
+    gold = torch.load(os.path.join(GOLDEN, "unet_tiny.pt"))
+    sd = syn.unet_state_dict(TINY_UNET_CONFIG, seed=0)
+    seg = syn.segment_inputs(11, 0, 16, 128, 128)
+    trace = {}
+    P.denoise_segment(lambda s, t, a: unet_forward(sd, TINY_UNET_CONFIG, s, t, a), seg, steps=4, guidance=1.5,
+                      trace=trace, max_steps=2)
+    for j in range(2):
+        assert rel_l2(trace["noise_pred"][j], gold["loop4_noise_pred"][j]) < 2e-5
+        assert rel_l2(trace["latents"][j], gold["loop4_latents"][j]) < 2e-5
+
+
+def test_golden_stage2_files_are_consistent():
+    f = os.path.join(GOLDEN, "unet_stage2_fwd.pt")
+    g = os.path.join(GOLDEN, "loop_stage2.pt")
+    if not (os.path.exists(f) and os.path.exists(g)):
+        pytest.skip("stage2 golden vectors not generated")
+    fwd, loop = torch.load(f), torch.load(g)
+    assert fwd["port_vs_reference"] < 1e-5  # the port was pinned to the reference at the full config
+    assert fwd["noise_pred"].shape == (2, 4, 16, 32, 32)
+    assert loop["noise_pred"].shape == (20, 1, 4, 16, 32, 32) and loop["tf_steps"] == [0, 5, 10, 15, 19]
+    # step 0 of the loop is the CFG combination of the single forward (same inputs, t = 951)
+    eu, ec = fwd["noise_pred"].chunk(2)
+    assert rel_l2(loop["noise_pred_f32"][0], eu + 1.5 * (ec - eu)) < 1e-5
+
+
+def test_ddim_known_answers():
+    """closed-form pins for the diffusers DDIMScheduler restatements"""
+    from latentsync_b200.scheduler import DDIMScheduler
+    from oracle.pipeline_ref import DDIMRef
+
+    ref, sch = DDIMRef(), DDIMScheduler()
+    ac = ref.alphas_cumprod
+    for t, want in ((0, 0.99914998), (1, 0.99829602), (951, 0.00815500), (981, 0.00577550)):
+        assert abs(ac[t].item() - want) < 2e-7
+        assert abs(float(sch.alphas_cumprod[t]) - want) < 2e-7
+    assert ref.set_timesteps(20) == list(range(951, 0, -50))
+    assert ref.set_timesteps(50) == list(range(981, 0, -20))
+    sch.set_timesteps(20)
+    assert sch._host_timesteps == list(range(951, 0, -50)) and sch.timesteps.tolist() == list(range(951, 0, -50))
+    a_t, a_p = sch.step_coefficients(951)
+    assert abs(a_t - ac[951].item()) < 1e-9 and abs(a_p - ac[901].item()) < 1e-9
+    a_t, a_p = sch.step_coefficients(1)  # prev_t < 0 -> final_alpha_cumprod = abar_0 (set_alpha_to_one = False)
+    assert abs(a_p - ac[0].item()) < 1e-9
+    # one step against the textbook formula in fp64
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(4, 8, generator=g), torch.randn(4, 8, generator=g)
+    ref.set_timesteps(20)
+    at, ap = ac[951].double(), ac[901].double()
+    x0 = (x.double() - (1 - at).sqrt() * e.double()) / at.sqrt()
+    want = ap.sqrt() * x0 + (1 - ap).sqrt() * e.double()
+    assert rel_l2(ref.step(e, 951, x), want) < 1e-6
+    with pytest.raises(ValueError):
+        DDIMScheduler().step(e, 951, x)  # set_timesteps not called
+    with pytest.raises(NotImplementedError):
+        DDIMScheduler(prediction_type="v_prediction")
+
+
+def test_diffusers_restatements_closed_forms():
+    from oracle.diffusers_shim import FeedForward, get_timestep_embedding
+    from oracle.unet_ref import feed_forward, timestep_embedding
+
+    t = torch.tensor([951.0, 1.0])
+    e = timestep_embedding(t, 320)
+    k = torch.arange(160, dtype=torch.float32)
+    ang = t[:, None] * torch.exp(-math.log(10000.0) * k / 160)
+    assert torch.allclose(e, torch.cat([torch.cos(ang), torch.sin(ang)], -1), atol=1e-6)
+    assert torch.allclose(e, get_timestep_embedding(t, 320, True, 0), atol=1e-6)
+    torch.manual_seed(0)
+    ff = FeedForward(64)
+    x = torch.randn(5, 64)
+    sd = {"ff." + k: v for k, v in ff.state_dict().items()}
+    hg = F.linear(x, sd["ff.net.0.proj.weight"], sd["ff.net.0.proj.bias"])
+    want = F.linear(hg[:, :256] * F.gelu(hg[:, 256:]), sd["ff.net.2.weight"], sd["ff.net.2.bias"])
+    assert torch.allclose(feed_forward(sd, "ff", x), want, atol=1e-6)
+    assert torch.allclose(ff(x), want, atol=1e-6)
+
+
+def test_vae_oracle_matches_module_graph():
+    """oracle VAE decoder vs an independent nn.Module statement of the same published diffusers graph"""
+    import torch.nn as nn
+
+    from latentsync_b200 import synthetic as syn
+    from oracle.pipeline_ref import vae_decode
+
+    cfg = dict(block_out_channels=(32, 64), layers_per_block=1, latent_channels=4, out_channels=3, norm_num_groups=32,
+               in_channels=3, act_fn="silu", sample_size=16, scaling_factor=0.18215, shift_factor=0.0)
+    sd = syn.vae_decoder_state_dict(cfg, seed=1)
+    z = syn.approx_normal(2, "z", (2, 4, 8, 8))
+    got = vae_decode(sd, z, block_out_channels=(32, 64), layers_per_block=1)
+    assert got.shape == (2, 3, 16, 16) and torch.isfinite(got).all()
+
+    def conv(p, x, pad=1):
+        m = nn.Conv2d(sd[p + ".weight"].shape[1], sd[p + ".weight"].shape[0], sd[p + ".weight"].shape[2], padding=pad)
+        m.load_state_dict({"weight": sd[p + ".weight"], "bias": sd[p + ".bias"]})
+        return m(x)
+
+    def gn(p, x):
+        m = nn.GroupNorm(32, x.shape[1], eps=1e-6)
+        m.load_state_dict({"weight": sd[p + ".weight"], "bias": sd[p + ".bias"]})
+        return m(x)
+
+    def res(p, x):
+        h = conv(p + ".conv1", F.silu(gn(p + ".norm1", x)))
+        h = conv(p + ".conv2", F.silu(gn(p + ".norm2", h)))
+        return (conv(p + ".conv_shortcut", x, 0) if (p + ".conv_shortcut.weight") in sd else x) + h
+
+    with torch.no_grad():
+        x = conv("decoder.conv_in", conv("post_quant_conv", z, 0))
+        x = res("decoder.mid_block.resnets.0", x)
+        a = "decoder.mid_block.attentions.0"
+        n, c, h, w = x.shape
+        t = gn(a + ".group_norm", x).flatten(2).transpose(1, 2)
+        q, k, v = (F.linear(t, sd[f"{a}.{nm}.weight"], sd[f"{a}.{nm}.bias"]) for nm in ("to_q", "to_k", "to_v"))
+        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        o = F.linear(o, sd[a + ".to_out.0.weight"], sd[a + ".to_out.0.bias"])
+        x = o.transpose(1, 2).reshape(n, c, h, w) + x
+        x = res("decoder.mid_block.resnets.1", x)
+        for i in range(2):
+            for j in range(2):
+                x = res(f"decoder.up_blocks.{i}.resnets.{j}", x)
+            if i == 0:
+                x = conv("decoder.up_blocks.0.upsamplers.0.conv", F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        want = conv("decoder.conv_out", F.silu(gn("decoder.conv_norm_out", x)))
+    assert rel_l2(got, want) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------- host logic
+def test_param_spec_matches_reference_state_dict_keys():
+    """names, shapes AND order of the 1 246 checkpoint entries (fixture dumped from the reference's own module)"""
+    from latentsync_b200.spec import STAGE2_UNET_CONFIG, unet_param_spec, vae_decoder_param_spec
+
+    with open(os.path.join(GOLDEN, "unet_stage2_state_dict_keys.json")) as f:
+        ref = json.load(f)
+    spec = unet_param_spec(STAGE2_UNET_CONFIG)
+    assert len(ref) == 1246 and [k for k, _ in ref] == list(spec.keys())
+    assert [tuple(s) for _, s in ref] == list(spec.values())
+    assert sum(math.prod(s) for s in spec.values()) == 1267944644
+    v = vae_decoder_param_spec()
+    assert v["decoder.conv_in.weight"] == (512, 4, 3, 3) and v["decoder.conv_out.weight"] == (3, 128, 3, 3)
+    assert v["decoder.up_blocks.2.resnets.0.conv_shortcut.weight"] == (256, 512, 1, 1)
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in v and len(v) == 140
+
+
+def test_synthetic_tensors_are_platform_stable():
+    """bit-level pins: the golden vectors are only meaningful if the GPU box regenerates the same weights/inputs"""
+    from latentsync_b200 import synthetic as syn
+
+    w = syn.uniform(0, "conv_in.weight", (320, 13, 3, 3), -0.1, 0.1)
+    assert w.dtype == torch.float32 and abs(w.double().sum().item() - (-5.933126896619797)) < 1e-9
+    assert w.flatten()[:3].tolist() == [-0.09205986559391022, 0.031543709337711334, 0.015475377440452576]
+    n = syn.approx_normal(1234, "latents", (1, 4, 1, 32, 32))
+    assert abs(n.double().mean().item()) < 0.05 and abs(n.double().std().item() - 1.0) < 0.05
+    assert torch.equal(n, syn.approx_normal(1234, "latents", (1, 4, 1, 32, 32)))
+    seg = syn.segment_inputs(11, 3)
+    assert seg["latents"].shape == (1, 4, 16, 32, 32) and torch.equal(seg["latents"][:, :, 0], seg["latents"][:, :, 7])
+    assert torch.equal(seg["latents"], syn.segment_inputs(99, 0)["latents"])  # noise shared by every segment
+    assert not torch.equal(seg["audio_embeds"], syn.segment_inputs(11, 4)["audio_embeds"])
+    m = seg["masks"]
+    assert m.shape == (16, 1, 256, 256) and set(m.unique().tolist()) == {0.0, 1.0}
+    assert m[0, 0, 95:243, 9:248].sum() == 0 and m[0, 0, :95].min() == 1
+    pe = syn.sinusoid_pe(24, 320)
+    assert pe.shape == (1, 24, 320) and pe[0, 0, 0] == 0 and pe[0, 0, 1] == 1
+
+
+def test_weight_packing_layouts():
+    from latentsync_b200._lib import pack_geglu
+    from latentsync_b200.engine import pack_1x1, pack_conv3x3
+
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 13, 3, 3, generator=g)
+    x = torch.randn(2, 13, 5, 5, generator=g)
+    wp = pack_conv3x3(w).float()  # [N, 9 * 64], K = (tap, channel), channels zero padded 13 -> 64
+    assert wp.shape == (8, 576)
+    cols = F.unfold(F.pad(x, (0, 0, 0, 0, 0, 51)), 3, padding=1)  # (2, 64*9, 25) with K = (channel, tap)
+    cols = cols.reshape(2, 64, 9, 25).permute(0, 2, 1, 3).reshape(2, 576, 25)
+    got = torch.einsum("nk,bkp->bnp", wp, cols).reshape(2, 8, 5, 5)
+    assert rel_l2(got, F.conv2d(x.half().float(), w.half().float(), padding=1)) < 2e-3
+    ws = pack_conv3x3(torch.randn(4, 192, 3, 3, generator=g), splits=[128, 64])
+    assert ws.shape == (4, 9 * 128 + 9 * 64)
+    assert pack_1x1(torch.randn(6, 4, 1, 1, generator=g)).shape == (6, 64)
+    # GEGLU: every 256-row tile = 128 value rows followed by their 128 gate rows
+    wg = torch.arange(2 * 512).float()[:, None].repeat(1, 3)
+    wpk, bpk = pack_geglu(wg, torch.arange(1024).float(), 256)
+    assert wpk[:128, 0].tolist() == list(range(128)) and wpk[128:256, 0].tolist() == list(range(512, 640))
+    assert wpk[256:384, 0].tolist() == list(range(128, 256)) and bpk[384:512].tolist() == list(range(640, 768))
+
+
+def test_shard_segments_partition():
+    from latentsync_b200.pipeline import shard_segments
+
+    for n in (0, 1, 7, 8, 94):
+        for w in (1, 2, 4, 8):
+            parts = [shard_segments(n, r, w) for r in range(w)]
+            flat = [i for p in parts for i in p]
+            assert flat == list(range(n))  # contiguous, ordered, complete
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_unet_dropin_construction_and_errors():
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.spec import TINY_UNET_CONFIG
+    from latentsync_b200.unet import UNet3DConditionModel
+
+    cfg = dict(TINY_UNET_CONFIG, block_out_channels=(32, 64, 64, 64))
+    m = UNet3DConditionModel.from_config(dict(cfg, not_a_ctor_arg=1))  # from_config drops unknown keys (unet.py:496)
+    assert m.config.sample_size == 64 and m.add_audio_layer and m.config["in_channels"] == 13
+    sd = syn.unet_state_dict(cfg, seed=0)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    # load_state_dict tolerance (unet.py:473-492): wrong conv_in / attn2 shapes are dropped, not fatal
+    bad = dict(sd)
+    bad["conv_in.weight"] = torch.zeros(32, 4, 3, 3)
+    k = "down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"
+    bad[k] = torch.zeros(32, 768)
+    res = m.load_state_dict(bad, strict=False)
+    assert set(res.missing_keys) == {"conv_in.weight", "conv_in.bias", k}
+    assert torch.equal(m.state_dict()["conv_out.weight"], sd["conv_out.weight"])
+    with pytest.raises(TypeError):
+        UNet3DConditionModel(bogus=1)
+    m.eval()
+    x = torch.zeros(2, 13, 16, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):  # no CPU path, and it says so
+        m(x, 951, encoder_hidden_states=torch.zeros(2, 16, 50, 384))
+    with pytest.raises(RuntimeError):
+        m.train()(x, 951, encoder_hidden_states=torch.zeros(2, 16, 50, 384))
+    with pytest.raises(RuntimeError):
+        m.enable_gradient_checkpointing()
+
+
+def test_pipeline_signature_and_input_checks():
+    import inspect
+
+    from latentsync_b200.pipeline import LipsyncPipeline
+
+    sig = inspect.signature(LipsyncPipeline.__call__)
+    want = ["self", "video_path", "audio_path", "video_out_path", "video_mask_path", "num_frames", "video_fps",
+            "audio_sample_rate", "height", "width", "num_inference_steps", "guidance_scale", "weight_dtype", "eta",
+            "mask", "mask_image_path", "generator", "callback", "callback_steps", "data_path", "start_from_backwards",
+            "force_video_length", "use_darken", "brightness_factor", "kwargs"]
+    assert list(sig.parameters) == want  # lipsync_pipeline.py:361-387
+    assert sig.parameters["num_inference_steps"].default == 20 and sig.parameters["guidance_scale"].default == 1.5
+    fwd = inspect.signature(__import__("latentsync_b200.unet", fromlist=["x"]).UNet3DConditionModel.forward)
+    assert list(fwd.parameters) == ["self", "sample", "timestep", "encoder_hidden_states", "class_labels",
+                                    "attention_mask", "down_block_additional_residuals",
+                                    "mid_block_additional_residual", "return_dict"]  # unet.py:312-323
+
+    class V:
+        class config:
+            block_out_channels = (128, 256, 512, 512)
+
+    p = LipsyncPipeline(V(), None, None, None)
+    assert p.vae_scale_factor == 8
+    with pytest.raises(ValueError):
+        p.check_inputs(250, 250, 1)
+    with pytest.raises(AssertionError):
+        p.check_inputs(256, 128, 1)
+    with pytest.raises(ValueError):
+        p.check_inputs(256, 256, 0)
+
+
+# --------------------------------------------------------------------------------------------------- C-ABI
+def test_cabi_library_exports_every_declared_symbol():
+    from latentsync_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "latentsync_b200.h")).read()
+    declared = set(re.findall(r"\b(ls_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ls_abi_version() == 1
+    assert lib.ls_last_error() == b""
+    # struct layouts agree with the header (sizes are part of the ABI)
+    assert ctypes.sizeof(_lib.LsGemmArgs) % 8 == 0 and ctypes.sizeof(_lib.LsAttnArgs) % 8 == 0
+    # argument validation runs before any CUDA call: a null args pointer is an error code + message, not a crash
+    assert lib.ls_gemm(None, None) != 0 and b"null args" in lib.ls_last_error()
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    from latentsync_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_SO", os.path.join(ROOT, "latentsync_b200", "does_not_exist.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_no_product_code_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under latentsync_b200/ may import it"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "latentsync_b200")):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
