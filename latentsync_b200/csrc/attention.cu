@@ -67,6 +67,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // -------------------------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
+  pdl_prologue();
   constexpr int DP = (D + 15) / 16 * 16;
   constexpr int DS = DP + 8;  // padded smem row (halfs): conflict-free ldmatrix, 16B aligned
   constexpr int CPR = D / 8;  // 16-byte chunks per row
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
 // -------------------------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(128) attn_short_kernel(const AttnKParams p) {
+  pdl_prologue();
   constexpr int DP = (D + 15) / 16 * 16;
   constexpr int DS = DP + 8;
   constexpr int CPR = D / 8;
@@ -356,7 +358,7 @@ static int launch_attn(const AttnKParams& p, cudaStream_t stream) {
       set_short = true;
     }
     const int64_t probs = (int64_t)p.batch * p.heads;
-    attn_short_kernel<D><<<(unsigned)((probs + 3) / 4), 128, smem, stream>>>(p);
+    LS_CUDA(launch_k(attn_short_kernel<D>, dim3((unsigned)((probs + 3) / 4)), dim3(128), (size_t)(smem), (cudaStream_t)(stream), p));
   } else {
     const size_t smem = (size_t)5 * 64 * DS * sizeof(__half);
     static bool set_gen = false;
@@ -365,7 +367,7 @@ static int launch_attn(const AttnKParams& p, cudaStream_t stream) {
       set_gen = true;
     }
     dim3 grid((p.sq + 63) / 64, p.heads, p.batch);
-    attn_fwd_kernel<D><<<grid, 128, smem, stream>>>(p);
+    LS_CUDA(launch_k(attn_fwd_kernel<D>, dim3(grid), dim3(128), (size_t)(smem), (cudaStream_t)(stream), p));
   }
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

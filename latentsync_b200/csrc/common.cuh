@@ -29,6 +29,24 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
+// host: launch helper; LS_PDL=1 in the environment adds the PDL attribute (off by default: measured no gain in graphs)
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------
@@ -185,6 +203,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
   return d;
+}
+
+// Programmatic dependent launch (PDL): every kernel is launched with programmaticStreamSerialization so that its CTAs
+// are scheduled while the previous kernel of the stream drains; `pdl_prologue()` (griddepcontrol.wait) must run before
+// the first access to memory written by earlier kernels, and EVERY kernel must execute it (completion is transitive
+// only then).  launch_dependents right away: the next kernel may start its own prologue as soon as SM resources free.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }

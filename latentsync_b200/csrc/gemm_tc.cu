@@ -375,6 +375,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == PRODUCER_WARP) {
     // ------------------------------------------------------------------ TMA producer (one lane, every CTA)
@@ -943,9 +944,9 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     attr_set = true;
   }
   if (CTAS == 1)
-    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, stream>>>(p);
+    LS_CUDA(launch_k(gemm_tc_kernel, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), (cudaStream_t)(stream), p));
   else
-    gemm_tc_pair_kernel<<<grid, GEMM_THREADS, smem, stream>>>(p);
+    LS_CUDA(launch_k(gemm_tc_pair_kernel, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), (cudaStream_t)(stream), p));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;

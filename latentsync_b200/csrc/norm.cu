@@ -14,59 +14,86 @@ namespace ls {
 extern std::atomic<int64_t> g_launch_count;
 
 // -------------------------------------------------------------------------------------------------- GroupNorm
-// Deterministic two-level reduction (no floating-point atomics): every CTA reduces its row chunk per channel pair,
-// folds pairs into groups in a fixed order and writes one partial per (instance, chunk, group); the CTA that arrives
-// last at the per-instance ticket (an integer atomic) sums the partials in chunk order and resets the ticket.
-__global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
-                                int rows_per_inst, int rows_per_chunk, int groups, float* __restrict__ partial,
-                                float* __restrict__ stats, unsigned int* __restrict__ tickets) {
-  extern __shared__ float gs_sm[];  // [npairs] sums, [npairs] sums of squares
+// Deterministic two-level reduction (no floating-point atomics): every CTA reduces its row chunk with 16-byte loads
+// (thread = one 8-channel column vector x one row lane, several rows in flight), folds row lanes and channels into groups
+// in a fixed order and writes one partial per (instance, chunk, group); the CTA that arrives last at the per-instance
+// ticket (an integer atomic) sums the partials in chunk order and resets the ticket.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x1, int c1,
+                                                       const __half* __restrict__ x2, int c2, int rows_per_inst,
+                                                       int rows_per_chunk, int groups, float* __restrict__ partial,
+                                                       float* __restrict__ stats, unsigned int* __restrict__ tickets) {
+  pdl_prologue();
+  extern __shared__ float gs_sm[];  // [RL][C] sums, then [RL][C] sums of squares
   __shared__ int s_last;
   const int C = c1 + c2;
   const int cg = C / groups;
-  const int npairs = C >> 1;
+  const int nvec = C >> 3;
+  const int RL = (nvec <= (int)blockDim.x) ? (int)blockDim.x / nvec : 1;  // row lanes
   float* sh_s = gs_sm;
-  float* sh_q = gs_sm + npairs;
+  float* sh_q = gs_sm + RL * C;
   const int inst = blockIdx.y;
   const int chunks = gridDim.x;
   const int64_t row0 = (int64_t)inst * rows_per_inst + (int64_t)blockIdx.x * rows_per_chunk;
   int64_t row_end = row0 + rows_per_chunk;
   const int64_t inst_end = (int64_t)(inst + 1) * rows_per_inst;
   if (row_end > inst_end) row_end = inst_end;
-  for (int pair = threadIdx.x; pair < npairs; pair += blockDim.x) {
-    const int c = pair * 2;
-    const __half* src;
-    int ld, cc;
-    if (c < c1) {
-      src = x1;
-      ld = c1;
-      cc = c;
-    } else {
-      src = x2;
-      ld = c2;
-      cc = c - c1;
+  const int rl = (nvec <= (int)blockDim.x) ? (int)threadIdx.x / nvec : 0;
+  const int cv0 = (nvec <= (int)blockDim.x) ? (int)threadIdx.x % nvec : (int)threadIdx.x;
+  const int cvstep = (nvec <= (int)blockDim.x) ? nvec : (int)blockDim.x;
+  if (rl < RL) {
+    for (int cv = cv0; cv < nvec; cv += cvstep) {
+      const int c = cv * 8;
+      const __half* src = (c < c1) ? (x1 + c) : (x2 + (c - c1));
+      const int ld = (c < c1) ? c1 : c2;
+      float s[8], q[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+      int64_t row = row0 + rl;
+      for (; row + 3 * RL < row_end; row += 4 * RL) {  // four rows in flight
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row + k * RL) * ld));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            s[2 * e] += f.x;
+            s[2 * e + 1] += f.y;
+            q[2 * e] += f.x * f.x;
+            q[2 * e + 1] += f.y * f.y;
+          }
+        }
+      }
+      for (; row < row_end; row += RL) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + row * ld));
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          s[2 * e] += f.x;
+          s[2 * e + 1] += f.y;
+          q[2 * e] += f.x * f.x;
+          q[2 * e + 1] += f.y * f.y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sh_s[rl * C + c + e] = s[e];
+        sh_q[rl * C + c + e] = q[e];
+      }
     }
-    float s = 0.f, ss = 0.f;
-#pragma unroll 4
-    for (int64_t row = row0; row < row_end; ++row) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(src + row * ld + cc));
-      s += f.x + f.y;
-      ss += f.x * f.x + f.y * f.y;
-    }
-    sh_s[pair] = s;
-    sh_q[pair] = ss;
   }
   __syncthreads();
   float* my_partial = partial + ((int64_t)inst * chunks + blockIdx.x) * groups * 2;
-  if (threadIdx.x < groups) {
-    const int ppg = cg >> 1;
-    float s = 0.f, ss = 0.f;
-    for (int i = 0; i < ppg; ++i) {
-      s += sh_s[threadIdx.x * ppg + i];
-      ss += sh_q[threadIdx.x * ppg + i];
-    }
-    my_partial[threadIdx.x * 2] = s;
-    my_partial[threadIdx.x * 2 + 1] = ss;
+  if (threadIdx.x < groups * 2) {  // thread = (group, stat); fixed summation order
+    const int g = threadIdx.x >> 1;
+    const float* base = (threadIdx.x & 1) ? sh_q : sh_s;
+    float acc = 0.f;
+    for (int r = 0; r < RL; ++r)
+      for (int i = 0; i < cg; ++i) acc += base[r * C + g * cg + i];
+    my_partial[threadIdx.x] = acc;
   }
   __threadfence();
   __syncthreads();
@@ -91,10 +118,12 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __h
   if (threadIdx.x == 0) tickets[inst] = 0u;
 }
 
-__global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
-                                int rows_per_inst, int rows_per_chunk, int groups, const float* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                                __half* __restrict__ y) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x1, int c1,
+                                                       const __half* __restrict__ x2, int c2, int rows_per_inst,
+                                                       int rows_per_chunk, int groups, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, int silu, __half* __restrict__ y) {
+  pdl_prologue();
   extern __shared__ float gn_sm[];
   const int C = c1 + c2;
   float* sa = gn_sm;
@@ -122,7 +151,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
     const int64_t row = row0 + idx / nvec;
     const int c = (int)(idx % nvec) * 8;
     const __half* src = (c < c1) ? (x1 + row * c1 + c) : (x2 + row * c2 + (c - c1));
-    const uint4 u = *reinterpret_cast<const uint4*>(src);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
     const __half2* h2 = reinterpret_cast<const __half2*>(&u);
     uint4 w;
     __half2* o2 = reinterpret_cast<__half2*>(&w);
@@ -153,69 +182,94 @@ static void gn_chunking(int64_t rows, int rows_per_inst, int target_ctas, int& n
 }
 
 // --------------------------------------------------------------------------------------------------- LayerNorm
-// one warp per row, values held in registers, exact two-pass variance
-constexpr int LN_MAXV = 5;  // C <= 5 * 32 * 8 = 1280
-
-__global__ void layernorm_kernel(const __half* __restrict__ x, int64_t rows, int C, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, const float* __restrict__ pe,
-                                 int rows_per_frame, int nframes, __half* __restrict__ y) {
+// One warp normalises ROWS rows at a time (all their 16-byte loads are issued before the first reduction, which is
+// what keeps enough bytes in flight per SM: one row per warp ran at 2.2 TB/s), values stay in registers, exact
+// two-pass variance.  VPL = 16-byte vectors per lane: C <= 256 * VPL.
+template <int VPL, int ROWS>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int64_t rows, int C,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        const float* __restrict__ pe, int rows_per_frame, int nframes,
+                                                        __half* __restrict__ y) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
   const int nvec = C >> 3;
-  float v[LN_MAXV][8];
-  float sum = 0.f;
+  uint4 raw[ROWS][VPL];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < nvec) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + vi * 8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+  for (int r = 0; r < ROWS; ++r) {
+    const int64_t row = row0 + r;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      raw[r][i] = (row < rows && vi < nvec) ? __ldg(reinterpret_cast<const uint4*>(x + row * C + vi * 8))
+                                            : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  const float inv_c = 1.f / (float)C;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int64_t row = row0 + r;
+    if (row >= rows) break;  // warp-uniform
+    float v[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw[r][i]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = __half22float2(h2[e]);
         v[i][2 * e] = f.x;
         v[i][2 * e + 1] = f.y;
-        sum += f.x + f.y;
+        sum += f.x + f.y;  // padded vectors are zero
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)C;
-  float sq = 0.f;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < nvec) {
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + 32 * i < nvec) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = v[i][e] - mean;
-        sq += d * d;
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[i][e] - mean;
+          sq += d * d;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / (float)C + eps);
-  const float* pe_row = nullptr;
-  if (pe != nullptr) pe_row = pe + (int64_t)((row / rows_per_frame) % nframes) * C;
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+    const float* pe_row = nullptr;
+    if (pe != nullptr) pe_row = pe + (int64_t)((row / rows_per_frame) % nframes) * C;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < nvec) {
-      const int c = vi * 8;
-      float r[8];
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const int c = vi * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float rr[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        r[e] = (v[i][e] - mean) * rstd * __ldg(gamma + c + e) + __ldg(beta + c + e);
-        if (pe_row != nullptr) r[e] += __ldg(pe_row + c + e);
+        for (int e = 0; e < 8; ++e) rr[e] = (v[i][e] - mean) * rstd * gg[e] + bb[e];
+        if (pe_row != nullptr) {
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe_row + c));
+          const float4 p1 = __ldg(reinterpret_cast<const float4*>(pe_row + c + 4));
+          rr[0] += p0.x; rr[1] += p0.y; rr[2] += p0.z; rr[3] += p0.w;
+          rr[4] += p1.x; rr[5] += p1.y; rr[6] += p1.z; rr[7] += p1.w;
+        }
+        uint4 w;
+        __half2* o2 = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(rr[2 * e], rr[2 * e + 1]);
+        *reinterpret_cast<uint4*>(y + row * C + c) = w;
       }
-      uint4 w;
-      __half2* o2 = reinterpret_cast<__half2*>(&w);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(r[2 * e], r[2 * e + 1]);
-      *reinterpret_cast<uint4*>(y + row * C + c) = w;
     }
   }
 }
@@ -225,6 +279,7 @@ constexpr int SM_MAXV = 8;  // cols <= 8 * 32 * 8 = 2048
 
 __global__ void softmax_rows_kernel(const float* __restrict__ s, int64_t rows, int cols, float scale,
                                     __half* __restrict__ p) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -276,6 +331,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, int64_t rows, i
 
 // --------------------------------------------------------------------------------------------------- transpose
 __global__ void transpose_kernel(const __half* __restrict__ x, int R, int C, __half* __restrict__ y) {
+  pdl_prologue();
   __shared__ __half tile[32][34];
   const int64_t boff = (int64_t)blockIdx.z * R * C;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -310,10 +366,10 @@ extern "C" int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, in
   const int C = c1 + (x2 ? c2 : 0);
   if (!x2) c2 = 0;
   LS_CHECK(x1 && stats && rows > 0 && rows_per_inst > 0 && rows % rows_per_inst == 0, "ls_groupnorm_stats: bad args");
-  LS_CHECK(groups > 0 && groups <= 32 && C % groups == 0 && (C / groups) % 2 == 0 && c1 % 2 == 0,
+  LS_CHECK(groups > 0 && groups <= 32 && C % groups == 0 && C % 8 == 0 && c1 % 8 == 0,
            "ls_groupnorm_stats: C=%d groups=%d unsupported", C, groups);
   int ninst, chunks, rpc;
-  gn_chunking(rows, rows_per_inst, 1184, ninst, chunks, rpc);
+  gn_chunking(rows, rows_per_inst, 444, ninst, chunks, rpc);
   int dev = 0;
   LS_CUDA(cudaGetDevice(&dev));
   LS_CHECK(dev >= 0 && dev < 16, "ls_groupnorm_stats: device index %d out of range", dev);
@@ -337,13 +393,13 @@ extern "C" int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, in
       LS_CUDA(cudaMemset(sc.tickets, 0, sc.ntickets * sizeof(unsigned int)));
     }
   }
-  int threads = C / 2;
-  if (threads > 512) threads = 512;
-  threads = (threads + 31) / 32 * 32;
-  if (threads < 256) threads = 256;  // the final reduction uses 4 threads per (group, stat): 4 * 64 = 256
-  const size_t smem = (size_t)C * sizeof(float);
-  gn_stats_kernel<<<dim3(chunks, ninst), threads, smem, (cudaStream_t)stream>>>(
-      (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial, stats, sc.tickets);
+  const int threads = 256;
+  const int nvec = C / 8;
+  const int RL = nvec <= threads ? threads / nvec : 1;
+  const size_t smem = (size_t)2 * RL * C * sizeof(float);
+  LS_CHECK(smem <= 48 * 1024, "ls_groupnorm_stats: C=%d needs %zu bytes of smem", C, smem);
+  LS_CUDA(launch_k(gn_stats_kernel, dim3(dim3(chunks, ninst)), dim3(threads), (size_t)(smem), (cudaStream_t)((cudaStream_t)stream), 
+      (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial, stats, sc.tickets));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -360,22 +416,39 @@ extern "C" int ls_groupnorm_apply(const void* x1, int32_t c1, const void* x2, in
   LS_CHECK(2 * C * sizeof(float) <= 48 * 1024, "ls_groupnorm_apply: C=%d too large", C);
   int ninst, chunks, rpc;
   gn_chunking(rows, rows_per_inst, 2368, ninst, chunks, rpc);
-  gn_apply_kernel<<<dim3(chunks, ninst), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+  LS_CUDA(launch_k(gn_apply_kernel, dim3(dim3(chunks, ninst)), dim3(256), (size_t)(2 * C * sizeof(float)), (cudaStream_t)((cudaStream_t)stream), 
       (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, stats, gamma, beta, eps, silu,
-      (__half*)y);
+      (__half*)y));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+template <int VPL, int ROWS>
+static int launch_ln(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps,
+                      const float* pe, int32_t rows_per_frame, int32_t nframes, void* y, cudaStream_t stream) {
+  const int wpb = 8;
+  const int64_t rows_per_block = (int64_t)wpb * ROWS;
+  LS_CUDA(launch_k(layernorm_kernel<VPL, ROWS>, dim3((unsigned)((rows + rows_per_block - 1) / rows_per_block)), dim3(wpb * 32), (size_t)(0), (cudaStream_t)(stream), 
+      (const __half*)x, rows, C, gamma, beta, eps, pe, rows_per_frame, nframes, (__half*)y));
   return 0;
 }
 
 extern "C" int ls_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps,
                             const float* pe, int32_t rows_per_frame, int32_t nframes, void* y, void* stream) {
   LS_CHECK(x && y && gamma && beta && rows > 0, "ls_layernorm: bad args");
-  LS_CHECK(C % 8 == 0 && C <= LN_MAXV * 256, "ls_layernorm: C=%d unsupported (multiple of 8, <= 1280)", C);
+  LS_CHECK(C % 8 == 0 && C <= 5 * 256, "ls_layernorm: C=%d unsupported (multiple of 8, <= 1280)", C);
   LS_CHECK(pe == nullptr || (rows_per_frame > 0 && nframes > 0), "ls_layernorm: bad pe geometry");
-  const int wpb = 8;
-  layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, rows, C, gamma, beta, eps, pe, rows_per_frame, nframes, (__half*)y);
+  LS_CHECK(((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+             reinterpret_cast<uintptr_t>(pe)) & 15) == 0, "ls_layernorm: gamma/beta/pe must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nvec = C / 8;
+  int rc;
+  if (nvec <= 32) rc = launch_ln<1, 8>(x, rows, C, gamma, beta, eps, pe, rows_per_frame, nframes, y, st);
+  else if (nvec <= 64) rc = launch_ln<2, 4>(x, rows, C, gamma, beta, eps, pe, rows_per_frame, nframes, y, st);
+  else if (nvec <= 96) rc = launch_ln<3, 2>(x, rows, C, gamma, beta, eps, pe, rows_per_frame, nframes, y, st);
+  else rc = launch_ln<5, 1>(x, rows, C, gamma, beta, eps, pe, rows_per_frame, nframes, y, st);
+  if (rc != 0) return rc;
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -385,8 +458,8 @@ extern "C" int ls_softmax_rows(const float* s, int64_t rows, int32_t cols, float
   LS_CHECK(s && p && rows > 0 && cols % 8 == 0 && cols <= SM_MAXV * 256 && scale > 0.f,
            "ls_softmax_rows: cols=%d unsupported", cols);
   const int wpb = 8;
-  softmax_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      s, rows, cols, scale, (__half*)p);
+  LS_CUDA(launch_k(softmax_rows_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), 
+      s, rows, cols, scale, (__half*)p));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -395,7 +468,7 @@ extern "C" int ls_softmax_rows(const float* s, int64_t rows, int32_t cols, float
 extern "C" int ls_transpose(const void* x, int32_t batch, int32_t R, int32_t C, void* y, void* stream) {
   LS_CHECK(x && y && batch > 0 && R > 0 && C > 0, "ls_transpose: bad args");
   dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
-  transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const __half*)x, R, C, (__half*)y);
+  LS_CUDA(launch_k(transpose_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), (const __half*)x, R, C, (__half*)y));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
