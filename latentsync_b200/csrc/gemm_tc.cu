@@ -46,7 +46,7 @@ constexpr int PRODUCER_WARP = 8;
 constexpr int MMA_WARP = 9;
 constexpr int SLAB_BYTES = BM * 64;            // 128 rows x 32 fp16 columns, SWIZZLE_64B
 constexpr int STAGING_BYTES = 4 * SLAB_BYTES;  // 2 epilogue groups x 2 slabs (ping-pong)
-constexpr int BIAS_BYTES = 2 * 256 * 4;        // 2 epilogue groups x 256 floats
+constexpr int BIAS_BYTES = 2 * 256 * 4;        // double-buffered bias row of 256 floats (shared by both groups)
 constexpr int ACC_COLS = 256;                  // TMEM columns per accumulator
 constexpr int TMEM_COLS = 512;                 // two accumulators: the whole TMEM (one CTA per SM anyway)
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -495,13 +495,31 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       // are requested before waiting for the accumulator, so global-load latency hides behind the main loop.
       const bool issuer = (warp == 4 * group) && lane == 0;
       uint8_t* my_stage = staging + group * 2 * SLAB_BYTES;
-      float* my_bias = bias_sm + group * 256;
       constexpr int NSLAB_MAX = 4;  // slabs per group at BN = 256
       const int nslab = geglu ? BN / 64 : BN / 32;
       const int n_out_total = geglu ? p.N / 2 : p.N;
       const int gtid = (warp - 4 * group) * 32 + lane;  // 0..127 inside the group
       uint32_t slab_count = 0;
       int lt = 0;
+      // bias row of the NEXT tile is fetched into registers one tile ahead and parked in a double-buffered smem row, so
+      // its global-load latency never sits on the epilogue's critical path (ncu: 9 % of the stall samples before)
+      float bias_next = 0.f;
+      auto fetch_bias = [&](int tile) {
+        if (tile >= total_tiles || p.bias == nullptr) {
+          bias_next = 0.f;
+          return;
+        }
+        const int mu = tile / p.n_tiles;
+        const int nt = tile - mu * p.n_tiles;
+        int x0, y0, i0;
+        decode_m_tile(p, mu * CTAS + rank, x0, y0, i0);
+        const int64_t m0 = ((int64_t)i0 * p.H + y0) * p.W + x0;
+        const int64_t brow_i = (p.bias_div > 0 && m0 < p.M) ? (m0 / p.bias_div) : 0;
+        const float* brow = p.bias + brow_i * (int64_t)p.bias_ld + nt * BN;
+        const int c = group * 128 + gtid;  // each group fetches its half of the row
+        bias_next = (c < BN && nt * BN + c < p.N) ? __ldg(brow + c) : 0.f;
+      };
+      fetch_bias(unit);
       for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1u;
@@ -515,31 +533,28 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         const bool row_ok = m < p.M;
         const bool tile_ok = m0 < p.M;
         const int last_j = group + ((nslab - 1 - group) / 2) * 2;  // last slab this group handles
-        // (1) bias row of this tile -> smem (host guarantees one bias row per tile: bias_div % 128 == 0)
-        {
-          const int64_t brow_i = (p.bias_div > 0 && tile_ok) ? (m0 / p.bias_div) : 0;
-          const float* brow = p.bias + brow_i * (int64_t)p.bias_ld + nt * BN;
-          for (int c = gtid; c < BN; c += 128)
-            my_bias[c] = (p.bias != nullptr && nt * BN + c < p.N) ? __ldg(brow + c) : 0.f;
-        }
-        // (2) residual fragments of every slab this group owns
-        uint4 res[NSLAB_MAX][4];
-        if (p.residual != nullptr) {
+        // (1) this tile's bias row (host guarantees one row per tile: bias_div % 128 == 0) -> smem buffer lt & 1.  The
+        //     buffer was last read two tiles ago and every thread has passed a group barrier since.
+        float* my_bias = bias_sm + (lt & 1) * 256;
+        my_bias[group * 128 + gtid] = bias_next;
+        // (2) residual fragments: two slabs in flight (a rolling pair of register buffers)
+        uint4 res[2][4];
+        auto fetch_res = [&](int s, uint4 (&dst)[4]) {
+          const int j = group + 2 * s;
+          const int ncol0 = nt * BN + j * 32;
+          if (p.residual != nullptr && j < nslab && row_ok && ncol0 + 32 <= n_out_total) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * (int64_t)p.ldr + ncol0);
 #pragma unroll
-          for (int s = 0; s < NSLAB_MAX; ++s) {
-            const int j = group + 2 * s;
-            const int ncol0 = nt * BN + j * 32;
-            if (j < nslab && row_ok && ncol0 + 32 <= n_out_total) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * (int64_t)p.ldr + ncol0);
+            for (int e = 0; e < 4; ++e) dst[e] = __ldg(rp + e);
+          } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) res[s][e] = __ldg(rp + e);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) res[s][e] = make_uint4(0u, 0u, 0u, 0u);
-            }
+            for (int e = 0; e < 4; ++e) dst[e] = make_uint4(0u, 0u, 0u, 0u);
           }
-        }
-        named_bar_sync(1 + group, 128);  // bias row visible to the group
+        };
+        fetch_res(0, res[0]);
+        fetch_res(1, res[1]);
+        fetch_bias(tile + nunits);  // (3) next tile's bias row -> registers
+        named_bar_sync(3, 256);  // bias row (written by both groups) visible to all epilogue warps
         mbar_wait_relaxed(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
@@ -568,10 +583,16 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             tmem_ld_32x32(tbase + BN / 2 + j * 32, g);
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float fv = __uint_as_float(v[e]) + my_bias[j * 32 + e];
-              const float fg = __uint_as_float(g[e]) + my_bias[BN / 2 + j * 32 + e];
-              f[e] = fv * gelu_erf_f(fg);
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 bv = *reinterpret_cast<const float4*>(my_bias + j * 32 + e4 * 4);
+              const float4 bg = *reinterpret_cast<const float4*>(my_bias + BN / 2 + j * 32 + e4 * 4);
+              f[e4 * 4] = (__uint_as_float(v[e4 * 4]) + bv.x) * gelu_erf_f(__uint_as_float(g[e4 * 4]) + bg.x);
+              f[e4 * 4 + 1] =
+                  (__uint_as_float(v[e4 * 4 + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[e4 * 4 + 1]) + bg.y);
+              f[e4 * 4 + 2] =
+                  (__uint_as_float(v[e4 * 4 + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[e4 * 4 + 2]) + bg.z);
+              f[e4 * 4 + 3] =
+                  (__uint_as_float(v[e4 * 4 + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[e4 * 4 + 3]) + bg.w);
             }
           }
           if (j == last_j) {
@@ -584,7 +605,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             if (ncol0 + 32 <= n_out_total) {
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4) {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&res[s][e4]);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&res[s & 1][e4]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 t = __half22float2(h2[e]);
@@ -598,6 +619,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
               for (int e = 0; e < 32; ++e)
                 if (ncol0 + e < n_out_total) f[e] += __half2float(rr[e]);
             }
+            if (s + 2 < NSLAB_MAX) fetch_res(s + 2, res[s & 1]);  // refill the buffer just consumed
           }
           if (p.flags & LS_EPI_SILU) {
 #pragma unroll
