@@ -76,6 +76,10 @@ struct GemmKParams {
   int ldo;
   int flags;
   int tma_store;
+  int splits;            // split-K factor: `splits` CTAs share one output tile, each reducing `kb_per` k-blocks
+  int kb_per;
+  float* ws;             // split-K partials, fp32 [splits][M][N] (library-owned scratch)
+  unsigned int* tickets; // one arrival counter per output tile (self-resetting)
   int64_t M;  // total output rows
 };
 
@@ -355,6 +359,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   const int nunits = gridDim.x / CTAS;
   const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
   const int total_tiles = m_units * p.n_tiles;
+  const int total_work = total_tiles * p.splits;  // work item w = (tile w / splits, K-range w % splits)
 
   if (warp == PRODUCER_WARP && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.mapA[s]);
@@ -390,7 +395,11 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       long long pr_wait = 0, pr_miss = 0;
       const long long pr_t0 = clock64();
 #endif
-      for (int tile = unit; tile < total_tiles; tile += nunits) {
+      for (int w = unit; w < total_work; w += nunits) {
+        const int tile = w / p.splits;
+        const int sp = w - tile * p.splits;
+        const int kb0 = sp * p.kb_per;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per);
         const int mu = tile / p.n_tiles;
         const int nt = tile - mu * p.n_tiles;
         const int mt = mu * CTAS + rank;  // may run past m_tiles for the odd last pair: TMA zero-fills, stores clip
@@ -398,31 +407,40 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         decode_m_tile(p, mt, x0, y0, i0);
         const int bz = p.b_batched ? i0 : 0;
         const int brow = nt * BN + rank * b_rows;
-        int kcol = 0;
-        for (int s = 0; s < p.nseg; ++s) {
+        // position of k-block kb0 in the (segment, tap, channel block) nest
+        int s = 0, rem = kb0;
+        while (s + 1 < p.nseg && rem >= p.seg_taps[s] * p.seg_cblk[s]) {
+          rem -= p.seg_taps[s] * p.seg_cblk[s];
+          ++s;
+        }
+        int tap = rem / p.seg_cblk[s];
+        int cb = rem - tap * p.seg_cblk[s];
+        int kcol = kb0 * BK;
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int taps = p.seg_taps[s];
-          const int cblk = p.seg_cblk[s];
-          const CUtensorMap* mapA = &p.mapA[s];
-          for (int tap = 0; tap < taps; ++tap) {
-            const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
-            const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
-            for (int cb = 0; cb < cblk; ++cb) {
+          const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+          const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
 #ifdef LS_GEMM_PROBE
-              const long long pc0 = clock64();
-              pr_miss += ready ? 0 : 1;
+          const long long pc0 = clock64();
+          pr_miss += ready ? 0 : 1;
 #endif
-              if (!ready) mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (!ready) mbar_wait(&empty_bar[stage], phase ^ 1u);
 #ifdef LS_GEMM_PROBE
-              pr_wait += clock64() - pc0;
+          pr_wait += clock64() - pc0;
 #endif
-              const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
-              const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
-              const uint32_t sa = smem_base + stage * stage_bytes;
-              ready = produce_kblock<CTAS>(sa, sa + A_STAGE_BYTES, mapA, &p.mapB, full0 + stage * 8, tx, cb * BK,
-                                           x0 + dx, y0 + dy, i0, kcol, brow, bz, empty0 + nstage * 8, nphase ^ 1u);
-              kcol += BK;
-              stage = nstage;
-              phase = nphase;
+          const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
+          const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          ready = produce_kblock<CTAS>(sa, sa + A_STAGE_BYTES, &p.mapA[s], &p.mapB, full0 + stage * 8, tx, cb * BK,
+                                       x0 + dx, y0 + dy, i0, kcol, brow, bz, empty0 + nstage * 8, nphase ^ 1u);
+          kcol += BK;
+          stage = nstage;
+          phase = nphase;
+          if (++cb == p.seg_cblk[s]) {
+            cb = 0;
+            if (++tap == taps) {
+              tap = 0;
+              ++s;
             }
           }
         }
@@ -446,7 +464,10 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       long long mm_wait = 0, mm_miss = 0, mm_acc = 0;
       const long long mm_t0 = clock64();
 #endif
-      for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {
+      for (int w = unit; w < total_work; w += nunits, ++lt) {
+        const int sp = w % p.splits;
+        const int kb0 = sp * p.kb_per;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per);
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1u;
 #ifdef LS_GEMM_PROBE
@@ -458,7 +479,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
 #endif
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
 #ifdef LS_GEMM_PROBE
           const long long mc0 = clock64();
           mm_miss += ready ? 0 : 1;
@@ -472,7 +493,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
           const uint32_t sa = smem_base + stage * stage_bytes;
           ready = mma_kblock<CTAS>(d_tmem, umma_desc_sw128(sa), umma_desc_sw128(sa + A_STAGE_BYTES), idesc,
-                                   kb != 0 ? 1u : 0u, empty0 + stage * 8, full0 + nstage * 8, nphase);
+                                   kb != kb0 ? 1u : 0u, empty0 + stage * 8, full0 + nstage * 8, nphase);
           stage = nstage;
           phase = nphase;
         }
@@ -504,8 +525,9 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       // bias row of the NEXT tile is fetched into registers one tile ahead and parked in a double-buffered smem row, so
       // its global-load latency never sits on the epilogue's critical path (ncu: 9 % of the stall samples before)
       float bias_next = 0.f;
-      auto fetch_bias = [&](int tile) {
-        if (tile >= total_tiles || p.bias == nullptr) {
+      auto fetch_bias = [&](int w_next) {
+        const int tile = w_next / p.splits;
+        if (w_next >= total_work || p.bias == nullptr) {
           bias_next = 0.f;
           return;
         }
@@ -520,7 +542,9 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         bias_next = (c < BN && nt * BN + c < p.N) ? __ldg(brow + c) : 0.f;
       };
       fetch_bias(unit);
-      for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {
+      for (int w = unit; w < total_work; w += nunits, ++lt) {
+        const int tile = w / p.splits;
+        const int sp = w - tile * p.splits;
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1u;
         const int mu = tile / p.n_tiles;
@@ -553,12 +577,116 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         };
         fetch_res(0, res[0]);
         fetch_res(1, res[1]);
-        fetch_bias(tile + nunits);  // (3) next tile's bias row -> registers
+        fetch_bias(w + nunits);  // (3) next work item's bias row -> registers
         named_bar_sync(3, 256);  // bias row (written by both groups) visible to all epilogue warps
         mbar_wait_relaxed(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
         bool released = false;
+        if (p.splits > 1) {
+          // split-K.  Phase A: park this CTA's fp32 partial in the workspace and hand the accumulator back.
+#pragma unroll
+          for (int s = 0; s < NSLAB_MAX; ++s) {
+            const int j = group + 2 * s;
+            const int ncol0 = nt * BN + j * 32;
+            if (j >= nslab || ncol0 >= n_out_total) break;
+            uint32_t v[32];
+            tmem_ld_32x32(tbase + j * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float* dst = p.ws + ((int64_t)sp * p.M + m) * p.N + ncol0;
+              if (ncol0 + 32 <= n_out_total) {
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4)
+                  __stcg(reinterpret_cast<float4*>(dst) + e4,
+                         make_float4(__uint_as_float(v[e4 * 4]), __uint_as_float(v[e4 * 4 + 1]),
+                                     __uint_as_float(v[e4 * 4 + 2]), __uint_as_float(v[e4 * 4 + 3])));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                  if (ncol0 + e < n_out_total) __stcg(dst + e, __uint_as_float(v[e]));
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
+          __threadfence();
+          named_bar_sync(3, 256);
+          // Rendezvous of the `splits` CTAs that share this tile.  They are all resident: the host only splits when the
+          // whole launch is a single wave of one CTA per SM.
+          unsigned int* tk = p.tickets + 2 * tile;
+          if (warp == 0 && lane == 0) {
+            atomicAdd(tk, 1u);
+            uint32_t spins = 0;
+            while (*reinterpret_cast<volatile unsigned int*>(tk) < (unsigned int)p.splits) {
+              __nanosleep(64);
+              if (++spins > (1u << 24)) {
+                printf("latentsync_b200: split-K rendezvous timeout (block %d)\n", blockIdx.x);
+                __trap();
+              }
+            }
+          }
+          named_bar_sync(3, 256);
+          __threadfence();
+          // Phase B: every CTA finishes 1/splits of the tile's 8-column chunks: sum of the partials in split order
+          // (deterministic) + bias + residual -> fp16, coalesced 16-byte accesses.
+          {
+            const int ncols = min(BN, p.N - nt * BN);
+            const int cpr = ncols >> 3;
+            const int total = BM * cpr;
+            const int per = (total + p.splits - 1) / p.splits;
+            const int i1 = min(total, (sp + 1) * per);
+            const int64_t brow_i = (p.bias_div > 0 && tile_ok) ? (m0 / p.bias_div) : 0;
+            const float* brow = p.bias != nullptr ? p.bias + brow_i * (int64_t)p.bias_ld : nullptr;
+            __half* outp = reinterpret_cast<__half*>(p.out);
+            for (int i = sp * per + warp * 32 + lane; i < i1; i += 256) {
+              const int row = i / cpr;
+              const int col = nt * BN + (i - row * cpr) * 8;
+              const int64_t mm = m0 + row;
+              if (mm >= p.M) continue;
+              float a8[8];
+              if (brow != nullptr) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(brow + col + 4));
+                a8[0] = b0.x; a8[1] = b0.y; a8[2] = b0.z; a8[3] = b0.w;
+                a8[4] = b1.x; a8[5] = b1.y; a8[6] = b1.z; a8[7] = b1.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a8[e] = 0.f;
+              }
+              uint4 rs = make_uint4(0u, 0u, 0u, 0u);
+              if (p.residual != nullptr) rs = __ldg(reinterpret_cast<const uint4*>(p.residual + mm * (int64_t)p.ldr + col));
+              const float* src = p.ws + mm * (int64_t)p.N + col;
+              const int64_t sstride = p.M * (int64_t)p.N;
+#pragma unroll 4
+              for (int q2 = 0; q2 < p.splits; ++q2) {
+                const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + q2 * sstride));
+                const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + q2 * sstride + 4));
+                a8[0] += t0.x; a8[1] += t0.y; a8[2] += t0.z; a8[3] += t0.w;
+                a8[4] += t1.x; a8[5] += t1.y; a8[6] += t1.z; a8[7] += t1.w;
+              }
+              const __half2* rh = reinterpret_cast<const __half2*>(&rs);
+              uint4 o;
+              __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __half22float2(rh[e]);
+                oh[e] = __floats2half2_rn(a8[2 * e] + t.x, a8[2 * e + 1] + t.y);
+              }
+              *reinterpret_cast<uint4*>(outp + mm * (int64_t)p.ldo + col) = o;
+            }
+          }
+          named_bar_sync(3, 256);
+          if (warp == 0 && lane == 0) {
+            const unsigned int old = atomicAdd(tk + 1, 1u);
+            if (old == (unsigned int)p.splits - 1u) {  // last CTA to leave resets both counters for the next launch
+              tk[0] = 0u;
+              tk[1] = 0u;
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int s = 0; s < NSLAB_MAX; ++s) {
           const int j = group + 2 * s;
@@ -567,8 +695,8 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           if (ncol0 >= n_out_total) break;  // this and all later slabs lie beyond N (uniform over the group)
           uint32_t v[32];
           float f[32];
-          tmem_ld_32x32(tbase + j * 32, v);
           if (!geglu) {
+            tmem_ld_32x32(tbase + j * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
@@ -580,6 +708,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             }
           } else {
             uint32_t g[32];
+            tmem_ld_32x32(tbase + j * 32, v);
             tmem_ld_32x32(tbase + BN / 2 + j * 32, g);
             tmem_ld_wait();
 #pragma unroll
@@ -660,7 +789,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       const int iy = (r / p.bw) % p.bh;
       const int in = r / (p.bw * p.bh);
       int lt = 0;
-      for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {
+      for (int tile = unit; tile < total_tiles; tile += nunits, ++lt) {  // splits == 1 on this path
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1u;
         const int mu = tile / p.n_tiles;
@@ -785,19 +914,31 @@ static int num_sms() {
 // by the SM's shared-memory port, which TMA writes and tcgen05 operand reads share: measured with the clock64 probes
 // (profiles/r1_gemm_issue_loop.txt) ~ 330 + BN cycles for a single CTA (128 x BN tile) and ~ 560 + 0.15 BN for a CTA pair
 // (256 x BN tile), against 2 BN cycles of tensor work - so pairs only tie, and wide tiles win unless they waste columns.
-static double tile_cost(int ctas, int bn, int m_tiles, int N, int num_kb, int sms) {
+static double tile_cost(int ctas, int bn, int splits, int m_tiles, int N, int num_kb, int sms) {
   const int n_tiles = (N + bn - 1) / bn;
   const int m_units = (m_tiles + ctas - 1) / ctas;
-  const long tiles = (long)m_units * n_tiles;
+  const long work = (long)m_units * n_tiles * splits;
   const int units = sms / ctas;
-  const long waves = (tiles + units - 1) / units;
+  const long waves = (work + units - 1) / units;
   const double port = (ctas == 1) ? 330.0 + bn : 1.05 * (560.0 + 0.15 * bn);
   const double t_kb = (2.0 * bn > port) ? 2.0 * bn : port;
   const double t_epi = 400.0 + 300.0 * ((bn / 32 + 1) / 2);
-  const double t_main = num_kb * t_kb;
+  const int kb_per = (num_kb + splits - 1) / splits;
+  const double t_main = kb_per * t_kb;
   const double t_tile = (t_main > t_epi ? t_main : t_epi);
-  return waves * t_tile + t_epi + 2000.0;
+  // split-K: every CTA parks an fp32 partial, meets its peers and finishes 1/splits of the tile
+  const double t_split = splits > 1 ? 6000.0 + 300.0 * splits : 0.0;
+  return waves * t_tile + t_epi + t_split + 2000.0;
 }
+
+// split-K scratch (fp32 partials + per-tile tickets), owned by the library, grown outside graph capture
+struct SplitScratch {
+  float* ws = nullptr;
+  size_t ws_floats = 0;
+  unsigned int* tickets = nullptr;
+  size_t ntickets = 0;
+};
+static SplitScratch g_split[16];
 
 static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   LS_CHECK(a != nullptr, "ls_gemm: null args");
@@ -856,7 +997,18 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.b_batched = a->b_batch_stride != 0 ? 1 : 0;
   if (p.b_batched) LS_CHECK(p.bn == 1, "ls_gemm: batched GEMM needs >= 128 rows per problem or H == 1");
 
-  // ---- tile width and CTA pairing
+  // output path: smem-staged TMA bulk stores when the tile's 128 rows are contiguous output rows and the row pitch
+  // is 16-byte aligned; otherwise (fp32 output, ragged geometry, narrow ld) per-thread direct stores
+  const int64_t M = (int64_t)a->nimg * a->H * a->W;
+  p.M = M;
+  const bool rows_contig = (a->W < BM) || (a->W % BM == 0) || (a->H == 1 && a->nimg == 1);
+  p.tma_store = (!(a->flags & LS_EPI_OUT_F32) && (a->ldo % 8 == 0) && rows_contig && M < (1ll << 31) &&
+                 (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->bias_div == 0 || a->bias_div % BM == 0) &&
+                 (a->residual == nullptr || ((a->ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0)))
+                    ? 1
+                    : 0;
+
+  // ---- tile width, CTA pairing and split-K factor
   const int sms = num_sms();
   const bool geglu = (a->flags & LS_EPI_GEGLU) != 0;
   static int env_ctas = -1;
@@ -867,7 +1019,15 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   const int force_ctas = a->cta_pair != 0 ? a->cta_pair : env_ctas;
   // a pair shares one B tile: both 128-row halves must belong to the same batched problem
   const bool pair_ok = (p.m_tiles >= 2) && (!p.b_batched || ((p.tiles_x * p.tiles_y) % 2 == 0)) && (sms % 2 == 0);
-  int best_bn = 0, best_ctas = 1;
+  static int env_split = -1;
+  if (env_split < 0) {
+    const char* e = getenv("LS_GEMM_SPLITK");  // 0 disables split-K (A/B measurements)
+    env_split = e ? atoi(e) : 1;
+  }
+  // split-K only where SMs would idle: few output tiles, long K; needs the TMA-store epilogue and a plain GEMM
+  const bool split_ok = env_split != 0 && p.tma_store && !geglu && !p.b_batched && !(a->flags & LS_EPI_SILU) &&
+                        (a->N % 8 == 0) && (a->bias_ld % 4 == 0);
+  int best_bn = 0, best_ctas = 1, best_split = 1;
   double best_cost = -1.0;
   const int step = geglu ? 64 : 32;
   for (int ctas = 1; ctas <= 2; ++ctas) {
@@ -878,11 +1038,23 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
       if (a->tile_n != 0 && bn != a->tile_n) continue;
       if (geglu && (a->N % bn != 0)) continue;
       if (bn > 32 && bn - 32 >= a->N && a->tile_n == 0) continue;  // wider than the problem
-      const double c = tile_cost(ctas, bn, p.m_tiles, a->N, p.num_kb, sms);
-      if (best_cost < 0 || c < best_cost) {
-        best_cost = c;
-        best_bn = bn;
-        best_ctas = ctas;
+      for (int sp = 1; sp <= 8; ++sp) {
+        if (env_split >= 2 && split_ok && ctas == 1 && sp != env_split && p.num_kb >= 4 * env_split) continue;  // forced
+        if (sp > 1) {
+          if (!split_ok || ctas != 1) break;
+          const int kb_per = (p.num_kb + sp - 1) / sp;
+          if (kb_per < 4 || (sp - 1) * kb_per >= p.num_kb) continue;        // every split needs work
+          if ((double)sp * M * a->N * 4.0 > 64.0 * 1024 * 1024) break;      // workspace bound
+          const long tiles = (long)p.m_tiles * ((a->N + bn - 1) / bn);
+          if (tiles * sp > sms) break;  // the rendezvous needs every CTA of the launch resident: a single wave
+        }
+        const double c = tile_cost(ctas, bn, sp, p.m_tiles, a->N, p.num_kb, sms);
+        if (best_cost < 0 || c < best_cost) {
+          best_cost = c;
+          best_bn = bn;
+          best_ctas = ctas;
+          best_split = sp;
+        }
       }
     }
   }
@@ -890,6 +1062,35 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   const int BN = best_bn, CTAS = best_ctas;
   p.BN = BN;
   p.n_tiles = (a->N + BN - 1) / BN;
+  p.splits = best_split;
+  p.kb_per = (p.num_kb + best_split - 1) / best_split;
+  if (best_split > 1) {
+    int dev = 0;
+    LS_CUDA(cudaGetDevice(&dev));
+    LS_CHECK(dev >= 0 && dev < 16, "ls_gemm: device index %d out of range", dev);
+    SplitScratch& sc = g_split[dev];
+    const size_t need = (size_t)best_split * M * a->N;
+    const size_t ntick = (size_t)p.m_tiles * p.n_tiles * 2 + 2;
+    if (need > sc.ws_floats || ntick > sc.ntickets) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cs);
+      LS_CHECK(cs == cudaStreamCaptureStatusNone, "ls_gemm: split-K scratch must be sized by an eager warm-up run");
+      LS_CUDA(cudaDeviceSynchronize());
+      if (need > sc.ws_floats) {
+        if (sc.ws) cudaFree(sc.ws);
+        sc.ws_floats = need > (size_t)(16u << 20) ? need : (size_t)(16u << 20);  // 64 MB covers every UNet/VAE shape
+        LS_CUDA(cudaMalloc(&sc.ws, sc.ws_floats * sizeof(float)));
+      }
+      if (ntick > sc.ntickets) {
+        if (sc.tickets) cudaFree(sc.tickets);
+        sc.ntickets = ntick > 8192 ? ntick : 8192;
+        LS_CUDA(cudaMalloc(&sc.tickets, sc.ntickets * sizeof(unsigned int)));
+        LS_CUDA(cudaMemset(sc.tickets, 0, sc.ntickets * sizeof(unsigned int)));
+      }
+    }
+    p.ws = sc.ws;
+    p.tickets = sc.tickets;
+  }
 
   // tensor maps
   for (int s = 0; s < a->nseg; ++s) {
@@ -917,17 +1118,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     LS_CHECK(r == CUDA_SUCCESS, "ls_gemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
 
-  // output path: smem-staged TMA bulk stores when the tile's 128 rows are contiguous output rows and the row pitch
-  // is 16-byte aligned; otherwise (fp32 output, ragged geometry, narrow ld) per-thread direct stores
-  const int64_t M = (int64_t)a->nimg * a->H * a->W;
-  p.M = M;
   const int n_out = geglu ? a->N / 2 : a->N;
-  const bool rows_contig = (a->W < BM) || (a->W % BM == 0) || (a->H == 1 && a->nimg == 1);
-  p.tma_store = (!(a->flags & LS_EPI_OUT_F32) && (a->ldo % 8 == 0) && rows_contig && M < (1ll << 31) &&
-                 (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->bias_div == 0 || a->bias_div % BM == 0) &&
-                 (a->residual == nullptr || ((a->ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0)))
-                    ? 1
-                    : 0;
   if (p.tma_store) {
     cuuint64_t gdim[2] = {(cuuint64_t)n_out, (cuuint64_t)M};
     cuuint64_t gstr[1] = {(cuuint64_t)a->ldo * 2};
@@ -956,7 +1147,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   const size_t smem = (size_t)stages * stage_bytes + fixed;
 
   const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
-  const long total = (long)m_units * p.n_tiles;
+  const long total = (long)m_units * p.n_tiles * p.splits;
   const int units = sms / CTAS;
   const int grid = (int)(total < units ? total : units) * CTAS;
   static bool attr_set = false;
