@@ -30,6 +30,19 @@ WORKLOAD = "configs[1]: one 16-frame 256x256 segment per step: 20x(UNet3D fwd, C
            "Whisper embeds 16x50x384) + DDIM + VAE decode + paste-back, random-init stage2 weights"
 
 
+# DRAM traffic of the dominant kernel (gemm_tc_kernel): sum of dram__bytes_read.sum + dram__bytes_write.sum over the 341
+# GEMM launches of ONE CFG-batched UNet forward, from the ncu capture profiles/r1_launches_unet.csv (joined table:
+# profiles/r1_launch_table.txt).  Same unit of work as `achieved` (FLOPs of those 341 launches / their summed duration).
+GEMM_DRAM_BYTES_PER_UNET_FORWARD = 9.5814e9
+
+
+def make_config(world: int, steps: int) -> dict:
+    return {"workload": WORKLOAD, "segments_per_gpu": steps, "frames_per_segment": FRAMES, "ddim_steps": DDIM_STEPS,
+            "guidance_scale": GUIDANCE, "parallelism": f"segments x{world}",
+            "operands": "fp16 tensor-core operands, fp32 accumulate (bf16 cannot meet rel-L2 1e-2, DESIGN.md)",
+            "l2": "no explicit flush: 2.5 GB of fp16 weights stream through the 126 MB L2 every UNet forward"}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -142,7 +155,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": warm_done, "ms_per_step": DDIM_STEPS * t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD}, "unet_step_ms": t * 1e3,
+        "config": make_config(args.gpus, len(times)), "unet_step_ms": t * 1e3,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -284,17 +297,17 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "segments_per_gpu": args.steps, "frames_per_segment": FRAMES,
-                       "ddim_steps": DDIM_STEPS, "guidance_scale": GUIDANCE, "parallelism": f"segments x{world}",
-                       "operands": "fp16 tensor-core operands, fp32 accumulate (bf16 cannot meet rel-L2 1e-2, DESIGN.md)",
-                       "l2": "no explicit flush: 2.5 GB of fp16 weights stream through the 126 MB L2 every UNet forward"},
+            "config": make_config(world, args.steps),
             "unet_step_ms": unet_ms,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": gemm_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "frac": gemm_tf / peak_tf, "traffic": GEMM_DRAM_BYTES_PER_UNET_FORWARD,
+                         "traffic_unit": "bytes per UNet forward (341 launches, ncu profiles/r1_launches_unet.csv)",
+                         "algorithmic_bytes_per_unet_forward": uplan.bytes("gemm"),
+                         "peak_source": peak_src,
                          "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
                          "launches_per_unet_forward": n_gemm,
                          "flops_per_unet_forward": uplan.flops("gemm"),

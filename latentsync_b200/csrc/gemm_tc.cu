@@ -46,7 +46,7 @@ constexpr int PRODUCER_WARP = 8;
 constexpr int MMA_WARP = 9;
 constexpr int SLAB_BYTES = BM * 64;            // 128 rows x 32 fp16 columns, SWIZZLE_64B
 constexpr int STAGING_BYTES = 4 * SLAB_BYTES;  // 2 epilogue groups x 2 slabs (ping-pong)
-constexpr int BIAS_BYTES = 2 * 256 * 4;        // double-buffered bias row of 256 floats (shared by both groups)
+constexpr int BIAS_BYTES = 2 * 256 * 4;        // one bias row of 256 floats per epilogue group
 constexpr int ACC_COLS = 256;                  // TMEM columns per accumulator
 constexpr int TMEM_COLS = 512;                 // two accumulators: the whole TMEM (one CTA per SM anyway)
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -524,11 +524,11 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       int lt = 0;
       // bias row of the NEXT tile is fetched into registers one tile ahead and parked in a double-buffered smem row, so
       // its global-load latency never sits on the epilogue's critical path (ncu: 9 % of the stall samples before)
-      float bias_next = 0.f;
+      float bias_next[2] = {0.f, 0.f};
       auto fetch_bias = [&](int w_next) {
         const int tile = w_next / p.splits;
         if (w_next >= total_work || p.bias == nullptr) {
-          bias_next = 0.f;
+          bias_next[0] = bias_next[1] = 0.f;
           return;
         }
         const int mu = tile / p.n_tiles;
@@ -538,8 +538,11 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         const int64_t m0 = ((int64_t)i0 * p.H + y0) * p.W + x0;
         const int64_t brow_i = (p.bias_div > 0 && m0 < p.M) ? (m0 / p.bias_div) : 0;
         const float* brow = p.bias + brow_i * (int64_t)p.bias_ld + nt * BN;
-        const int c = group * 128 + gtid;  // each group fetches its half of the row
-        bias_next = (c < BN && nt * BN + c < p.N) ? __ldg(brow + c) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c = gtid + 128 * k;
+          bias_next[k] = (c < BN && nt * BN + c < p.N) ? __ldg(brow + c) : 0.f;
+        }
       };
       fetch_bias(unit);
       for (int w = unit; w < total_work; w += nunits, ++lt) {
@@ -556,15 +559,17 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         const int64_t m = m0 + r;
         const bool row_ok = m < p.M;
         const bool tile_ok = m0 < p.M;
-        const int last_j = group + ((nslab - 1 - group) / 2) * 2;  // last slab this group handles
-        // (1) this tile's bias row (host guarantees one row per tile: bias_div % 128 == 0) -> smem buffer lt & 1.  The
-        //     buffer was last read two tiles ago and every thread has passed a group barrier since.
-        float* my_bias = bias_sm + (lt & 1) * 256;
-        my_bias[group * 128 + gtid] = bias_next;
+        const int g0 = (group + lt) & 1;  // slab parity of this group alternates per tile: 5 slabs = 3 + 2, then 2 + 3
+        const int last_j = g0 + ((nslab - 1 - g0) / 2) * 2;  // last slab this group handles
+        // (1) this tile's bias row (host guarantees one row per tile: bias_div % 128 == 0) -> the group's smem row.  Its
+        //     previous contents were last read before the final slab barrier of the previous tile.
+        float* my_bias = bias_sm + group * 256;
+        my_bias[gtid] = bias_next[0];
+        my_bias[gtid + 128] = bias_next[1];
         // (2) residual fragments: two slabs in flight (a rolling pair of register buffers)
         uint4 res[2][4];
         auto fetch_res = [&](int s, uint4 (&dst)[4]) {
-          const int j = group + 2 * s;
+          const int j = g0 + 2 * s;
           const int ncol0 = nt * BN + j * 32;
           if (p.residual != nullptr && j < nslab && row_ok && ncol0 + 32 <= n_out_total) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * (int64_t)p.ldr + ncol0);
@@ -578,7 +583,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         fetch_res(0, res[0]);
         fetch_res(1, res[1]);
         fetch_bias(w + nunits);  // (3) next work item's bias row -> registers
-        named_bar_sync(3, 256);  // bias row (written by both groups) visible to all epilogue warps
+        named_bar_sync(1 + group, 128);  // bias row visible to the group
         mbar_wait_relaxed(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
@@ -587,7 +592,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           // split-K.  Phase A: park this CTA's fp32 partial in the workspace and hand the accumulator back.
 #pragma unroll
           for (int s = 0; s < NSLAB_MAX; ++s) {
-            const int j = group + 2 * s;
+            const int j = g0 + 2 * s;
             const int ncol0 = nt * BN + j * 32;
             if (j >= nslab || ncol0 >= n_out_total) break;
             uint32_t v[32];
@@ -689,7 +694,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         }
 #pragma unroll
         for (int s = 0; s < NSLAB_MAX; ++s) {
-          const int j = group + 2 * s;
+          const int j = g0 + 2 * s;
           if (j >= nslab) break;
           const int ncol0 = geglu ? nt * (BN / 2) + j * 32 : nt * BN + j * 32;  // first output column of the slab
           if (ncol0 >= n_out_total) break;  // this and all later slabs lie beyond N (uniform over the group)

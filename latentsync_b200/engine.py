@@ -96,6 +96,7 @@ class Plan:
         self.kinds: List[str] = []  # one tag per recorded launch (bench.py times kernels by kind)
         self.descs: List[str] = []
         self.op_flops: List[float] = []  # algorithmic FLOPs of each launch (2*M*N*K for GEMM/conv, 4*B*h*Sq*Sk*d for SDPA)
+        self.op_bytes: List[float] = []  # algorithmic bytes of each GEMM launch: A once + W once + out (+ residual) once
 
     # ---- buffers
     def buf(self, rows, cols, dtype=torch.float16) -> Buf:
@@ -161,15 +162,19 @@ class Plan:
             self.graph.replay()
 
     # ---- emitters (each records ONE launch)
-    def _emit(self, fn, kind: str = "other", flops: float = 0.0, desc: str = "") -> None:
+    def _emit(self, fn, kind: str = "other", flops: float = 0.0, desc: str = "", nbytes: float = 0.0) -> None:
         self.ops.append(fn)
         self.kinds.append(kind)
         self.op_flops.append(flops)
+        self.op_bytes.append(nbytes)
         self.descs.append(desc)
         self.launches += 1
 
     def flops(self, kind: Optional[str] = None) -> float:
         return sum(f for k, f in zip(self.kinds, self.op_flops) if kind is None or k == kind)
+
+    def bytes(self, kind: Optional[str] = None) -> float:
+        return sum(b for k, b in zip(self.kinds, self.op_bytes) if kind is None or k == kind)
 
     def gemm(self, segs: Sequence[Tuple[int, int, int, int]], nimg: int, H: int, W: int, w: torch.Tensor, N: int,
              out_ptr: int, ldo: int, bias_ptr: int = 0, bias_div: int = 0, bias_ld: int = 0, residual_ptr: int = 0,
@@ -196,8 +201,14 @@ class Plan:
         a.out, a.ldo, a.flags, a.tile_n = out_ptr, ldo, flags, tile_n
         fn = self.lib.ls_gemm
         taps = "+".join(f"{ch}x{tp}" for _, ch, _, tp in segs)
-        self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_gemm"), "gemm", 2.0 * nimg * H * W * N * ktot,
-                   f"M={nimg * H * W} N={N} K={ktot} img={nimg}x{H}x{W} segs={taps} flags={flags} batched={int(b_batch_stride != 0)}")
+        M = nimg * H * W
+        n_out = N // 2 if flags & L.EPI_GEGLU else N
+        nb = nimg if b_batch_stride else 1
+        nbytes = (sum(M * ch * 2 for _, ch, _, _ in segs) + nb * N * ktot * 2 + M * n_out * (4 if flags & L.EPI_OUT_F32 else 2)
+                  + (M * n_out * 2 if residual_ptr else 0))
+        self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_gemm"), "gemm", 2.0 * M * N * ktot,
+                   f"M={M} N={N} K={ktot} img={nimg}x{H}x{W} segs={taps} flags={flags} batched={int(b_batch_stride != 0)}",
+                   float(nbytes))
 
     def begin_stats(self, nfloats: int) -> None:
         """one fp32 arena for the (sum, sumsq) results of every GroupNorm of the plan"""
