@@ -36,8 +36,8 @@ WORKLOAD = "configs[1]: one 16-frame 256x256 segment per step: 20x(UNet3D fwd, C
 GEMM_DRAM_BYTES_PER_UNET_FORWARD = 9.5814e9
 
 
-def make_config(world: int, steps: int) -> dict:
-    return {"workload": WORKLOAD, "segments_per_gpu": steps, "frames_per_segment": FRAMES, "ddim_steps": DDIM_STEPS,
+def make_config(world: int, steps: int, spb: int = 1) -> dict:
+    return {"workload": WORKLOAD, "segments_per_gpu": steps, "segments_per_batch": spb, "frames_per_segment": FRAMES, "ddim_steps": DDIM_STEPS,
             "guidance_scale": GUIDANCE, "parallelism": f"segments x{world}",
             "operands": "fp16 tensor-core operands, fp32 accumulate (bf16 cannot meet rel-L2 1e-2, DESIGN.md)",
             "l2": "no explicit flush: 2.5 GB of fp16 weights stream through the 126 MB L2 every UNet forward"}
@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--segments-per-batch", type=int, default=1,
+                    help="advance this many segments of the clip together as one UNet batch (throughput mode; the "
+                         "default 1 is BASELINE.json configs[1], one segment at a time like the reference's loop)")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-kind time table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -215,25 +218,25 @@ def main():
     d2h = out_host.numel() * out_host.element_size()
     gather_list = [torch.empty(FRAMES, 3, HEIGHT, WIDTH, device=dev) for _ in range(world)] if rank == 0 else None
 
-    def step(seg, e2e: bool):
-        frames = pipe.run_segments([seg], DDIM_STEPS, GUIDANCE)[0]
-        if world > 1:
-            dist.gather(frames, gather_list, dst=0)
-        if e2e:
-            out_host.copy_(frames, non_blocking=True)
-        return frames
+    spb = max(1, args.segments_per_batch)
+
+    def run(seg_list, e2e: bool):
+        """`len(seg_list)` steps (= segments), advanced `spb` at a time"""
+        for frames in pipe.run_segments(seg_list, DDIM_STEPS, GUIDANCE, segments_per_batch=spb):
+            if world > 1:
+                dist.gather(frames, gather_list, dst=0)
+            if e2e:
+                out_host.copy_(frames, non_blocking=True)
 
     def timed(segs, e2e: bool):
-        for i in range(args.warmup):
-            step(segs[i % len(segs)], e2e)
+        run([segs[i % len(segs)] for i in range(args.warmup)], e2e)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(args.steps):
-            step(segs[(args.warmup + i) % len(segs)], e2e)
+        run([segs[(args.warmup + i) % len(segs)] for i in range(args.steps)], e2e)
         b.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -297,7 +300,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": make_config(world, args.steps),
+            "config": make_config(world, args.steps, spb),
             "unet_step_ms": unet_ms,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},

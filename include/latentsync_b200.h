@@ -96,6 +96,12 @@ int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, int32_t c2, i
 int ls_groupnorm_apply(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows, int32_t rows_per_inst,
                        int32_t groups, const float* stats, const float* gamma, const float* beta, float eps,
                        int32_t silu, void* y, void* stream);
+/* Fused single-launch form of the two calls above: y = GroupNorm(x) (+ SiLU).  Statistics, the cross-CTA rendezvous and
+ * the normalisation happen in one kernel whenever the launch fits the GPU as one co-resident wave (every UNet / VAE
+ * shape); otherwise it falls back to stats + apply.  stats_scratch: fp32 [ninst][groups][2] (used by the fallback). */
+int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows, int32_t rows_per_inst,
+                 int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu, float* stats_scratch,
+                 void* y, void* stream);
 /* LayerNorm over C (nn.LayerNorm defaults, attention.py:145,157,172; motion_module.py:195,201), optionally adding
  * the temporal sinusoidal table pe[frame][C] (motion_module.py:232-234) with frame = (row / rows_per_frame) % nframes.
  * pe may be NULL. */

@@ -86,6 +86,7 @@ SYMBOLS = {
     "ls_gemm": (C.c_int, [C.POINTER(LsGemmArgs), _vp]),
     "ls_groupnorm_stats": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
     "ls_groupnorm_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _i32, _vp, _vp]),
+    "ls_groupnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp]),
     "ls_layernorm": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp]),
     "ls_attention": (C.c_int, [C.POINTER(LsAttnArgs), _vp]),
     "ls_softmax_rows": (C.c_int, [_vp, _i64, _i32, _f32, _vp, _vp]),
@@ -241,6 +242,14 @@ def groupnorm(
         L.ls_groupnorm_apply(_ptr(x1), c1, _ptr(x2), c2, rows, rows_per_inst, groups, _ptr(stats), _ptr(gamma),
                              _ptr(beta), eps, int(silu), _ptr(out), st),
         "ls_groupnorm_apply",
+    )
+
+
+def groupnorm_fused(x1, c1, x2, c2, rows, rows_per_inst, groups, gamma, beta, eps, silu, out, stats) -> None:
+    _check(
+        lib().ls_groupnorm(_ptr(x1), c1, _ptr(x2), c2, rows, rows_per_inst, groups, _ptr(gamma), _ptr(beta), eps,
+                           int(silu), _ptr(stats), _ptr(out), _stream()),
+        "ls_groupnorm",
     )
 
 

@@ -170,6 +170,163 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
   }
 }
 
+// Fused GroupNorm: statistics and normalisation in ONE launch.  Every CTA reduces its row chunk (same code path as
+// gn_stats_kernel), publishes the partial and meets the other CTAs of its instance at a ticket; after the rendezvous
+// each CTA sums the instance's partials in chunk order (deterministic, redundantly: chunks x 64 floats from L2),
+// builds the per-channel scale/shift in smem and normalises the chunk it has just read (L2-hot).  The host guarantees
+// that the whole grid is co-resident (grid <= occupancy x SMs, stream-ordered launches), so the rendezvous cannot hang.
+__global__ void __launch_bounds__(256) gn_fused_kernel(const __half* __restrict__ x1, int c1,
+                                                       const __half* __restrict__ x2, int c2, int rows_per_inst,
+                                                       int rows_per_chunk, int groups, float* __restrict__ partial,
+                                                       unsigned int* __restrict__ tickets,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, int silu, __half* __restrict__ y) {
+  pdl_prologue();
+  extern __shared__ float gf_sm[];  // phase 1: [RL][C] sums + [RL][C] squares; phase 2: sa[C], sb[C] (aliased)
+  __shared__ float s_stats[64];
+  const int C = c1 + c2;
+  const int cg = C / groups;
+  const int nvec = C >> 3;
+  const int RL = (nvec <= (int)blockDim.x) ? (int)blockDim.x / nvec : 1;
+  float* sh_s = gf_sm;
+  float* sh_q = gf_sm + RL * C;
+  const int inst = blockIdx.y;
+  const int chunks = gridDim.x;
+  const int64_t row0 = (int64_t)inst * rows_per_inst + (int64_t)blockIdx.x * rows_per_chunk;
+  int64_t row_end = row0 + rows_per_chunk;
+  const int64_t inst_end = (int64_t)(inst + 1) * rows_per_inst;
+  if (row_end > inst_end) row_end = inst_end;
+  const int rl = (nvec <= (int)blockDim.x) ? (int)threadIdx.x / nvec : 0;
+  const int cv0 = (nvec <= (int)blockDim.x) ? (int)threadIdx.x % nvec : (int)threadIdx.x;
+  const int cvstep = (nvec <= (int)blockDim.x) ? nvec : (int)blockDim.x;
+  if (rl < RL) {
+    for (int cv = cv0; cv < nvec; cv += cvstep) {
+      const int c = cv * 8;
+      const __half* src = (c < c1) ? (x1 + c) : (x2 + (c - c1));
+      const int ld = (c < c1) ? c1 : c2;
+      float s[8], q[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+      int64_t row = row0 + rl;
+      for (; row + 3 * RL < row_end; row += 4 * RL) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row + k * RL) * ld));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            s[2 * e] += f.x;
+            s[2 * e + 1] += f.y;
+            q[2 * e] += f.x * f.x;
+            q[2 * e + 1] += f.y * f.y;
+          }
+        }
+      }
+      for (; row < row_end; row += RL) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + row * ld));
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          s[2 * e] += f.x;
+          s[2 * e + 1] += f.y;
+          q[2 * e] += f.x * f.x;
+          q[2 * e + 1] += f.y * f.y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sh_s[rl * C + c + e] = s[e];
+        sh_q[rl * C + c + e] = q[e];
+      }
+    }
+  }
+  __syncthreads();
+  float* inst_partial = partial + (int64_t)inst * chunks * groups * 2;
+  if (threadIdx.x < groups * 2) {
+    const int g = threadIdx.x >> 1;
+    const float* base = (threadIdx.x & 1) ? sh_q : sh_s;
+    float acc = 0.f;
+    for (int r = 0; r < RL; ++r)
+      for (int i = 0; i < cg; ++i) acc += base[r * C + g * cg + i];
+    inst_partial[(int64_t)blockIdx.x * groups * 2 + threadIdx.x] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  unsigned int* tk = tickets + 2 * inst;
+  if (threadIdx.x == 0) {
+    atomicAdd(tk, 1u);
+    uint32_t spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(tk) < (unsigned int)chunks) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) {
+        printf("latentsync_b200: GroupNorm rendezvous timeout (block %d,%d)\n", blockIdx.x, blockIdx.y);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence();
+  {  // 4 threads per (group, stat): interleaved chunk ranges, combined in a fixed shuffle order
+    const int item = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const bool active = item < groups * 2;
+    float acc = 0.f;
+    if (active)
+      for (int ch = part; ch < chunks; ch += 4) acc += __ldcg(inst_partial + (int64_t)ch * groups * 2 + item);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (active && part == 0) s_stats[item] = acc;
+  }
+  __syncthreads();
+  float* sa = gf_sm;  // phase-1 arrays are dead from here on
+  float* sb = gf_sm + C;
+  const float inv_n = 1.f / ((float)rows_per_inst * (float)cg);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cg;
+    const float mean = s_stats[2 * g] * inv_n;
+    float var = s_stats[2 * g + 1] * inv_n - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float a = rsqrtf(var + eps) * gamma[c];
+    sa[c] = a;
+    sb[c] = beta[c] - mean * a;
+  }
+  __syncthreads();
+  const int64_t total = (row_end - row0) * nvec;
+  for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int64_t row = row0 + idx / nvec;
+    const int c = (int)(idx % nvec) * 8;
+    const __half* src = (c < c1) ? (x1 + row * c1 + c) : (x2 + row * c2 + (c - c1));
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    uint4 w;
+    __half2* o2 = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      float a = f.x * sa[c + 2 * e] + sb[c + 2 * e];
+      float b = f.y * sa[c + 2 * e + 1] + sb[c + 2 * e + 1];
+      if (silu) {
+        a = silu_f(a);
+        b = silu_f(b);
+      }
+      o2[e] = __floats2half2_rn(a, b);
+    }
+    *reinterpret_cast<uint4*>(y + row * C + c) = w;
+  }
+  // leave: the last CTA of the instance resets both counters for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(tk + 1, 1u);
+    if (old == (unsigned int)chunks - 1u) {
+      tk[0] = 0u;
+      tk[1] = 0u;
+    }
+  }
+}
+
 static void gn_chunking(int64_t rows, int rows_per_inst, int target_ctas, int& ninst, int& chunks, int& rpc) {
   ninst = (int)(rows / rows_per_inst);
   chunks = (target_ctas + ninst - 1) / ninst;
@@ -419,6 +576,82 @@ extern "C" int ls_groupnorm_apply(const void* x1, int32_t c1, const void* x2, in
   LS_CUDA(launch_k(gn_apply_kernel, dim3(dim3(chunks, ninst)), dim3(256), (size_t)(2 * C * sizeof(float)), (cudaStream_t)((cudaStream_t)stream), 
       (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, stats, gamma, beta, eps, silu,
       (__half*)y));
+  LS_CUDA(cudaGetLastError());
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// Fused single-launch GroupNorm (+SiLU): y = GN(x) [* sigmoid]; replaces the stats + apply pair when the grid fits the
+// GPU in one co-resident wave (always true for the UNet / VAE shapes); otherwise falls back to the two-kernel path.
+extern "C" int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows, int32_t rows_per_inst,
+                            int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
+                            float* stats_scratch, void* y, void* stream) {
+  if (!x2) c2 = 0;
+  const int C = c1 + c2;
+  LS_CHECK(x1 && gamma && beta && y && stats_scratch && rows > 0 && rows_per_inst > 0 && rows % rows_per_inst == 0,
+           "ls_groupnorm: bad args");
+  LS_CHECK(groups > 0 && groups <= 32 && C % groups == 0 && C % 8 == 0 && c1 % 8 == 0,
+           "ls_groupnorm: C=%d groups=%d unsupported", C, groups);
+  const int threads = 256;
+  const int nvec = C / 8;
+  const int RL = nvec <= threads ? threads / nvec : 1;
+  size_t smem = (size_t)2 * RL * C * sizeof(float);
+  if (smem < (size_t)2 * C * sizeof(float)) smem = (size_t)2 * C * sizeof(float);
+  int dev = 0;
+  LS_CUDA(cudaGetDevice(&dev));
+  static int occ_cache[16][8] = {};  // per device, per smem bucket (8 KB steps)
+  int sms = 0;
+  LS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int bucket = (int)((smem + 8191) / 8192);
+  int occ = 0;
+  if (dev < 16 && bucket < 8) {
+    if (occ_cache[dev][bucket] == 0) {
+      int o = 0;
+      LS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, gn_fused_kernel, threads, (size_t)bucket * 8192));
+      occ_cache[dev][bucket] = o > 0 ? o : -1;
+    }
+    occ = occ_cache[dev][bucket];
+  }
+  const int ninst0 = (int)(rows / rows_per_inst);
+  const int capacity = occ > 0 ? occ * sms : 0;
+  if (smem > 48 * 1024 || capacity < ninst0 || dev >= 16) {
+    // cannot guarantee co-residency: two launches
+    int rc = ls_groupnorm_stats(x1, c1, x2, c2, rows, rows_per_inst, groups, stats_scratch, stream);
+    if (rc != 0) return rc;
+    return ls_groupnorm_apply(x1, c1, x2, c2, rows, rows_per_inst, groups, stats_scratch, gamma, beta, eps, silu, y,
+                              stream);
+  }
+  int ninst, chunks, rpc;
+  int target = capacity < 592 ? capacity : 592;
+  gn_chunking(rows, rows_per_inst, target, ninst, chunks, rpc);
+  while (chunks > 1 && (int64_t)chunks * ninst > capacity) {  // gn_chunking rounds up: stay inside one wave
+    rpc += 1;
+    chunks = (rows_per_inst + rpc - 1) / rpc;
+  }
+  LS_CHECK((int64_t)chunks * ninst <= capacity, "ls_groupnorm: %d instances do not fit one wave", ninst);
+  GnScratch& sc = g_gn[dev];
+  const size_t need = (size_t)ninst * chunks * groups * 2;
+  const size_t ntick = (size_t)2 * ninst + 2;
+  if (need > sc.partial_floats || ntick > sc.ntickets) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+    LS_CHECK(cs == cudaStreamCaptureStatusNone, "ls_groupnorm: scratch must be sized by an eager warm-up run");
+    LS_CUDA(cudaDeviceSynchronize());
+    if (need > sc.partial_floats) {
+      if (sc.partial) cudaFree(sc.partial);
+      sc.partial_floats = need > (1u << 20) ? need : (1u << 20);
+      LS_CUDA(cudaMalloc(&sc.partial, sc.partial_floats * sizeof(float)));
+    }
+    if (ntick > sc.ntickets) {
+      if (sc.tickets) cudaFree(sc.tickets);
+      sc.ntickets = ntick > 8192 ? ntick : 8192;
+      LS_CUDA(cudaMalloc(&sc.tickets, sc.ntickets * sizeof(unsigned int)));
+      LS_CUDA(cudaMemset(sc.tickets, 0, sc.ntickets * sizeof(unsigned int)));
+    }
+  }
+  LS_CUDA(launch_k(gn_fused_kernel, dim3(chunks, ninst), dim3(threads), smem, (cudaStream_t)stream,
+                   (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial, sc.tickets,
+                   gamma, beta, eps, silu, (__half*)y));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;

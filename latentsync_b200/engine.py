@@ -221,13 +221,11 @@ class Plan:
         assert self.stats is not None and self.stats_cursor + n <= self.stats.numel(), "GroupNorm stats arena too small"
         sp = self.stats.data_ptr() + self.stats_cursor * 4
         self.stats_cursor += n
-        f1, f2 = self.lib.ls_groupnorm_stats, self.lib.ls_groupnorm_apply
+        fn = self.lib.ls_groupnorm
         g, b = gamma.data_ptr(), beta.data_ptr()
         x2p = x2 or None
-        self._emit(lambda: _chk(f1(x1, c1, x2p, c2, rows, rows_per_inst, groups, sp, _stream()), "ls_groupnorm_stats"),
-                   "gn_stats")
-        self._emit(lambda: _chk(f2(x1, c1, x2p, c2, rows, rows_per_inst, groups, sp, g, b, eps, int(silu), out_ptr,
-                                   _stream()), "ls_groupnorm_apply"), "gn_apply")
+        self._emit(lambda: _chk(fn(x1, c1, x2p, c2, rows, rows_per_inst, groups, g, b, eps, int(silu), sp, out_ptr,
+                                   _stream()), "ls_groupnorm"), "groupnorm")
 
     def layernorm(self, x: int, rows: int, Cc: int, gamma: torch.Tensor, beta: torch.Tensor, out_ptr: int,
                   pe: Optional[torch.Tensor] = None, rows_per_frame: int = 1, nframes: int = 1) -> None:

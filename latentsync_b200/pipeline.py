@@ -184,16 +184,68 @@ class LipsyncPipeline:
         return out.to(weight_dtype)
 
     @torch.no_grad()
+    def denoise_segments(self, segments: Sequence[Dict[str, torch.Tensor]], num_inference_steps: int = 20,
+                         guidance_scale: float = 1.5) -> List[torch.Tensor]:
+        """Denoising loops of SEVERAL independent segments advanced together as one UNet batch (batch order
+        [seg0 uncond, seg0 cond, seg1 uncond, ...]).  Same arithmetic per segment as `denoise_segment` - segments never
+        interact (GroupNorm statistics are per batch element, attention per frame / per pixel) - but the small 8x8 / 4x4
+        levels fill more SMs and every launch is amortised over more rows.  Returns the final latents per segment."""
+        if len(segments) == 1:
+            g = segments[0]
+            return [self.denoise_segment(g["latents"], g.get("audio_embeds"), g["mask_latents"],
+                                         g["masked_image_latents"], g["ref_latents"], num_inference_steps,
+                                         guidance_scale)]
+        unet, sch = self.denoising_unet, self.scheduler
+        dev = unet.device
+        do_cfg = guidance_scale > 1.0
+        nb = 2 if do_cfg else 1
+        n = len(segments)
+        lats = [g["latents"].to(dev, torch.float32).contiguous().clone() for g in segments]
+        _, _, F, h, w = lats[0].shape
+        masks = [g["mask_latents"][:1].to(dev, torch.float32).contiguous() for g in segments]
+        maskeds = [g["masked_image_latents"][:1].to(dev, torch.float32).contiguous() for g in segments]
+        refs = [g["ref_latents"][:1].to(dev, torch.float32).contiguous() for g in segments]
+        S = segments[0]["audio_embeds"].shape[-2] if unet.add_audio_layer else 0
+        plan = unet.plan(nb * n, F, h, w, S)
+        rows_seg = nb * F * h * w
+        if S:
+            buf = plan.audio_in.tensor()
+            buf.zero_()
+            for i, g in enumerate(segments):
+                a = g["audio_embeds"].to(dev, torch.float16).reshape(F * S, -1)
+                r0 = (i * nb + (nb - 1)) * F * S
+                buf[r0:r0 + F * S, : a.shape[1]].copy_(a)
+        sch.set_timesteps(num_inference_steps)
+        lib = L.lib()
+        t_view = plan.t_in.tensor().view(-1)
+        x_stride = rows_seg * plan.x_in.cols * 2  # bytes per segment in the fp16 UNet input
+        e_stride = rows_seg * plan.eps_out.cols * 4
+        for t in sch._host_timesteps:
+            st = torch.cuda.current_stream().cuda_stream
+            for i in range(n):
+                L._check(lib.ls_concat13(lats[i].data_ptr(), masks[i].data_ptr(), maskeds[i].data_ptr(),
+                                         refs[i].data_ptr(), nb, F, h * w, plan.x_in.ptr + i * x_stride, st),
+                         "ls_concat13")
+            t_view.fill_(float(t))
+            plan.replay()
+            a_t, a_p = sch.step_coefficients(t)
+            for i in range(n):
+                L._check(lib.ls_cfg_ddim_step(plan.eps_out.ptr + i * e_stride, plan.eps_out.cols, nb, F, h * w,
+                                              float(guidance_scale), a_t, a_p, lats[i].data_ptr(), None, st),
+                         "ls_cfg_ddim_step")
+        return lats
+
+    @torch.no_grad()
     def run_segments(self, segments: Sequence[Dict[str, torch.Tensor]], num_inference_steps: int = 20,
-                     guidance_scale: float = 1.5) -> List[torch.Tensor]:
+                     guidance_scale: float = 1.5, segments_per_batch: int = 1) -> List[torch.Tensor]:
         """HOT LOOP 1 (lipsync_pipeline.py:500-575) over already-prepared segment inputs (keys as produced by
-        synthetic.segment_inputs / the reference's prepare_* helpers).  Returns one (f,3,H,W) fp32 tensor each."""
+        synthetic.segment_inputs / the reference's prepare_* helpers).  Returns one (f,3,H,W) fp32 tensor each.
+        `segments_per_batch` > 1 advances that many segments of the clip together (see denoise_segments)."""
         frames = []
-        for seg in segments:
-            lat = self.denoise_segment(seg["latents"], seg.get("audio_embeds"), seg["mask_latents"],
-                                       seg["masked_image_latents"], seg["ref_latents"], num_inference_steps,
-                                       guidance_scale)
-            frames.append(self.decode_and_paste(lat, seg["ref_pixel_values"], seg["masks"]))
+        for i0 in range(0, len(segments), max(1, segments_per_batch)):
+            group = segments[i0:i0 + max(1, segments_per_batch)]
+            for seg, lat in zip(group, self.denoise_segments(group, num_inference_steps, guidance_scale)):
+                frames.append(self.decode_and_paste(lat, seg["ref_pixel_values"], seg["masks"]))
         return frames
 
     @staticmethod

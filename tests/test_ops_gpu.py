@@ -223,6 +223,12 @@ def test_groupnorm(c1, c2, rows_per_inst, ninst, silu):
         ref = F.silu(ref)
     ref = ref.permute(0, 2, 1).reshape(rows, C)
     assert rel_l2(out, ref) < 2e-3
+    out2 = torch.empty_like(out)
+    L.groupnorm_fused(x1, c1, x2, c2, rows, rows_per_inst, 32, gamma, beta, 1e-5, silu, out2, stats)
+    assert rel_l2(out2, ref) < 2e-3
+    out3 = torch.empty_like(out)
+    L.groupnorm_fused(x1, c1, x2, c2, rows, rows_per_inst, 32, gamma, beta, 1e-5, silu, out3, stats)
+    assert torch.equal(out2, out3)  # deterministic, and the self-resetting tickets survive a relaunch
 
 
 @pytest.mark.parametrize("C", [320, 640, 1280])
