@@ -374,6 +374,8 @@ static int launch_attn(const AttnKParams& p, cudaStream_t stream) {
   return 0;
 }
 
+int attention_tc_try(const LsAttnArgs* a, cudaStream_t stream);  // attention_tc.cu (tcgen05 path, sq >= 128)
+
 static int attention_impl(const LsAttnArgs* a, cudaStream_t stream) {
   LS_CHECK(a && a->q && a->k && a->v && a->out, "ls_attention: null pointer");
   LS_CHECK(a->batch > 0 && a->heads > 0 && a->sq > 0 && a->skv > 0, "ls_attention: bad sizes");
@@ -381,6 +383,11 @@ static int attention_impl(const LsAttnArgs* a, cudaStream_t stream) {
   LS_CHECK((a->ldq % 8 == 0) && (a->ldk % 8 == 0) && (a->ldv % 8 == 0) && (a->ldo % 2 == 0),
            "ls_attention: leading dims must be multiples of 8");
   LS_CHECK(a->q_inner >= 1 && a->kv_inner >= 1, "ls_attention: inner must be >= 1");
+  LS_CHECK(a->scale > 0.f, "ls_attention: scale must be > 0");
+  {
+    const int rc = attention_tc_try(a, stream);
+    if (rc >= 0) return rc;
+  }
   AttnKParams p;
   p.q = reinterpret_cast<const __half*>(a->q);
   p.k = reinterpret_cast<const __half*>(a->k);
@@ -402,7 +409,6 @@ static int attention_impl(const LsAttnArgs* a, cudaStream_t stream) {
   p.kv_outer = a->kv_outer_stride;
   p.kv_in_stride = a->kv_inner_stride;
   p.kv_seq = a->kv_seq_stride;
-  LS_CHECK(a->scale > 0.f, "ls_attention: scale must be > 0");
   p.scale_log2 = a->scale * kLog2e;
   switch (a->head_dim) {
     case 40: return launch_attn<40>(p, stream);

@@ -1,0 +1,442 @@
+// Flash-style attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) for the long-sequence spatial
+// self-attention of the UNet (attention.py:271: S = H*W = 1024 / 256 / 4096 tokens per frame, head_dim 40 / 80 / 160).
+//
+//   per CTA: one 128-query tile of one (frame, head); loop over 64-key tiles
+//     control warp (1 elected lane): TMA loads of Q / K_j / V_j (4-D maps over [batch][seq][head][d]: the box is 64
+//                                    columns wide, columns >= head_dim and rows >= seq are zero-filled by TMA),
+//                                    S_j = Q K_j^T (tcgen05.mma, both operands K-major, 128B swizzle) -> TMEM,
+//                                    O  += P_j V_j (A = P_j from shared memory, B = V_j MN-major: V is used as it lies
+//                                    in memory, [key][d], no transpose) -> TMEM
+//     4 softmax warps (thread = query row = TMEM lane): tcgen05.ld S_j -> registers, release S early so that
+//                                    S_{j+1} overlaps the exponentials, running max with LAZY rescale (the reference
+//                                    max only moves when it grows by more than 2^8; O in TMEM is then rescaled with
+//                                    tcgen05.ld/st), P_j = exp2(...) as fp16 into the swizzled shared-memory A tile.
+//   The exponentials (MUFU, 16 per clock per SM) bound this kernel, not the tensor pipe: 128 x 64 exp per tile = 512
+//   clocks against 192 clocks of MMA (head_dim 40), so several CTAs are resident per SM to keep the MUFU pipe busy.
+//
+// Replaces F.scaled_dot_product_attention at latentsync/models/attention.py:271 for sq >= 128 (the short sequences -
+// 16 frames of temporal attention, 50 audio tokens, the 8x8 / 4x4 levels - stay on the warp-level kernels of
+// attention.cu, they are launch/latency bound).
+#include "common.cuh"
+#include "../../include/latentsync_b200.h"
+
+#include <atomic>
+#include <stdlib.h>
+#include <string.h>
+
+namespace ls {
+
+extern std::atomic<int64_t> g_launch_count;
+
+struct AttnTcParams {
+  CUtensorMap mapQ, mapK, mapV;
+  __half* o;
+  int ldo;
+  int sq, skv;
+  int64_t o_batch_stride;  // rows
+  int64_t o_seq_stride;    // rows
+  float scale_log2;
+};
+
+constexpr int ATC_BQ = 128;
+constexpr int ATC_BKV = 64;
+constexpr int ATC_THREADS = 160;  // 4 softmax warps + 1 control warp
+constexpr float ATC_RESCALE_THRESHOLD = 8.0f;  // in log2 units: P <= 2^8 stays far inside fp16 range
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major operand, 128-byte swizzle: the tile lies in shared memory as [k][64 MN elements] (128-byte rows, 8-row
+// groups 1024 B apart = stride byte offset); 64-element MN blocks are `lbo_bytes` apart (leading byte offset).
+// Canonical layout Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int D>
+struct AtcCfg {
+  static constexpr int DP = (D + 15) / 16 * 16;        // head_dim padded to the MMA K step / N granularity
+  static constexpr int KS = (DP + 63) / 64;            // 64-column slabs of Q / K / V
+  static constexpr int KSTEPS = DP / 16;               // K = 16 steps of S = Q K^T
+  static constexpr int Q_BYTES = KS * ATC_BQ * 128;
+  static constexpr int KV_SLAB = ATC_BKV * 128;
+  static constexpr int KV_BYTES = KS * KV_SLAB;        // one stage of K (or V)
+  static constexpr int P_BYTES = ATC_BQ * 128;         // 128 rows x 64 keys fp16
+  static constexpr int TILE_BYTES = Q_BYTES + 4 * KV_BYTES + P_BYTES;
+  static constexpr int SMEM = TILE_BYTES + 1024 /*alignment*/ + 128 /*barriers*/;
+  static constexpr int TMEM_NEED = ATC_BKV + DP;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static constexpr int CTAS_PER_SM = (D <= 40) ? 3 : (D <= 80 ? 2 : 1);
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  using Cfg = AtcCfg<D>;
+  constexpr int DP = Cfg::DP, KS = Cfg::KS, KSTEPS = Cfg::KSTEPS;
+  pdl_prologue();
+  extern __shared__ uint8_t atc_smem_raw[];
+  const uint32_t raw = smem_u32(atc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = atc_smem_raw + (base - raw);
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + Cfg::Q_BYTES;
+  const uint32_t sV = sK + 2 * Cfg::KV_BYTES;
+  const uint32_t sP = sV + 2 * Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Cfg::TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* v_full = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.skv + ATC_BKV - 1) / ATC_BKV;
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(k_full + 0, 1);
+    mbar_init(k_full + 1, 1);
+    mbar_init(v_full + 0, 1);
+    mbar_init(v_full + 1, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem;              // columns [0, 64): scores
+  const uint32_t tO = tmem + ATC_BKV;    // columns [64, 64 + DP): output accumulator
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ control: TMA producer + MMA issuer
+      tma_prefetch_desc(&p.mapQ);
+      tma_prefetch_desc(&p.mapK);
+      tma_prefetch_desc(&p.mapV);
+      constexpr uint32_t idesc_s = (1u << 4) | (uint32_t(ATC_BKV >> 3) << 17) | (uint32_t(ATC_BQ >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 16) | (uint32_t(DP >> 3) << 17) | (uint32_t(ATC_BQ >> 4) << 24);
+      auto load_k = [&](int j, int st) {
+        mbar_expect_tx(k_full + st, Cfg::KV_BYTES);
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+          tma_load_4d(sm + (sK - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapK, k_full + st, s * 64, h,
+                      j * ATC_BKV, b);
+      };
+      auto load_v = [&](int j, int st) {
+        mbar_expect_tx(v_full + st, Cfg::KV_BYTES);
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+          tma_load_4d(sm + (sV - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapV, v_full + st, s * 64, h,
+                      j * ATC_BKV, b);
+      };
+      auto issue_s = [&](int st) {
+        // S = Q K^T: KSTEPS steps of K = 16; step ks lies in slab ks / 4 at byte offset (ks % 4) * 32
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t qa = sQ + (ks >> 2) * (ATC_BQ * 128) + (ks & 3) * 32;
+          const uint32_t ka = sK + st * Cfg::KV_BYTES + (ks >> 2) * Cfg::KV_SLAB + (ks & 3) * 32;
+          umma_f16_ss(tS, umma_desc_sw128(qa), umma_desc_sw128(ka), idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      };
+      auto issue_pv = [&](int st, uint32_t accumulate) {
+        // O += P V: 4 steps of 16 keys; A = P [128][64 keys] K-major, B = V [64 keys][DP] MN-major
+#pragma unroll
+        for (int kk = 0; kk < ATC_BKV / 16; ++kk) {
+          const uint32_t pa = sP + kk * 32;
+          const uint32_t va = sV + st * Cfg::KV_BYTES + kk * 16 * 128;
+          umma_f16_ss(tO, umma_desc_sw128(pa), umma_desc_mn_sw128(va, Cfg::KV_SLAB), idesc_o,
+                      (accumulate | (uint32_t)(kk > 0)) ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+      };
+
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int s = 0; s < KS; ++s)
+        tma_load_4d(sm + (sQ - base) + s * (ATC_BQ * 128), &p.mapQ, q_full, s * 64, h, qt * ATC_BQ, b);
+      load_k(0, 0);
+      load_v(0, 0);
+      if (n_tiles > 1) {
+        load_k(1, 1);
+        load_v(1, 1);
+      }
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full + 0, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (uint32_t)(j & 1);
+        if (j + 2 < n_tiles) {
+          mbar_wait(s_full, ph);  // S_j finished reading K stage st
+          load_k(j + 2, st);
+        }
+        if (j + 1 < n_tiles) {
+          mbar_wait(k_full + (st ^ 1), (uint32_t)(((j + 1) >> 1) & 1));
+          mbar_wait(s_empty, ph);  // the softmax warps hold S_j in registers
+          tc_fence_after();
+          issue_s(st ^ 1);
+        }
+        mbar_wait(v_full + st, (uint32_t)((j >> 1) & 1));
+        mbar_wait(p_full, ph);  // P_j is in shared memory, O has been rescaled if needed
+        tc_fence_after();
+        issue_pv(st, j > 0 ? 1u : 0u);
+        if (j + 2 < n_tiles) {
+          mbar_wait(pv_done, ph);  // P V_j finished reading V stage st
+          load_v(j + 2, st);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // -------------------------------------------------------------------------- softmax: thread = query row
+    const int r = tid;  // 0..127 = TMEM lane
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float sl = p.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    const uint32_t p_row = sP + r * 128;
+    const int rx = r & 7;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = (uint32_t)(j & 1);
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      uint32_t sv[2][32];
+      tmem_ld_32x32(tS + lane_off, sv[0]);
+      tmem_ld_32x32(tS + lane_off + 32, sv[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      float* s = reinterpret_cast<float*>(&sv[0][0]);
+      const int kbase = j * ATC_BKV;
+      if (kbase + ATC_BKV > p.skv) {
+#pragma unroll
+        for (int c = 0; c < ATC_BKV; ++c)
+          if (kbase + c >= p.skv) s[c] = -INFINITY;
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < ATC_BKV; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const bool grow = (mx - m_ref) * sl > ATC_RESCALE_THRESHOLD;  // first tile: m_ref = -inf -> true
+      bool waited_pv = false;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_ref, mx);
+        const float alpha = ex2_approx((m_ref - m_new) * sl);  // 0 on the first tile
+        m_ref = m_new;
+        l *= alpha;
+        if (j > 0) {
+          mbar_wait(pv_done, (uint32_t)((j - 1) & 1));  // O holds tiles 0..j-1
+          tc_fence_after();
+          waited_pv = true;
+#pragma unroll
+          for (int c = 0; c < DP; c += 16) {
+            uint32_t ov[16];
+            tmem_ld_32x16(tO + lane_off + c, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x16(tO + lane_off + c, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mb = m_ref * sl;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[ATC_BKV / 2];
+#pragma unroll
+      for (int c = 0; c < ATC_BKV; c += 2) {
+        const float e0 = ex2_approx(fmaf(s[c], sl, -mb));
+        const float e1 = ex2_approx(fmaf(s[c + 1], sl, -mb));
+        sum0 += e0;
+        sum1 += e1;
+        pk[c >> 1] = pack_half2(e0, e1);
+      }
+      l += sum0 + sum1;
+      if (j > 0 && !waited_pv) mbar_wait(pv_done, (uint32_t)((j - 1) & 1));  // P V_{j-1} has read the P tile
+#pragma unroll
+      for (int c = 0; c < ATC_BKV / 8; ++c)
+        st_shared_v4(p_row + ((c ^ rx) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> fp16 -> global (each thread owns one output row of D contiguous halfs)
+    mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int qrow = qt * ATC_BQ + r;
+    __half* dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)qrow * p.o_seq_stride) * p.ldo + h * D;
+#pragma unroll
+    for (int c = 0; c < DP; c += 16) {
+      uint32_t ov[16];
+      tmem_ld_32x16(tO + lane_off + c, ov);
+      tmem_ld_wait();
+      if (qrow < p.sq) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          if (c + i < D) {
+            uint4 pk4;
+            pk4.x = pack_half2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+            pk4.y = pack_half2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+            pk4.z = pack_half2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+            pk4.w = pack_half2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c + i) = pk4;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled atc_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// [batch][seq][head][d] view of a token matrix: element (b, s, h, c) at ptr + ((b*outer + s*seq) * ld + h*D + c)
+static int encode_bshd(PFN_tmapEncodeTiled encode, CUtensorMap* map, const void* ptr, int D, int heads, int seq,
+                       int batch, int64_t ld, int64_t seq_stride, int64_t outer_stride, int box_rows, const char* what) {
+  cuuint64_t gdim[4] = {(cuuint64_t)D, (cuuint64_t)heads, (cuuint64_t)seq, (cuuint64_t)batch};
+  cuuint64_t gstr[3] = {(cuuint64_t)D * 2, (cuuint64_t)(seq_stride * ld) * 2, (cuuint64_t)(outer_stride * ld) * 2};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LS_CHECK(r == CUDA_SUCCESS, "ls_attention: cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+  return 0;
+}
+
+static bool atc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LS_ATTN_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int D>
+static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
+  using Cfg = AtcCfg<D>;
+  PFN_tmapEncodeTiled encode = atc_encode_fn();
+  LS_CHECK(encode != nullptr, "ls_attention: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  AttnTcParams p;
+  memset(&p, 0, sizeof(p));
+  if (encode_bshd(encode, &p.mapQ, a->q, D, a->heads, a->sq, a->batch, a->ldq, a->q_seq_stride, a->q_outer_stride,
+                  ATC_BQ, "Q"))
+    return 1;
+  if (encode_bshd(encode, &p.mapK, a->k, D, a->heads, a->skv, a->batch, a->ldk, a->kv_seq_stride, a->kv_outer_stride,
+                  ATC_BKV, "K"))
+    return 1;
+  if (encode_bshd(encode, &p.mapV, a->v, D, a->heads, a->skv, a->batch, a->ldv, a->kv_seq_stride, a->kv_outer_stride,
+                  ATC_BKV, "V"))
+    return 1;
+  p.o = reinterpret_cast<__half*>(a->out);
+  p.ldo = a->ldo;
+  p.sq = a->sq;
+  p.skv = a->skv;
+  p.o_batch_stride = a->q_outer_stride;
+  p.o_seq_stride = a->q_seq_stride;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LS_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((a->sq + ATC_BQ - 1) / ATC_BQ, a->heads, a->batch);
+  LS_CUDA(launch_k(attn_tc_kernel<D>, grid, dim3(ATC_THREADS), (size_t)Cfg::SMEM, stream, p));
+  LS_CUDA(cudaGetLastError());
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// returns -1 when the problem is not one for this path (the caller then uses the warp-level kernels)
+int attention_tc_try(const LsAttnArgs* a, cudaStream_t stream) {
+  if (!atc_enabled()) return -1;
+  if (a->q_inner != 1 || a->kv_inner != 1) return -1;      // strided batches (temporal attention)
+  if (a->sq < ATC_BQ || a->skv < ATC_BKV) return -1;        // short sequences
+  if (a->batch > 65535 || a->heads > 65535) return -1;
+  if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8)) return -1;
+  if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
+       reinterpret_cast<uintptr_t>(a->out)) & 15)
+    return -1;
+  switch (a->head_dim) {
+    case 40: return launch_attn_tc<40>(a, stream);
+    case 80: return launch_attn_tc<80>(a, stream);
+    case 160: return launch_attn_tc<160>(a, stream);
+    default: return -1;
+  }
+}
+
+}  // namespace ls

@@ -267,7 +267,9 @@ def test_softmax_and_transpose():
 @pytest.mark.parametrize(
     "batch,heads,d,sq,skv",
     [(4, 8, 40, 1024, 1024), (4, 8, 80, 256, 256), (4, 8, 160, 64, 64), (3, 8, 160, 16, 16), (4, 8, 40, 1024, 50),
-     (4, 8, 80, 256, 50), (2, 8, 160, 64, 50), (2, 8, 160, 16, 50), (2, 8, 40, 100, 77), (1, 8, 40, 4096, 4096)],
+     (4, 8, 80, 256, 50), (2, 8, 160, 64, 50), (2, 8, 160, 16, 50), (2, 8, 40, 100, 77), (1, 8, 40, 4096, 4096),
+     # ragged shapes on the tcgen05 path (sq >= 128, skv >= 64): partial query tiles, masked keys in the last tile
+     (2, 8, 40, 300, 200), (3, 8, 80, 200, 130), (2, 8, 160, 256, 256), (2, 8, 160, 130, 65), (2, 8, 80, 1024, 1024)],
 )
 def test_attention(batch, heads, d, sq, skv):
     L = _ops()
@@ -283,6 +285,25 @@ def test_attention(batch, heads, d, sq, skv):
     vh = v.float().reshape(batch, skv, heads, d).transpose(1, 2)
     ref = torch.softmax(qh @ kh.transpose(-1, -2), -1) @ vh
     ref = ref.transpose(1, 2).reshape(batch * sq, C)
+    assert rel_l2(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("d,S", [(40, 1024), (80, 256), (160, 256)])
+def test_attention_packed_qkv(d, S):
+    """spatial self-attention as the UNet plan calls it (engine._transformer): q, k, v are column blocks of one
+    [rows, 3C] matrix (leading dimension 3C), the output overwrites a [rows, C] buffer; score magnitudes like the
+    network's (|s| up to ~60 before the softmax scale) exercise the lazy rescale of the tcgen05 kernel."""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(15)
+    batch, heads = 3, 8
+    C = heads * d
+    rows = batch * S
+    qkv = (torch.randn(rows, 3 * C, generator=g) * 1.7).half().to(DEV)
+    out = torch.empty(rows, C, dtype=torch.float16, device=DEV)
+    L.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, 3 * C, 3 * C, 3 * C, C, batch, heads, d, S, S)
+    x = qkv.float().reshape(batch, S, 3, heads, d).permute(2, 0, 3, 1, 4)  # (3, B, h, S, d)
+    ref = torch.softmax(x[0] @ x[1].transpose(-1, -2) * d ** -0.5, -1) @ x[2]
+    ref = ref.permute(0, 2, 1, 3).reshape(rows, C)
     assert rel_l2(out, ref) < 3e-3
 
 
