@@ -36,7 +36,16 @@ struct AttnTcParams {
   int64_t o_batch_stride;  // rows
   int64_t o_seq_stride;    // rows
   float scale_log2;
+  long long* probe;  // LS_ATC_PROBE builds only: clock64 stamps [cta][tile][8]
 };
+
+#ifdef LS_ATC_PROBE
+#define ATC_STAMP(slot) \
+  do { if (p.probe && blockIdx.y == 0 && (blockIdx.z == 0 || blockIdx.z == 16)) \
+      p.probe[(((blockIdx.z ? 8 : 0) + blockIdx.x) * 64 + j) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define ATC_STAMP(slot) do {} while (0)
+#endif
 
 constexpr int ATC_BQ = 128;
 constexpr int ATC_BKV = 64;
@@ -138,8 +147,8 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
     mbar_init(v_full + 0, 1);
     mbar_init(v_full + 1, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -204,35 +213,37 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
         tma_load_4d(sm + (sQ - base) + s * (ATC_BQ * 128), &p.mapQ, q_full, s * 64, h, qt * ATC_BQ, b);
       load_k(0, 0);
       load_v(0, 0);
-      if (n_tiles > 1) {
-        load_k(1, 1);
-        load_v(1, 1);
-      }
+      if (n_tiles > 1) load_k(1, 1);
       mbar_wait(q_full, 0);
       mbar_wait(k_full + 0, 0);
       tc_fence_after();
       issue_s(0);
+      // Per key tile: 4 barrier waits.  Completion of earlier tensor work is inferred instead of waited for:
+      //   s_empty(j) (the softmax warps hold S_j)      => S_j is complete      => K stage j&1 can be refilled
+      //   p_full(j)  (they waited for P V_{j-1} first) => P V_{j-1} is complete => V stage (j+1)&1 can be refilled
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         const uint32_t ph = (uint32_t)(j & 1);
-        if (j + 2 < n_tiles) {
-          mbar_wait(s_full, ph);  // S_j finished reading K stage st
-          load_k(j + 2, st);
-        }
+        ATC_STAMP(8);
         if (j + 1 < n_tiles) {
+          mbar_wait(s_empty, ph);
+          ATC_STAMP(9);
+          if (j + 2 < n_tiles) load_k(j + 2, st);
+          ATC_STAMP(10);
           mbar_wait(k_full + (st ^ 1), (uint32_t)(((j + 1) >> 1) & 1));
-          mbar_wait(s_empty, ph);  // the softmax warps hold S_j in registers
           tc_fence_after();
+          ATC_STAMP(0);
           issue_s(st ^ 1);
+          ATC_STAMP(12);
         }
+        mbar_wait(p_full, ph);
+        ATC_STAMP(11);
+        if (j + 1 < n_tiles) load_v(j + 1, st ^ 1);
         mbar_wait(v_full + st, (uint32_t)((j >> 1) & 1));
-        mbar_wait(p_full, ph);  // P_j is in shared memory, O has been rescaled if needed
         tc_fence_after();
+        ATC_STAMP(1);
         issue_pv(st, j > 0 ? 1u : 0u);
-        if (j + 2 < n_tiles) {
-          mbar_wait(pv_done, ph);  // P V_j finished reading V stage st
-          load_v(j + 2, st);
-        }
+        ATC_STAMP(14);
       }
     }
     __syncwarp();
@@ -246,14 +257,18 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
     const int rx = r & 7;
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = (uint32_t)(j & 1);
+      if (tid == 0) ATC_STAMP(3);
       mbar_wait(s_full, ph);
       tc_fence_after();
+      if (tid == 0) ATC_STAMP(4);
       uint32_t sv[2][32];
       tmem_ld_32x32(tS + lane_off, sv[0]);
       tmem_ld_32x32(tS + lane_off + 32, sv[1]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_empty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      if (tid == 0) ATC_STAMP(5);
       float* s = reinterpret_cast<float*>(&sv[0][0]);
       const int kbase = j * ATC_BKV;
       if (kbase + ATC_BKV > p.skv) {
@@ -305,13 +320,16 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
         pk[c >> 1] = pack_half2(e0, e1);
       }
       l += sum0 + sum1;
+      if (tid == 0) ATC_STAMP(6);
       if (j > 0 && !waited_pv) mbar_wait(pv_done, (uint32_t)((j - 1) & 1));  // P V_{j-1} has read the P tile
 #pragma unroll
       for (int c = 0; c < ATC_BKV / 8; ++c)
         st_shared_v4(p_row + ((c ^ rx) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (tid == 0) ATC_STAMP(7);
     }
     // epilogue: O / l -> fp16 -> global (each thread owns one output row of D contiguous halfs)
     mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
@@ -386,6 +404,15 @@ static bool atc_enabled() {
   return v == 1;
 }
 
+#ifdef LS_ATC_PROBE
+static long long* g_atc_probe = nullptr;
+extern "C" int ls_atc_probe_read(long long* host, int n) {
+  if (!g_atc_probe) return 1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(host, g_atc_probe, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
+#endif
+
 template <int D>
 static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
   using Cfg = AtcCfg<D>;
@@ -409,6 +436,17 @@ static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
   p.o_batch_stride = a->q_outer_stride;
   p.o_seq_stride = a->q_seq_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+#ifdef LS_ATC_PROBE
+  {
+    static long long* probe_buf = nullptr;
+    if (!probe_buf) {
+      cudaMalloc(&probe_buf, 16 * 64 * 16 * sizeof(long long));
+      cudaMemset(probe_buf, 0, 16 * 64 * 16 * sizeof(long long));
+    }
+    p.probe = probe_buf;
+    g_atc_probe = probe_buf;
+  }
+#endif
   static bool attr_set = false;
   if (!attr_set) {
     LS_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
