@@ -44,24 +44,52 @@ constexpr int GEMM_THREADS = 320;
 constexpr int MAX_STAGES = 8;
 constexpr int PRODUCER_WARP = 8;
 constexpr int MMA_WARP = 9;
-constexpr int SLAB_BYTES = BM * 64;            // 128 rows x 32 fp16 columns, SWIZZLE_64B
-constexpr int STAGING_BYTES = 4 * SLAB_BYTES;  // 2 epilogue groups x 2 slabs (ping-pong)
+constexpr int WSLAB_BYTES = 32 * 64;           // one warp's share of a slab: 32 rows x 32 fp16 columns, SWIZZLE_64B
+constexpr int STAGING_BYTES = 8 * 2 * WSLAB_BYTES;  // 8 epilogue warps x (32 rows x 128 bytes): a pair of slabs each
 constexpr int BIAS_BYTES = 2 * 256 * 4;        // one bias row of 256 floats per epilogue group
 constexpr int ACC_COLS = 256;                  // TMEM columns per accumulator
 constexpr int TMEM_COLS = 512;                 // two accumulators: the whole TMEM (one CTA per SM anyway)
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address (-> pair leader)
 
+// n / d for 0 <= n < 2^31 without the ~40-instruction integer-division sequence (the epilogue warps decode a tile per
+// loop trip; the probes showed ~1800 clocks between the last slab of one tile and the first instruction after the
+// decode of the next).  Magic numbers by the round-up method: q = umulhi(n, mul) >> shr, d == 1 handled apart.
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) {
+    f.mul = 0;
+    f.shr = 0;
+    f.d = 1;
+    return f;
+  }
+  uint32_t lg = 0;
+  while ((1ull << lg) < d) ++lg;
+  const uint32_t pw = 31 + lg;
+  f.mul = (uint32_t)(((1ull << pw) + d - 1) / d);
+  f.shr = pw - 32;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+
 struct GemmKParams {
   CUtensorMap mapA[LS_GEMM_MAX_SEG];
   CUtensorMap mapB;
-  CUtensorMap mapOut;  // fp16 [M][N_out] output, box 32 columns x 128 rows, SWIZZLE_64B (valid iff tma_store)
+  CUtensorMap mapOut;    // fp16 [M][N_out] output, box 64 columns x 32 rows (one warp's slab pair), SWIZZLE_128B
+  CUtensorMap mapOut32;  // same tensor, box 32 columns x 32 rows (trailing single slab of an odd count), SWIZZLE_64B
   int nseg;
   int seg_taps[LS_GEMM_MAX_SEG];
   int seg_cblk[LS_GEMM_MAX_SEG];
   int bw, bh, bn;  // TMA box in pixels: bw * bh * bn == 128
   int H, W, nimg;
   int tiles_x, tiles_y;
+  FastDiv fd_tiles_x, fd_tiles_y, fd_n_tiles, fd_splits, fd_bias_div;
   int m_tiles, n_tiles, num_kb;
   int N;
   int BN;  // tile width (multiple of 32, <= 256)
@@ -243,10 +271,10 @@ __device__ __forceinline__ uint32_t produce_kblock(uint32_t sa, uint32_t sb, con
 }
 
 __device__ __forceinline__ void decode_m_tile(const GemmKParams& p, int mt, int& x0, int& y0, int& i0) {
-  const int tx = mt % p.tiles_x;
-  const int rest = mt / p.tiles_x;
-  const int ty = rest % p.tiles_y;
-  const int tn = rest / p.tiles_y;
+  const int rest = (int)fdiv((uint32_t)mt, p.fd_tiles_x);
+  const int tx = mt - rest * p.tiles_x;
+  const int tn = (int)fdiv((uint32_t)rest, p.fd_tiles_y);
+  const int ty = rest - tn * p.tiles_y;
   x0 = tx * p.bw;
   y0 = ty * p.bh;
   i0 = tn * p.bn;
@@ -364,7 +392,10 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   if (warp == PRODUCER_WARP && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.mapA[s]);
     tma_prefetch_desc(&p.mapB);
-    if (p.tma_store) tma_prefetch_desc(&p.mapOut);
+    if (p.tma_store) {
+      tma_prefetch_desc(&p.mapOut);
+      tma_prefetch_desc(&p.mapOut32);
+    }
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -514,29 +545,30 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
     if (p.tma_store) {
       // Latency-tolerant epilogue: the tile's bias row goes to smem and ALL residual fragments of the group's slabs
       // are requested before waiting for the accumulator, so global-load latency hides behind the main loop.
-      const bool issuer = (warp == 4 * group) && lane == 0;
-      uint8_t* my_stage = staging + group * 2 * SLAB_BYTES;
+      // Every warp stages and stores its own 32 rows of a slab (two 2 KB buffers, ping-pong): no block barrier and no
+      // wait for the PREVIOUS store per slab.  (With one store per 128-row slab issued behind a 128-thread barrier
+      // and a wait on the preceding store, each slab cost ~1500 clocks of latency: a K = 64 GEMM took as long as K = 320.)
+      uint8_t* my_stage = staging + warp * 2 * WSLAB_BYTES;  // 32 rows x 128 bytes
       constexpr int NSLAB_MAX = 4;  // slabs per group at BN = 256
       const int nslab = geglu ? BN / 64 : BN / 32;
       const int n_out_total = geglu ? p.N / 2 : p.N;
       const int gtid = (warp - 4 * group) * 32 + lane;  // 0..127 inside the group
-      uint32_t slab_count = 0;
       int lt = 0;
       // bias row of the NEXT tile is fetched into registers one tile ahead and parked in a double-buffered smem row, so
       // its global-load latency never sits on the epilogue's critical path (ncu: 9 % of the stall samples before)
       float bias_next[2] = {0.f, 0.f};
       auto fetch_bias = [&](int w_next) {
-        const int tile = w_next / p.splits;
         if (w_next >= total_work || p.bias == nullptr) {
           bias_next[0] = bias_next[1] = 0.f;
           return;
         }
-        const int mu = tile / p.n_tiles;
+        const int tile = (int)fdiv((uint32_t)w_next, p.fd_splits);
+        const int mu = (int)fdiv((uint32_t)tile, p.fd_n_tiles);
         const int nt = tile - mu * p.n_tiles;
         int x0, y0, i0;
         decode_m_tile(p, mu * CTAS + rank, x0, y0, i0);
         const int64_t m0 = ((int64_t)i0 * p.H + y0) * p.W + x0;
-        const int64_t brow_i = (p.bias_div > 0 && m0 < p.M) ? (m0 / p.bias_div) : 0;
+        const int64_t brow_i = (p.bias_div > 0 && m0 < p.M) ? (int64_t)fdiv((uint32_t)m0, p.fd_bias_div) : 0;  // M < 2^31 here
         const float* brow = p.bias + brow_i * (int64_t)p.bias_ld + nt * BN;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -545,12 +577,21 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         }
       };
       fetch_bias(unit);
+#ifdef LS_GEMM_PROBE
+      long long ep[5][12];
+      for (int i = 0; i < 5; ++i)
+        for (int k = 0; k < 12; ++k) ep[i][k] = 0;
+      const long long ep_t0 = clock64();
+#define EP_STAMP(k) do { if (lt < 4) ep[lt][k] = clock64() - ep_t0; } while (0)
+#else
+#define EP_STAMP(k) do {} while (0)
+#endif
       for (int w = unit; w < total_work; w += nunits, ++lt) {
-        const int tile = w / p.splits;
+        const int tile = (int)fdiv((uint32_t)w, p.fd_splits);
         const int sp = w - tile * p.splits;
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1u;
-        const int mu = tile / p.n_tiles;
+        const int mu = (int)fdiv((uint32_t)tile, p.fd_n_tiles);
         const int nt = tile - mu * p.n_tiles;
         const int mt = mu * CTAS + rank;
         int x0, y0, i0;
@@ -559,8 +600,13 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         const int64_t m = m0 + r;
         const bool row_ok = m < p.M;
         const bool tile_ok = m0 < p.M;
-        const int g0 = (group + lt) & 1;  // slab parity of this group alternates per tile: 5 slabs = 3 + 2, then 2 + 3
-        const int last_j = g0 + ((nslab - 1 - g0) / 2) * 2;  // last slab this group handles
+        EP_STAMP(8);
+        const int g0 = (group + lt) & 1;  // split-K parking: slab parity of this group alternates per tile
+        // normal path: contiguous slab range; with an odd slab count the larger half alternates (5 = 3 + 2, then 2 + 3)
+        const int n_first = ((lt & 1) == 0) ? (nslab + 1) / 2 : nslab / 2;
+        const int j_lo = group == 0 ? 0 : n_first;
+        const int j_hi = group == 0 ? n_first : nslab;
+        const int n_mine = j_hi - j_lo;  // slabs are stored in pairs from j_lo on, an odd count leaves a single
         // (1) this tile's bias row (host guarantees one row per tile: bias_div % 128 == 0) -> the group's smem row.  Its
         //     previous contents were last read before the final slab barrier of the previous tile.
         float* my_bias = bias_sm + group * 256;
@@ -569,9 +615,9 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         // (2) residual fragments: two slabs in flight (a rolling pair of register buffers)
         uint4 res[2][4];
         auto fetch_res = [&](int s, uint4 (&dst)[4]) {
-          const int j = g0 + 2 * s;
+          const int j = j_lo + s;
           const int ncol0 = nt * BN + j * 32;
-          if (p.residual != nullptr && j < nslab && row_ok && ncol0 + 32 <= n_out_total) {
+          if (p.residual != nullptr && j < j_hi && row_ok && ncol0 + 32 <= n_out_total) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * (int64_t)p.ldr + ncol0);
 #pragma unroll
             for (int e = 0; e < 4; ++e) dst[e] = __ldg(rp + e);
@@ -580,12 +626,17 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             for (int e = 0; e < 4; ++e) dst[e] = make_uint4(0u, 0u, 0u, 0u);
           }
         };
+        EP_STAMP(9);
         fetch_res(0, res[0]);
         fetch_res(1, res[1]);
+        EP_STAMP(10);
         fetch_bias(w + nunits);  // (3) next work item's bias row -> registers
+        EP_STAMP(0);
         named_bar_sync(1 + group, 128);  // bias row visible to the group
+        EP_STAMP(1);
         mbar_wait_relaxed(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        EP_STAMP(2);
         const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
         bool released = false;
         if (p.splits > 1) {
@@ -692,10 +743,16 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           }
           continue;
         }
+        // Normal path.  The group owns a CONTIGUOUS range of slab pairs (the larger half alternates between the groups
+        // from tile to tile); a pair (64 output columns = one 128-byte line per row) is staged in the warp's own 4 KB
+        // buffer (128-byte swizzle) and leaves with ONE TMA store per warp.  Measured (clock64 probes, K = 64 so that
+        // only the epilogue counts): a store costs its issuer ~450 clocks whatever the box, so 32-column boxes
+        // (64-byte rows) made the TMA unit the bound of every short-K launch at ~16 B/clk/SM; coalesced st.global
+        // from the staging buffer was slower still (15.0 vs 11.5 us at M = 32768, N = 320).
 #pragma unroll
         for (int s = 0; s < NSLAB_MAX; ++s) {
-          const int j = g0 + 2 * s;
-          if (j >= nslab) break;
+          const int j = j_lo + s;
+          if (j >= j_hi) break;
           const int ncol0 = geglu ? nt * (BN / 2) + j * 32 : nt * BN + j * 32;  // first output column of the slab
           if (ncol0 >= n_out_total) break;  // this and all later slabs lie beyond N (uniform over the group)
           uint32_t v[32];
@@ -729,7 +786,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
                   (__uint_as_float(v[e4 * 4 + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[e4 * 4 + 3]) + bg.w);
             }
           }
-          if (j == last_j) {
+          if (j == j_hi - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
@@ -759,35 +816,50 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) f[e] = silu_f(f[e]);
           }
-          // stage the slab: row r is 64 bytes, 16-byte chunk c lives at position c ^ ((r >> 1) & 3)  (SWIZZLE_64B)
-          uint8_t* slab = my_stage + (slab_count & 1u) * SLAB_BYTES;
-          ++slab_count;
-          const int sw = (r >> 1) & 3;
+          // stage.  Pair: row `lane` of the warp's buffer is 128 bytes, 16-byte chunk c sits at c ^ (lane & 7)
+          // (SWIZZLE_128B).  Trailing single slab: 64-byte rows, chunk c at c ^ ((lane >> 1) & 3) (SWIZZLE_64B).
+          const int half_sel = s & 1;
+          const bool single = (half_sel == 0) && (s == n_mine - 1);
+          if (half_sel == 0) {  // the previous store has finished reading the buffer
+            if (lane == 0) bulk_wait_group_read<0>();
+            __syncwarp();
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 u;
             __half2* h2 = reinterpret_cast<__half2*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1]);
-            *reinterpret_cast<uint4*>(slab + r * 64 + ((c ^ sw) << 4)) = u;
+            uint8_t* dst = single ? my_stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)
+                                  : my_stage + lane * 128 + (((half_sel * 4 + c) ^ (lane & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = u;
           }
-          fence_proxy_async_smem();
-          // every store issued before this slab has finished READING its smem => the other slab may be overwritten
-          // once the group passes the barrier below
-          if (issuer) bulk_wait_group_read<0>();
-          named_bar_sync(1 + group, 128);
-          if (issuer && tile_ok) {
-            tma_store_2d(&p.mapOut, slab, ncol0, (int)m0);
-            bulk_commit_group();
+          EP_STAMP(3 + s);
+          if (half_sel == 1 || single || ncol0 + 32 >= n_out_total) {
+            // staged: one TMA store of the warp's 32 rows x 64 (32) columns; columns >= N and rows >= M are clipped
+            // by the TMA unit.  128-byte rows: half as many row requests per byte as a 32-column box.
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && m0 + q * 32 < p.M) {
+              tma_store_2d(single ? &p.mapOut32 : &p.mapOut, my_stage, ncol0 - half_sel * 32, (int)(m0 + q * 32));
+              bulk_commit_group();
+            }
           }
         }
+        EP_STAMP(7);
+        named_bar_sync(1 + group, 128);  // every warp of the group has read the bias row: the next tile may overwrite it
         if (!released) {  // group had no slab inside N for this tile: still hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
         }
       }
-      if (issuer) bulk_wait_group_read<0>();
+#ifdef LS_GEMM_PROBE
+      if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 3))
+        for (int i = 0; i < 4; ++i)
+          printf("gemm probe: epilogue warp %d tile %d: decoded %lld bias_st %lld res %lld top %lld bias_bar %lld acc_ready %lld slabs %lld %lld %lld %lld stored %lld\n",
+                 warp, i, ep[i][8], ep[i][9], ep[i][10], ep[i][0], ep[i][1], ep[i][2], ep[i][3], ep[i][4], ep[i][5], ep[i][6], ep[i][7]);
+#endif
     } else if (group == 0) {
       // legacy path (fp32 output / ragged geometry / narrow leading dimension): per-thread direct global stores
       const int ix = r % p.bw;
@@ -1125,17 +1197,28 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
 
   const int n_out = geglu ? a->N / 2 : a->N;
   if (p.tma_store) {
+    const int n_out = geglu ? a->N / 2 : a->N;
     cuuint64_t gdim[2] = {(cuuint64_t)n_out, (cuuint64_t)M};
     cuuint64_t gstr[1] = {(cuuint64_t)a->ldo * 2};
-    cuuint32_t box[2] = {32, (cuuint32_t)BM};
+    cuuint32_t box[2] = {64, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&p.mapOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->out, gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LS_CHECK(r == CUDA_SUCCESS, "ls_gemm: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+    cuuint32_t box32[2] = {32, 32};
+    r = encode(&p.mapOut32, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->out, gdim, gstr, box32, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LS_CHECK(r == CUDA_SUCCESS, "ls_gemm: cuTensorMapEncodeTiled(out32) failed with %d", (int)r);
   }
   p.bias = a->bias;
   p.bias_div = a->bias_div;
+  p.fd_tiles_x = make_fastdiv((uint32_t)p.tiles_x);
+  p.fd_tiles_y = make_fastdiv((uint32_t)p.tiles_y);
+  p.fd_n_tiles = make_fastdiv((uint32_t)p.n_tiles);
+  p.fd_splits = make_fastdiv((uint32_t)p.splits);
+  p.fd_bias_div = make_fastdiv((uint32_t)(a->bias_div > 0 ? a->bias_div : 1));
   p.bias_ld = a->bias_ld > 0 ? a->bias_ld : a->N;
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.ldr = a->ldr;
