@@ -161,6 +161,16 @@ int ls_cl_to_ncfhw(const float* x, int32_t ld, int32_t B, int32_t C, int32_t F, 
 int ls_upsample2x(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t C, void* y, void* stream);
 /* explicit im2col for the 3x3 stride-2 pad-1 Downsample3D conv (resnet.py:89): out [nimg*(H/2)*(W/2)][9*C]. */
 int ls_im2col_s2(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t C, void* y, void* stream);
+/* same with `pad_before` in {0, 1} zero rows/columns before the image (the window always extends to 2*(H/2)+1-pad):
+ * pad_before = 0 is diffusers' Downsample2D(padding=0) of the AutoencoderKL encoder - F.pad(x, (0, 1, 0, 1)) then a
+ * 3x3 stride-2 convolution (reached from vae.encode, lipsync_pipeline.py:298,315). */
+int ls_im2col_s2_pad(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t C, int32_t pad_before, void* y,
+                     void* stream);
+/* DiagonalGaussianDistribution.sample() followed by (z - shift_factor) * scaling_factor (lipsync_pipeline.py:298-299,
+ * 315-316): moments fp32 channels-last [n*HW][ld] = [mean(C) | logvar(C) | ...], logvar clamped to [-30, 20];
+ * noise fp32 [n][C][HW] (NULL = the mode); z fp32 [n][C][HW]. */
+int ls_gaussian_sample(const float* moments_cl, int32_t ld, const float* noise, int32_t n, int32_t C, int32_t HW,
+                       float shift, float scale, float* z, void* stream);
 /* paste_surrounding_pixels_back (lipsync_pipeline.py:328-333, called with 1-masks at :572-574):
  *   out = decoded*(1-m) + ref*m.  decoded_cl: fp32 channels-last [n*HW][ld] (VAE conv_out, 3 real channels);
  *   ref fp32 [n][3][HW]; mask fp32 [n][1][HW]; out fp32 [n][3][HW]. */

@@ -97,6 +97,8 @@ SYMBOLS = {
     "ls_cl_to_ncfhw": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ls_upsample2x": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ls_im2col_s2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ls_im2col_s2_pad": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ls_gaussian_sample": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
     "ls_paste_back": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "ls_small_linear": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "ls_timestep_embedding": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
@@ -316,6 +318,16 @@ def upsample2x(x, nimg, H, W, Cc, y) -> None:
 
 def im2col_s2(x, nimg, H, W, Cc, y) -> None:
     _check(lib().ls_im2col_s2(_ptr(x), nimg, H, W, Cc, _ptr(y), _stream()), "ls_im2col_s2")
+
+
+def im2col_s2_pad(x, nimg, H, W, Cc, pad_before, y) -> None:
+    _check(lib().ls_im2col_s2_pad(_ptr(x), nimg, H, W, Cc, pad_before, _ptr(y), _stream()), "ls_im2col_s2_pad")
+
+
+def gaussian_sample(moments_cl, ld, noise, n, Cc, HW, shift, scale, z) -> None:
+    assert moments_cl.dtype == torch.float32 and z.dtype == torch.float32
+    _check(lib().ls_gaussian_sample(_ptr(moments_cl), ld, _ptr(noise) if noise is not None else None, n, Cc, HW,
+                                    shift, scale, _ptr(z), _stream()), "ls_gaussian_sample")
 
 
 def paste_back(decoded_cl, ld, ref, mask, n, HW, out) -> None:

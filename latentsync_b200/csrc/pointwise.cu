@@ -140,7 +140,8 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, int nimg, int H,
   }
 }
 
-__global__ void im2col_s2_kernel(const __half* __restrict__ x, int nimg, int H, int W, int C, __half* __restrict__ y) {
+__global__ void im2col_s2_kernel(const __half* __restrict__ x, int nimg, int H, int W, int C, int pad,
+                                 __half* __restrict__ y) {
   pdl_prologue();
   const int nvec = C >> 3;
   const int Ho = H >> 1, Wo = W >> 1;
@@ -155,7 +156,7 @@ __global__ void im2col_s2_kernel(const __half* __restrict__ x, int nimg, int H, 
     r /= Wo;
     const int ho = (int)(r % Ho);
     const int n = (int)(r / Ho);
-    const int hi = 2 * ho - 1 + tap / 3, wi = 2 * wo - 1 + tap % 3;
+    const int hi = 2 * ho - pad + tap / 3, wi = 2 * wo - pad + tap % 3;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (hi >= 0 && hi < H && wi >= 0 && wi < W)
       u = *reinterpret_cast<const uint4*>(x + (((int64_t)n * H + hi) * W + wi) * C + v * 8);
@@ -307,7 +308,47 @@ extern "C" int ls_im2col_s2(const void* x, int32_t nimg, int32_t H, int32_t W, i
   const int64_t n = (int64_t)nimg * (H / 2) * (W / 2) * 9 * (C / 8);
   unsigned blocks = blocks_for(n, 256);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  LS_CUDA(launch_k(im2col_s2_kernel, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), (const __half*)x, nimg, H, W, C, (__half*)y));
+  LS_CUDA(launch_k(im2col_s2_kernel, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), (const __half*)x, nimg, H, W, C, 1, (__half*)y));
+  LS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int ls_im2col_s2_pad(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t C, int32_t pad_before,
+                                void* y, void* stream) {
+  LS_CHECK(x && y && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && (pad_before == 0 || pad_before == 1),
+           "ls_im2col_s2_pad: bad args");
+  const int64_t n = (int64_t)nimg * (H / 2) * (W / 2) * 9 * (C / 8);
+  unsigned blocks = blocks_for(n, 256);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  LS_CUDA(launch_k(im2col_s2_kernel, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), (const __half*)x, nimg, H, W, C, pad_before, (__half*)y));
+  LS_LAUNCHED();
+  return 0;
+}
+
+// DiagonalGaussianDistribution.sample + (z - shift) * scale (lipsync_pipeline.py:298-299,315-316):
+// moments fp32 channels-last [n*HW][ld] = [mean(C) | logvar(C)], noise fp32 [n][C][HW] -> z fp32 [n][C][HW]
+__global__ void gaussian_sample_kernel(const float* __restrict__ mom, int ld, const float* __restrict__ noise, int n,
+                                       int C, int HW, float shift, float scale, float* __restrict__ z) {
+  pdl_prologue();
+  const int64_t total = (int64_t)n * C * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int p = (int)(idx % HW);
+  const int c = (int)((idx / HW) % C);
+  const int i = (int)(idx / ((int64_t)HW * C));
+  const float* row = mom + ((int64_t)i * HW + p) * ld;
+  const float mean = row[c];
+  const float logvar = fminf(fmaxf(row[C + c], -30.f), 20.f);
+  const float eps = noise != nullptr ? noise[idx] : 0.f;  // no noise: the distribution's mode
+  z[idx] = (mean + expf(0.5f * logvar) * eps - shift) * scale;
+}
+
+extern "C" int ls_gaussian_sample(const float* moments_cl, int32_t ld, const float* noise, int32_t n, int32_t C,
+                                  int32_t HW, float shift, float scale, float* z, void* stream) {
+  LS_CHECK(moments_cl && z && n > 0 && C > 0 && HW > 0 && ld >= 2 * C, "ls_gaussian_sample: bad args");
+  const int64_t total = (int64_t)n * C * HW;
+  LS_CUDA(launch_k(gaussian_sample_kernel, dim3(blocks_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream,
+                   moments_cl, ld, noise, n, C, HW, shift, scale, z));
   LS_LAUNCHED();
   return 0;
 }

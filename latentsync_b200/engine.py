@@ -862,3 +862,65 @@ class VAEPlan(Plan):
         self.gemm([(y.ptr, ch, ch, 9)], nimg, h, wd, w.conv("decoder.conv_out.weight"), nout, self.dec_out.ptr,
                   self.ld_out, bias_ptr=w.f32("decoder.conv_out.bias").data_ptr(), flags=L.EPI_OUT_F32)
         del x, y
+
+
+# ------------------------------------------------------------------------------------------ VAE encoder engine
+class VAEEncoderEngine(VAEDecoderEngine):
+    """diffusers AutoencoderKL.encode(x).latent_dist.parameters for the sd-vae-ft-mse layout (call sites
+    lipsync_pipeline.py:298,315).  Same kernels as the decoder: implicit-GEMM 3x3 convolutions,
+    GroupNorm + SiLU passes, single-head mid attention; the stride-2 Downsample2D(padding=0) goes through an explicit
+    im2col with the library's asymmetric (0, 1, 0, 1) zero padding."""
+
+    def plan(self, nimg: int, h: int, w: int) -> "VAEEncodePlan":
+        key = (nimg, h, w)
+        if key not in self.plans:
+            self.plans[key] = VAEEncodePlan(self, nimg, h, w)
+        return self.plans[key]
+
+
+class VAEEncodePlan(VAEPlan):
+    """x_in: fp16 channels-last [(n H W), 64] pixels in [-1, 1] (3 real channels); mom_out: fp32 [(n h w), 8] =
+    [mean | logvar] of the diagonal Gaussian (h = H/8)."""
+
+    def _build(self) -> None:
+        eng, w, c = self.eng, self.eng.w, self.eng.cfg
+        nimg, h, wd = self.nimg, self.h, self.w
+        boc = list(c["block_out_channels"])
+        lat = c["latent_channels"]
+        self.x_in = self.static(nimg * h * wd, KPAD)
+        self.x_in.tensor().zero_()
+        self.begin_stats((2 * c["layers_per_block"] * len(boc) + 12) * nimg * 32 * 2)
+        x = self._conv("encoder.conv_in", self.x_in, KPAD, boc[0], h, wd)
+        ch = boc[0]
+        for i, cout in enumerate(boc):
+            for j in range(c["layers_per_block"]):
+                x = self._resnet(f"encoder.down_blocks.{i}.resnets.{j}", x, ch, cout, h, wd)
+                ch = cout
+            if i != len(boc) - 1:
+                key = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+                rows = nimg * (h // 2) * (wd // 2)
+                cols = self.buf(rows, 9 * ch)
+                self.call("ls_im2col_s2_pad", x.ptr, nimg, h, wd, ch, 0, cols.ptr)
+                h, wd = h // 2, wd // 2
+                y = self.buf(rows, ch)
+                self.gemm([(cols.ptr, 9 * ch, 9 * ch, 1)], 1, 1, rows, w.conv(key + ".weight"), ch, y.ptr, ch,
+                          bias_ptr=w.f32(key + ".bias").data_ptr())
+                del cols
+                x = y
+        x = self._resnet("encoder.mid_block.resnets.0", x, ch, ch, h, wd)
+        x = self._mid_attention("encoder.mid_block.attentions.0", x, ch, h, wd)
+        x = self._resnet("encoder.mid_block.resnets.1", x, ch, ch, h, wd)
+        y = self._gn("encoder.conv_norm_out", x, ch, h * wd, True)
+        rows = nimg * h * wd
+        # conv_out (3x3, C -> 2*latent) into a zero-padded 64-channel buffer, then the 1x1 quant_conv in fp32
+        co = self.static(rows, KPAD)
+        co.tensor().zero_()
+        self.gemm([(y.ptr, ch, ch, 9)], nimg, h, wd, w.conv("encoder.conv_out.weight"), 2 * lat, co.ptr, KPAD,
+                  bias_ptr=w.f32("encoder.conv_out.bias").data_ptr())
+        self.out_h, self.out_w = h, wd
+        self.ld_out = 2 * lat
+        self.mom_out = self.static(rows, self.ld_out, torch.float32)
+        self.gemm([(co.ptr, KPAD, KPAD, 1)], 1, 1, rows, w.lin("quant_conv.weight"), 2 * lat, self.mom_out.ptr,
+                  self.ld_out, bias_ptr=w.f32("quant_conv.bias").data_ptr(), flags=L.EPI_OUT_F32)
+        del x, y
+

@@ -68,6 +68,40 @@ class LipsyncPipeline:
         latents = latents.repeat(1, 1, num_frames, 1, 1)
         return latents * self.scheduler.init_noise_sigma
 
+    # ------------------------------------------------------------------- VAE encode of the conditioning frames
+    def _encode_scaled(self, images: torch.Tensor, device, dtype, generator) -> torch.Tensor:
+        """(vae.encode(x).latent_dist.sample(generator) - shift_factor) * scaling_factor -> (f, 4, h, w) fp32"""
+        sf, sh = self.vae.config.scaling_factor, self.vae.config.shift_factor
+        dist = self.vae.encode(images.to(device=device, dtype=dtype)).latent_dist
+        if hasattr(dist, "sample_scaled"):
+            # the draw diffusers' randn_tensor makes: on the generator's device when one is given, in `dtype`
+            rdev = generator.device if generator is not None else torch.device(device)
+            noise = torch.randn((dist.n, dist.c, dist.h, dist.w), generator=generator, device=rdev, dtype=dtype)
+            return dist.sample_scaled(noise.to(device), float(sh), float(sf))
+        return ((dist.sample(generator=generator) - sh) * sf).float()
+
+    @torch.no_grad()
+    def prepare_mask_latents(self, mask, masked_image, height, width, dtype, device, generator,
+                             do_classifier_free_guidance):
+        """lipsync_pipeline.py:284-311: nearest-resize the pixel mask to the latent grid, VAE-encode the masked frames
+        (sampled, shifted, scaled), "f c h w -> 1 c f h w", duplicate for CFG."""
+        mask = torch.nn.functional.interpolate(mask, size=(height // self.vae_scale_factor,
+                                                           width // self.vae_scale_factor))
+        masked_image_latents = self._encode_scaled(masked_image, device, dtype, generator).to(dtype)
+        mask = mask.to(device=device, dtype=dtype).permute(1, 0, 2, 3).unsqueeze(0)
+        masked_image_latents = masked_image_latents.permute(1, 0, 2, 3).unsqueeze(0)
+        if do_classifier_free_guidance:
+            mask = torch.cat([mask] * 2)
+            masked_image_latents = torch.cat([masked_image_latents] * 2)
+        return mask, masked_image_latents
+
+    @torch.no_grad()
+    def prepare_image_latents(self, images, device, dtype, generator, do_classifier_free_guidance):
+        """lipsync_pipeline.py:313-320"""
+        image_latents = self._encode_scaled(images, device, dtype, generator).to(dtype)
+        image_latents = image_latents.permute(1, 0, 2, 3).unsqueeze(0)
+        return torch.cat([image_latents] * 2) if do_classifier_free_guidance else image_latents
+
     # ------------------------------------------------------------------------------------------------ hot loop
     @torch.no_grad()
     def denoise_segment(self, latents: torch.Tensor, audio_embeds: Optional[torch.Tensor], mask_latents: torch.Tensor,
@@ -384,15 +418,10 @@ class LipsyncPipeline:
             latents = all_latents[:, :, i * num_frames:(i + 1) * num_frames]
             ref_px, masked_px, masks = self.image_processor.prepare_masks_and_masked_images(inference_faces,
                                                                                             affine_transform=False)
-            # VAE *encode* of masked/reference frames is upstream of the accelerated span
-            m = torch.nn.functional.interpolate(masks, size=(height // self.vae_scale_factor,
-                                                             width // self.vae_scale_factor))
-            sfac, shf = self.vae.config.scaling_factor, self.vae.config.shift_factor
-            enc = lambda x: (self.vae.encode(x.to(device, weight_dtype)).latent_dist.sample(generator=generator)
-                             - shf) * sfac
-            masked_lat = enc(masked_px).permute(1, 0, 2, 3).unsqueeze(0)
-            ref_lat = enc(ref_px).permute(1, 0, 2, 3).unsqueeze(0)
-            mask_lat = m.permute(1, 0, 2, 3).unsqueeze(0)
+            # VAE encode of the masked / reference frames (:525-535), fp32 latents for the loop
+            mask_lat, masked_lat = self.prepare_mask_latents(masks, masked_px, height, width, weight_dtype, device,
+                                                             generator, False)
+            ref_lat = self.prepare_image_latents(ref_px, device, weight_dtype, generator, False)
             lat = self.denoise_segment(latents, audio_embeds, mask_lat, masked_lat, ref_lat, num_inference_steps,
                                        guidance_scale if do_cfg else 1.0, callback, callback_steps)
             synced.append(self.decode_and_paste(lat, ref_px, masks).to(weight_dtype))

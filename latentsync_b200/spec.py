@@ -296,3 +296,32 @@ def vae_decoder_param_spec(cfg: dict = SD_VAE_FT_MSE_CONFIG) -> "OrderedDict[str
     _conv(d, "decoder.conv_out", cfg["out_channels"], boc[0], 3)
     _conv(d, "post_quant_conv", lat, lat, 1)
     return d
+
+
+def vae_encoder_param_spec(cfg: dict = SD_VAE_FT_MSE_CONFIG) -> "OrderedDict[str, Shape]":
+    """Encoder half of diffusers' AutoencoderKL (encoder.* + quant_conv), sd-vae-ft-mse layout: conv_in,
+    DownEncoderBlock2D x4 (2 ResnetBlock2D each, stride-2 conv after the first three), UNetMidBlock2D,
+    GroupNorm-SiLU-conv_out to 2*latent channels, 1x1 quant_conv.  Call sites: lipsync_pipeline.py:298,315."""
+    boc = tuple(cfg["block_out_channels"])
+    lat = cfg["latent_channels"]
+    d: "OrderedDict[str, Shape]" = OrderedDict()
+    _conv(d, "encoder.conv_in", boc[0], cfg.get("in_channels", 3), 3)
+    out_ch = boc[0]
+    for i in range(len(boc)):
+        prev, out_ch = out_ch, boc[i]
+        for j in range(cfg["layers_per_block"]):
+            _resnet2d(d, f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else out_ch, out_ch)
+        if i != len(boc) - 1:
+            _conv(d, f"encoder.down_blocks.{i}.downsamplers.0.conv", out_ch, out_ch, 3)
+    top = boc[-1]
+    a = "encoder.mid_block.attentions.0"
+    _norm(d, a + ".group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        _linear(d, f"{a}.{n}", top, top)
+    _resnet2d(d, "encoder.mid_block.resnets.0", top, top)
+    _resnet2d(d, "encoder.mid_block.resnets.1", top, top)
+    _norm(d, "encoder.conv_norm_out", top)
+    _conv(d, "encoder.conv_out", 2 * lat, top, 3)
+    _conv(d, "quant_conv", 2 * lat, 2 * lat, 1)
+    return d
+

@@ -22,7 +22,7 @@ from typing import Dict, Tuple
 import numpy as np
 import torch
 
-from .spec import SD_VAE_FT_MSE_CONFIG, unet_param_spec, vae_decoder_param_spec
+from .spec import SD_VAE_FT_MSE_CONFIG, unet_param_spec, vae_decoder_param_spec, vae_encoder_param_spec
 
 
 def _rng(seed: int, name: str) -> np.random.Generator:
@@ -79,6 +79,10 @@ def unet_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
 
 def vae_decoder_state_dict(cfg: dict = SD_VAE_FT_MSE_CONFIG, seed: int = 0) -> Dict[str, torch.Tensor]:
     return _state_dict(vae_decoder_param_spec(cfg), seed + 7919)
+
+
+def vae_encoder_state_dict(cfg: dict = SD_VAE_FT_MSE_CONFIG, seed: int = 0) -> Dict[str, torch.Tensor]:
+    return _state_dict(vae_encoder_param_spec(cfg), seed + 104729)
 
 
 def fixed_mask(height: int = 256, width: int = 256) -> torch.Tensor:

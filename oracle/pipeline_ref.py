@@ -3,6 +3,8 @@ under /root/reference, requirements.txt:4) and of the loop that drives them:
 
   * DDIMScheduler  (config: /root/reference/configs/scheduler_config.json:1-12; call sites lipsync_pipeline.py:478,562)
   * AutoencoderKL.decode, sd-vae-ft-mse layout (call site lipsync_pipeline.py:145-149; scripts/inference.py:56-58)
+  * AutoencoderKL.encode + DiagonalGaussianDistribution.sample (call sites lipsync_pipeline.py:298,315) and the
+    prepare_mask_latents / prepare_image_latents helpers around them (:284-320)
   * the segment loop lipsync_pipeline.py:500-575 (the real __call__ cannot run offline: face_alignment on "cuda",
     decord, soundfile, ffmpeg)
 
@@ -98,6 +100,51 @@ def vae_decode(sd: SD, z: torch.Tensor, block_out_channels=(128, 256, 512, 512),
             x = F.interpolate(x, scale_factor=2.0, mode="nearest")
             x = _conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", x)
     return _conv(sd, "decoder.conv_out", _gn(sd, "decoder.conv_norm_out", x, True))
+
+
+# ----------------------------------------------------------------------------------------------------- VAE encoder
+@torch.no_grad()
+def vae_encode_moments(sd: SD, x: torch.Tensor, block_out_channels=(128, 256, 512, 512), layers_per_block=2):
+    """AutoencoderKL.encode(x).latent_dist.parameters: Encoder(conv_in, DownEncoderBlock2D x4, mid[Res, Attn, Res],
+    GN-SiLU-conv_out) -> quant_conv.  diffusers Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) then 3x3 stride 2.
+    Returns (n, 2*latent, h/8, w/8) = [mean | logvar].  PARITY UNPINNED like the decoder (diffusers not vendored)."""
+    h = _conv(sd, "encoder.conv_in", x)
+    n = len(block_out_channels)
+    for i in range(n):
+        for j in range(layers_per_block):
+            h = _resnet2d(sd, f"encoder.down_blocks.{i}.resnets.{j}", h)
+        if i != n - 1:
+            p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[p + ".weight"], sd[p + ".bias"], stride=2)
+    h = _resnet2d(sd, "encoder.mid_block.resnets.0", h)
+    h = _vae_attention(sd, "encoder.mid_block.attentions.0", h)
+    h = _resnet2d(sd, "encoder.mid_block.resnets.1", h)
+    h = _conv(sd, "encoder.conv_out", _gn(sd, "encoder.conv_norm_out", h, True))
+    return _conv(sd, "quant_conv", h, padding=0)
+
+
+def gaussian_sample(moments: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """diffusers DiagonalGaussianDistribution.sample: mean, logvar = chunk(2, dim=1); logvar clamped to [-30, 20];
+    mean + exp(0.5 * logvar) * noise (the noise is `randn_tensor(mean.shape, generator=...)` in the library)"""
+    mean, logvar = moments.chunk(2, dim=1)
+    return mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise
+
+
+@torch.no_grad()
+def prepare_image_latents(sd: SD, images: torch.Tensor, noise: torch.Tensor, scaling_factor: float = 0.18215,
+                          shift_factor: float = 0.0) -> torch.Tensor:
+    """lipsync_pipeline.py:313-320 without the CFG duplicate: (f,3,H,W) -> (1,4,f,h,w)"""
+    z = (gaussian_sample(vae_encode_moments(sd, images), noise) - shift_factor) * scaling_factor
+    return z.permute(1, 0, 2, 3).unsqueeze(0)
+
+
+@torch.no_grad()
+def prepare_mask_latents(sd: SD, mask: torch.Tensor, masked_image: torch.Tensor, noise: torch.Tensor, height: int,
+                         width: int, scaling_factor: float = 0.18215, shift_factor: float = 0.0):
+    """lipsync_pipeline.py:284-311 without the CFG duplicate: nearest-resized mask (1,1,f,h,w), masked latents"""
+    m = F.interpolate(mask, size=(height // 8, width // 8))
+    return m.permute(1, 0, 2, 3).unsqueeze(0), prepare_image_latents(sd, masked_image, noise, scaling_factor,
+                                                                     shift_factor)
 
 
 # ----------------------------------------------------------------------------------------------------- the loop

@@ -176,6 +176,63 @@ def test_vae_oracle_matches_module_graph():
     assert rel_l2(got, want) < 1e-5
 
 
+def test_vae_encoder_oracle_matches_module_graph():
+    """oracle VAE encoder (+ DiagonalGaussian sample, prepare_*_latents) vs an independent nn.Module statement of the
+    published diffusers graph: Downsample2D(padding=0) = F.pad(x, (0, 1, 0, 1)) + stride-2 conv"""
+    import torch.nn as nn
+
+    from latentsync_b200 import synthetic as syn
+    from oracle import pipeline_ref as P
+
+    cfg = dict(block_out_channels=(32, 64), layers_per_block=1, latent_channels=4, out_channels=3, norm_num_groups=32,
+               in_channels=3, act_fn="silu", sample_size=16, scaling_factor=0.18215, shift_factor=0.0)
+    sd = syn.vae_encoder_state_dict(cfg, seed=1)
+    x = syn.approx_normal(3, "px", (2, 3, 16, 16)).clamp(-1, 1)
+    got = P.vae_encode_moments(sd, x, block_out_channels=(32, 64), layers_per_block=1)
+    assert got.shape == (2, 8, 8, 8) and torch.isfinite(got).all()
+
+    def conv(p, x, pad=1, stride=1):
+        wt = sd[p + ".weight"]
+        m = nn.Conv2d(wt.shape[1], wt.shape[0], wt.shape[2], padding=pad, stride=stride)
+        m.load_state_dict({"weight": wt, "bias": sd[p + ".bias"]})
+        return m(x)
+
+    def gn(p, x):
+        m = nn.GroupNorm(32, x.shape[1], eps=1e-6)
+        m.load_state_dict({"weight": sd[p + ".weight"], "bias": sd[p + ".bias"]})
+        return m(x)
+
+    def res(p, x):
+        h = conv(p + ".conv1", F.silu(gn(p + ".norm1", x)))
+        h = conv(p + ".conv2", F.silu(gn(p + ".norm2", h)))
+        return (conv(p + ".conv_shortcut", x, 0) if (p + ".conv_shortcut.weight") in sd else x) + h
+
+    with torch.no_grad():
+        h = conv("encoder.conv_in", x)
+        h = res("encoder.down_blocks.0.resnets.0", h)
+        h = conv("encoder.down_blocks.0.downsamplers.0.conv", nn.ZeroPad2d((0, 1, 0, 1))(h), 0, 2)
+        h = res("encoder.down_blocks.1.resnets.0", h)
+        h = res("encoder.mid_block.resnets.0", h)
+        a = "encoder.mid_block.attentions.0"
+        n, c, hh, ww = h.shape
+        t = gn(a + ".group_norm", h).flatten(2).transpose(1, 2)
+        q, k, v = (F.linear(t, sd[f"{a}.{nm}.weight"], sd[f"{a}.{nm}.bias"]) for nm in ("to_q", "to_k", "to_v"))
+        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        o = F.linear(o, sd[a + ".to_out.0.weight"], sd[a + ".to_out.0.bias"])
+        h = o.transpose(1, 2).reshape(n, c, hh, ww) + h
+        h = res("encoder.mid_block.resnets.1", h)
+        want = conv("quant_conv", conv("encoder.conv_out", F.silu(gn("encoder.conv_norm_out", h))), 0)
+    assert rel_l2(got, want) < 1e-5
+    # DiagonalGaussianDistribution.sample and the (z - shift) * scale / "f c h w -> 1 c f h w" helpers
+    noise = syn.approx_normal(4, "nz", (2, 4, 8, 8))
+    mean, logvar = want.chunk(2, dim=1)
+    z = mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * noise
+    assert torch.allclose(P.gaussian_sample(got, noise), z, atol=1e-5)
+    big = want.clone()
+    big[:, 4:] = 100.0  # logvar clamp at 20
+    assert torch.allclose(P.gaussian_sample(big, noise), mean + math.exp(10.0) * noise, rtol=1e-5)
+
+
 # ------------------------------------------------------------------------------------------------- host logic
 def test_param_spec_matches_reference_state_dict_keys():
     """names, shapes AND order of the 1 246 checkpoint entries (fixture dumped from the reference's own module)"""

@@ -149,6 +149,48 @@ def test_vae_decode_and_paste_vs_oracle(nimg, h):
     assert torch.equal(got.cpu()[keep], seg["ref_pixel_values"][keep])
 
 
+@pytest.mark.parametrize("nimg,H", [(2, 128), (16, 256)])
+def test_vae_encode_vs_oracle(nimg, H):
+    """AutoencoderKL.encode restatement (oracle/pipeline_ref.py) vs the CUDA encoder plan: moments, sample with a given
+    noise, and prepare_mask_latents / prepare_image_latents (lipsync_pipeline.py:284-320) through the drop-in classes"""
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.pipeline import LipsyncPipeline
+    from latentsync_b200.scheduler import DDIMScheduler
+    from latentsync_b200.vae import AutoencoderKL
+    from oracle import pipeline_ref as P
+
+    pipe0, vsd = get_pipe("tiny")
+    esd = syn.vae_encoder_state_dict(seed=0)
+    vae = AutoencoderKL({**vsd, **esd}, device="cuda")
+    pipe = LipsyncPipeline(vae, None, pipe0.denoising_unet, DDIMScheduler()).to("cuda")
+    seg = syn.segment_inputs(INPUT_SEED, 0, nimg, H, H)
+    ref_px = seg["ref_pixel_values"]
+    masked_px = ref_px * seg["masks"]
+    want_m = P.vae_encode_moments(esd, masked_px)
+    dist = vae.encode(masked_px.to("cuda")).latent_dist
+    got_m = torch.cat([dist.mean, dist._nchw(4)], dim=1)
+    e = rel_l2(got_m, want_m)
+    print(f"vae encode {nimg}x{H}: moments rel-L2 {e:.3e}, |mean| {want_m[:, :4].abs().mean():.3f}")
+    assert e < TOL
+    noise = syn.approx_normal(9, "enc.noise", (nimg, 4, H // 8, H // 8))
+    z = dist.sample_scaled(noise.to("cuda"), 0.0, 0.18215)
+    assert rel_l2(z, P.gaussian_sample(want_m, noise) * 0.18215) < TOL
+    assert rel_l2(dist.mode(), want_m[:, :4]) < TOL
+    # drop-in helpers: same generator => same draw as the reference's randn_tensor (device draw, weight dtype)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    nz1 = torch.randn((nimg, 4, H // 8, H // 8), generator=g, device="cuda", dtype=torch.float32)
+    nz2 = torch.randn((nimg, 4, H // 8, H // 8), generator=g, device="cuda", dtype=torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    m_lat, masked_lat = pipe.prepare_mask_latents(seg["masks"], masked_px, H, H, torch.float32, "cuda", g, True)
+    ref_lat = pipe.prepare_image_latents(ref_px, "cuda", torch.float32, g, True)
+    want_mask, want_masked = P.prepare_mask_latents(esd, seg["masks"], masked_px, nz1.cpu(), H, H)
+    want_ref = P.prepare_image_latents(esd, ref_px, nz2.cpu())
+    assert m_lat.shape == (2, 1, nimg, H // 8, H // 8) and masked_lat.shape == (2, 4, nimg, H // 8, H // 8)
+    assert torch.equal(m_lat[0], m_lat[1]) and torch.equal(masked_lat[0], masked_lat[1])
+    assert torch.equal(m_lat[:1].cpu(), want_mask)
+    assert rel_l2(masked_lat[:1], want_masked) < TOL and rel_l2(ref_lat[:1], want_ref) < TOL
+
+
 def _need(path):
     if not os.path.exists(path):
         pytest.skip(f"{os.path.basename(path)} not generated yet (python -m oracle.make_golden stage2)")
