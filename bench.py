@@ -202,7 +202,8 @@ def main():
     unet = UNet3DConditionModel.from_config(cfg)
     unet.load_state_dict(syn.unet_state_dict(cfg, seed=0))
     unet = unet.to(dev).eval()
-    vae = AutoencoderKLDecoder(syn.vae_decoder_state_dict(seed=0), device=dev)
+    # decoder + encoder halves: the encoder is only used by the informational `from_pixels` leg below
+    vae = AutoencoderKLDecoder({**syn.vae_decoder_state_dict(seed=0), **syn.vae_encoder_state_dict(seed=0)}, device=dev)
     pipe = LipsyncPipeline(vae, None, unet, DDIMScheduler()).to(dev)
     h, w = HEIGHT // 8, WIDTH // 8
     uplan = unet.plan(2, FRAMES, h, w, 50)
@@ -287,6 +288,47 @@ def main():
                 for d, n, ms, tf in pl.shape_table(kind):
                     print(f"{name} {kind} x{n:3d} {ms:8.3f} ms {tf:7.1f} TF/s  {d}", file=sys.stderr)
 
+    # ---- informational: one segment from PIXELS: pinned host frames -> H2D -> VAE encode of the
+    # masked and reference frames (2 x 16 images) + nearest mask resize -> 20-step loop -> decode + paste -> D2H
+    from_pixels = None
+    if rank == 0 and world == 1:
+        seg0 = host[0]
+        px_host = {"ref": seg0["ref_pixel_values"], "masks": seg0["masks"]}
+        gen = torch.Generator(device=dev).manual_seed(1234)
+
+        def pixels_step():
+            ref_px = px_host["ref"].to(dev, non_blocking=True)
+            masks = px_host["masks"].to(dev, non_blocking=True)
+            masked_px = ref_px * masks
+            mask_lat, masked_lat = pipe.prepare_mask_latents(masks, masked_px, HEIGHT, WIDTH, torch.float32, dev, gen,
+                                                             False)
+            ref_lat = pipe.prepare_image_latents(ref_px, dev, torch.float32, gen, False)
+            seg = {"latents": resident[0]["latents"], "audio_embeds": resident[0]["audio_embeds"],
+                   "mask_latents": mask_lat, "masked_image_latents": masked_lat, "ref_latents": ref_lat,
+                   "ref_pixel_values": ref_px, "masks": masks}
+            out_host.copy_(pipe.run_segments([seg], DDIM_STEPS, GUIDANCE)[0], non_blocking=True)
+
+        for _ in range(2):
+            pixels_step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            pixels_step()
+        b.record()
+        torch.cuda.synchronize()
+        ms_px = a.elapsed_time(b) / args.steps
+        eplan = vae.encode_plan(FRAMES, HEIGHT, WIDTH)
+        a.record()
+        for _ in range(4):
+            eplan.replay()
+        b.record()
+        torch.cuda.synchronize()
+        from_pixels = {"value": FRAMES / (ms_px * 1e-3), "unit": "frames/s", "ms_per_step": ms_px,
+                       "vae_encode_ms_per_16_frames": a.elapsed_time(b) / 4, "encode_flops_per_16_frames": eplan.flops(),
+                       "what": "encode(masked) + encode(ref) + 20-step loop + decode + paste, pixels from pinned host "
+                               "memory, frames back to host"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -319,6 +361,7 @@ def main():
                          "whole_step": {"flops_per_segment": seg_flops,
                                         "achieved": seg_flops * args.steps / (ms_total * 1e-3) / 1e12 / 1.0,
                                         "frac": seg_flops * args.steps / (ms_total * 1e-3) / 1e12 / peak_tf}},
+            "from_pixels": from_pixels,
             "cpu_baseline": cpu,
         }))
     if world > 1:
