@@ -284,7 +284,7 @@ def main():
         for k, (n, ms) in sorted(vtable.items(), key=lambda kv: -kv[1][1]):
             print(f"vae   {k:20s} {n:4d} launches {ms:8.3f} ms {100 * ms / tot:5.1f} %", file=sys.stderr)
         for name, pl in (("unet", uplan), ("vae", vplan)):
-            for kind in ("gemm", "attention"):
+            for kind in ("gemm", "attention", "groupnorm", "layernorm"):
                 for d, n, ms, tf in pl.shape_table(kind):
                     print(f"{name} {kind} x{n:3d} {ms:8.3f} ms {tf:7.1f} TF/s  {d}", file=sys.stderr)
 

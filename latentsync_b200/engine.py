@@ -224,8 +224,10 @@ class Plan:
         fn = self.lib.ls_groupnorm
         g, b = gamma.data_ptr(), beta.data_ptr()
         x2p = x2 or None
+        cc = c1 + c2
         self._emit(lambda: _chk(fn(x1, c1, x2p, c2, rows, rows_per_inst, groups, g, b, eps, int(silu), sp, out_ptr,
-                                   _stream()), "ls_groupnorm"), "groupnorm")
+                                   _stream()), "ls_groupnorm"), "groupnorm", 0.0,
+                   f"rows={rows} C={cc} rows_per_inst={rows_per_inst} silu={int(silu)}", 2.0 * rows * cc * 2)
 
     def layernorm(self, x: int, rows: int, Cc: int, gamma: torch.Tensor, beta: torch.Tensor, out_ptr: int,
                   pe: Optional[torch.Tensor] = None, rows_per_frame: int = 1, nframes: int = 1) -> None:
@@ -233,7 +235,8 @@ class Plan:
         g, b = gamma.data_ptr(), beta.data_ptr()
         pp = pe.data_ptr() if pe is not None else None
         self._emit(lambda: _chk(fn(x, rows, Cc, g, b, 1e-5, pp, rows_per_frame, nframes, out_ptr, _stream()),
-                                "ls_layernorm"), "layernorm")
+                                "ls_layernorm"), "layernorm", 0.0, f"rows={rows} C={Cc} pe={int(pe is not None)}",
+                   2.0 * rows * Cc * 2)
 
     def attention(self, q: int, k: int, v: int, out: int, ldq: int, ldk: int, ldv: int, ldo: int, batch: int,
                   heads: int, head_dim: int, sq: int, skv: int, q_addr=None, kv_addr=None) -> None:
