@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
 // each CTA sums the instance's partials in chunk order (deterministic, redundantly: chunks x 64 floats from L2),
 // builds the per-channel scale/shift in smem and normalises the chunk it has just read (L2-hot).  The host guarantees
 // that the whole grid is co-resident (grid <= occupancy x SMs, stream-ordered launches), so the rendezvous cannot hang.
-__global__ void __launch_bounds__(256) gn_fused_kernel(const __half* __restrict__ x1, int c1,
+__global__ void __launch_bounds__(256, 4) gn_fused_kernel(const __half* __restrict__ x1, int c1,
                                                        const __half* __restrict__ x2, int c2, int rows_per_inst,
                                                        int rows_per_chunk, int groups, float* __restrict__ partial,
                                                        unsigned int* __restrict__ tickets,
@@ -257,6 +257,14 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __half* __restrict_
   __threadfence();
   __syncthreads();
   unsigned int* tk = tickets + 2 * inst;
+  // affine parameters: requested before the rendezvous so that their latency hides behind it (C <= 10 x 256, host-checked)
+  float g_r[10], b_r[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const int c = threadIdx.x + k * 256;
+    g_r[k] = c < C ? __ldg(gamma + c) : 0.f;
+    b_r[k] = c < C ? __ldg(beta + c) : 0.f;
+  }
   if (threadIdx.x == 0) {
     atomicAdd(tk, 1u);
     uint32_t spins = 0;
@@ -270,12 +278,32 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __half* __restrict_
   }
   __syncthreads();
   __threadfence();
-  {  // 4 threads per (group, stat): interleaved chunk ranges, combined in a fixed shuffle order
+  {  // 4 threads per (group, stat): interleaved chunk ranges, combined in a fixed shuffle order.  16 independent loads
+    // per round: with a single running sum the 74 L2 reads per thread of a 296-chunk instance went out a few at a time
+    // (ncu: joint-statistics launches 12 us slower than per-frame ones of the same tensor).
     const int item = threadIdx.x >> 2, part = threadIdx.x & 3;
     const bool active = item < groups * 2;
     float acc = 0.f;
-    if (active)
-      for (int ch = part; ch < chunks; ch += 4) acc += __ldcg(inst_partial + (int64_t)ch * groups * 2 + item);
+    if (active) {
+      float a16[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a16[k] = 0.f;
+      const float* pp = inst_partial + item;
+      const int64_t ps = (int64_t)groups * 2;
+      int ch = part;
+      for (; ch + 60 < chunks; ch += 64) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a16[k] += __ldcg(pp + (int64_t)(ch + 4 * k) * ps);
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (ch + 4 * k < chunks) a16[k] += __ldcg(pp + (int64_t)(ch + 4 * k) * ps);
+#pragma unroll
+      for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) a16[k] += a16[k + w];
+      acc = a16[0];
+    }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (active && part == 0) s_stats[item] = acc;
@@ -284,14 +312,18 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __half* __restrict_
   float* sa = gf_sm;  // phase-1 arrays are dead from here on
   float* sb = gf_sm + C;
   const float inv_n = 1.f / ((float)rows_per_inst * (float)cg);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cg;
-    const float mean = s_stats[2 * g] * inv_n;
-    float var = s_stats[2 * g + 1] * inv_n - mean * mean;
-    var = fmaxf(var, 0.f);
-    const float a = rsqrtf(var + eps) * gamma[c];
-    sa[c] = a;
-    sb[c] = beta[c] - mean * a;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const int c = threadIdx.x + k * 256;
+    if (c < C) {
+      const int g = c / cg;
+      const float mean = s_stats[2 * g] * inv_n;
+      float var = s_stats[2 * g + 1] * inv_n - mean * mean;
+      var = fmaxf(var, 0.f);
+      const float a = rsqrtf(var + eps) * g_r[k];
+      sa[c] = a;
+      sb[c] = b_r[k] - mean * a;
+    }
   }
   __syncthreads();
   // normalise the chunk just read (L2-hot).  Four independent 16-byte loads per thread are issued before the first use:
@@ -638,7 +670,7 @@ extern "C" int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t 
   }
   const int ninst0 = (int)(rows / rows_per_inst);
   const int capacity = occ > 0 ? occ * sms : 0;
-  if (smem > 48 * 1024 || capacity < ninst0 || dev >= 16) {
+  if (smem > 48 * 1024 || capacity < ninst0 || dev >= 16 || C > 2560) {
     // cannot guarantee co-residency: two launches
     int rc = ls_groupnorm_stats(x1, c1, x2, c2, rows, rows_per_inst, groups, stats_scratch, stream);
     if (rc != 0) return rc;
