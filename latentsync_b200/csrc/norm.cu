@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
 // each CTA sums the instance's partials in chunk order (deterministic, redundantly: chunks x 64 floats from L2),
 // builds the per-channel scale/shift in smem and normalises the chunk it has just read (L2-hot).  The host guarantees
 // that the whole grid is co-resident (grid <= occupancy x SMs, stream-ordered launches), so the rendezvous cannot hang.
-__global__ void __launch_bounds__(256, 4) gn_fused_kernel(const __half* __restrict__ x1, int c1,
+__global__ void __launch_bounds__(256, 3) gn_fused_kernel(const __half* __restrict__ x1, int c1,
                                                        const __half* __restrict__ x2, int c2, int rows_per_inst,
                                                        int rows_per_chunk, int groups, float* __restrict__ partial,
                                                        unsigned int* __restrict__ tickets,
@@ -208,12 +208,12 @@ __global__ void __launch_bounds__(256, 4) gn_fused_kernel(const __half* __restri
 #pragma unroll
       for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
       int64_t row = row0 + rl;
-      for (; row + 3 * RL < row_end; row += 4 * RL) {
-        uint4 u[4];
+      for (; row + 7 * RL < row_end; row += 8 * RL) {
+        uint4 u[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row + k * RL) * ld));
+        for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row + k * RL) * ld));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k) {
           const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -257,13 +257,14 @@ __global__ void __launch_bounds__(256, 4) gn_fused_kernel(const __half* __restri
   __threadfence();
   __syncthreads();
   unsigned int* tk = tickets + 2 * inst;
-  // affine parameters: requested before the rendezvous so that their latency hides behind it (C <= 10 x 256, host-checked)
-  float g_r[10], b_r[10];
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    const int c = threadIdx.x + k * 256;
-    g_r[k] = c < C ? __ldg(gamma + c) : 0.f;
-    b_r[k] = c < C ? __ldg(beta + c) : 0.f;
+  // affine parameters of this thread's first column vector: requested before the rendezvous (latency hides behind it)
+  float4 gpre[2], bpre[2];
+  {
+    const int c = (cv0 < nvec ? cv0 : 0) * 8;
+    gpre[0] = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    gpre[1] = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    bpre[0] = __ldg(reinterpret_cast<const float4*>(beta + c));
+    bpre[1] = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
   }
   if (threadIdx.x == 0) {
     atomicAdd(tk, 1u);
@@ -309,68 +310,75 @@ __global__ void __launch_bounds__(256, 4) gn_fused_kernel(const __half* __restri
     if (active && part == 0) s_stats[item] = acc;
   }
   __syncthreads();
-  float* sa = gf_sm;  // phase-1 arrays are dead from here on
-  float* sb = gf_sm + C;
+  // Normalise the chunk just read (L2-hot).  Each thread keeps the column vector it reduced (8 channels): scale / shift
+  // live in 16 registers (per-channel smem tables read with stride 32 B were 8-way bank conflicted and made this phase
+  // MIO bound), rows advance RL at a time with four independent 16-byte loads in flight.
   const float inv_n = 1.f / ((float)rows_per_inst * (float)cg);
+  if (rl < RL) {
+    for (int cv = cv0; cv < nvec; cv += cvstep) {
+      const int c = cv * 8;
+      float ga[8], be[8];
+      if (cv == cv0) {
+        ga[0] = gpre[0].x; ga[1] = gpre[0].y; ga[2] = gpre[0].z; ga[3] = gpre[0].w;
+        ga[4] = gpre[1].x; ga[5] = gpre[1].y; ga[6] = gpre[1].z; ga[7] = gpre[1].w;
+        be[0] = bpre[0].x; be[1] = bpre[0].y; be[2] = bpre[0].z; be[3] = bpre[0].w;
+        be[4] = bpre[1].x; be[5] = bpre[1].y; be[6] = bpre[1].z; be[7] = bpre[1].w;
+      } else {
 #pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    const int c = threadIdx.x + k * 256;
-    if (c < C) {
-      const int g = c / cg;
-      const float mean = s_stats[2 * g] * inv_n;
-      float var = s_stats[2 * g + 1] * inv_n - mean * mean;
-      var = fmaxf(var, 0.f);
-      const float a = rsqrtf(var + eps) * g_r[k];
-      sa[c] = a;
-      sb[c] = b_r[k] - mean * a;
-    }
-  }
-  __syncthreads();
-  // normalise the chunk just read (L2-hot).  Four independent 16-byte loads per thread are issued before the first use:
-  // with one load in flight per thread (4 KB per CTA) this phase was latency bound at ~2.4 TB/s.
-  const int64_t total = (row_end - row0) * nvec;
-  auto apply_store = [&](const uint4& u, int64_t row, int c) {
-    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-    uint4 w;
-    __half2* o2 = reinterpret_cast<__half2*>(&w);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(h2[e]);
-      float a = f.x * sa[c + 2 * e] + sb[c + 2 * e];
-      float b = f.y * sa[c + 2 * e + 1] + sb[c + 2 * e + 1];
-      if (silu) {
-        a = silu_f(a);
-        b = silu_f(b);
+        for (int e = 0; e < 8; ++e) {
+          ga[e] = __ldg(gamma + c + e);
+          be[e] = __ldg(beta + c + e);
+        }
       }
-      o2[e] = __floats2half2_rn(a, b);
-    }
-    *reinterpret_cast<uint4*>(y + row * C + c) = w;
-  };
-  auto src_of = [&](int64_t row, int c) -> const uint4* {
-    return reinterpret_cast<const uint4*>((c < c1) ? (x1 + row * c1 + c) : (x2 + row * c2 + (c - c1)));
-  };
-  int64_t idx = threadIdx.x;
-  const int64_t step = blockDim.x;
-  for (; idx + 3 * step < total; idx += 4 * step) {
-    int64_t rr[4];
-    int cc[4];
-    uint4 u[4];
+      float sa8[8], sb8[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int64_t i = idx + k * step;
-      const int64_t rrel = i / nvec;
-      rr[k] = row0 + rrel;
-      cc[k] = (int)(i - rrel * nvec) * 8;
-      u[k] = __ldg(src_of(rr[k], cc[k]));
-    }
+      for (int e = 0; e < 8; ++e) {
+        const int g = (c + e) / cg;
+        const float mean = s_stats[2 * g] * inv_n;
+        float var = s_stats[2 * g + 1] * inv_n - mean * mean;
+        var = fmaxf(var, 0.f);
+        sa8[e] = rsqrtf(var + eps) * ga[e];
+        sb8[e] = be[e] - mean * sa8[e];
+      }
+      const __half* src = (c < c1) ? (x1 + c) : (x2 + (c - c1));
+      const int ld = (c < c1) ? c1 : c2;
+      auto apply_store = [&](const uint4& u, int64_t row) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+        uint4 w;
+        __half2* o2 = reinterpret_cast<__half2*>(&w);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) apply_store(u[k], rr[k], cc[k]);
-  }
-  for (; idx < total; idx += step) {
-    const int64_t rrel = idx / nvec;
-    const int c = (int)(idx - rrel * nvec) * 8;
-    const uint4 u = __ldg(src_of(row0 + rrel, c));
-    apply_store(u, row0 + rrel, c);
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          float a = f.x * sa8[2 * e] + sb8[2 * e];
+          float b = f.y * sa8[2 * e + 1] + sb8[2 * e + 1];
+          if (silu) {
+            a = silu_f(a);
+            b = silu_f(b);
+          }
+          o2[e] = __floats2half2_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>(y + row * C + c) = w;
+      };
+      int64_t row = row0 + rl;
+      for (; row + 7 * RL < row_end; row += 8 * RL) {
+        uint4 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row + k * RL) * ld));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) apply_store(u[k], row + k * RL);
+      }
+      for (; row + 1 * RL < row_end; row += 2 * RL) {
+        uint4 u[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row + k * RL) * ld));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) apply_store(u[k], row + k * RL);
+      }
+      for (; row < row_end; row += RL) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + row * ld));
+        apply_store(u, row);
+      }
+    }
   }
   // leave: the last CTA of the instance resets both counters for the next launch
   __syncthreads();
@@ -381,6 +389,185 @@ __global__ void __launch_bounds__(256, 4) gn_fused_kernel(const __half* __restri
       tk[1] = 0u;
     }
   }
+}
+
+
+// -------------------------------------------------------------------------------------------------------------
+// Cluster GroupNorm: one thread-block CLUSTER per instance.  Every CTA copies its rows ONCE into shared memory
+// (cp.async, the whole chunk in flight), reduces them there, the CTAs exchange their 64 (group, stat) partials through
+// distributed shared memory behind a hardware cluster barrier, and each CTA normalises its rows from shared memory.
+// DRAM/L2 traffic is one read + one write of the tensor, and the rendezvous costs a cluster barrier instead of the
+// global-memory ticket + fence + partial round trips of gn_fused_kernel (which needs ~11 us even for a 1 MB tensor).
+// Used whenever an instance fits the shared memory of <= 16 CTAs: all per-frame norms of the transformer / motion
+// modules, the joint norms of the 8x8 and 4x4 levels, the VAE mid block.  Sums in fixed rank order: deterministic.
+// -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gn_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gn_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float gn_ld_remote(const float* local_ptr, uint32_t rank) {
+  uint32_t raddr;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+  return v;
+}
+
+constexpr int GNC_THREADS = 512;
+
+__global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const __half* __restrict__ x1, int c1,
+                                                                 const __half* __restrict__ x2, int c2,
+                                                                 int rows_per_inst, int rows_per_cta, int cl, int groups,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps, int silu,
+                                                                 __half* __restrict__ y) {
+  pdl_prologue();
+  extern __shared__ __align__(16) uint8_t gnc_sm[];
+  __shared__ float s_part[64];   // this CTA's (group, stat) partial sums, read by the whole cluster
+  __shared__ float s_stats[64];  // instance totals
+  const int C = c1 + c2;
+  const int cg = C / groups;
+  const int nvec = C >> 3;
+  const int tid = threadIdx.x;
+  const uint32_t rank = gn_cluster_rank();
+  const int inst = blockIdx.x / cl;
+  const int64_t row0 = (int64_t)inst * rows_per_inst + (int64_t)rank * rows_per_cta;
+  __half* data = reinterpret_cast<__half*>(gnc_sm);                                   // [rows_per_cta][C]
+  float* red = reinterpret_cast<float*>(gnc_sm + (size_t)rows_per_cta * C * 2);       // [2][RL][C], later sa[C], sb[C]
+  const int RL = (nvec <= GNC_THREADS) ? GNC_THREADS / nvec : 1;  // row lanes: thread = (row lane, column vector)
+  const int rl = (nvec <= GNC_THREADS) ? tid / nvec : 0;
+  const int cv0 = (nvec <= GNC_THREADS) ? tid % nvec : tid;
+  const int cvstep = (nvec <= GNC_THREADS) ? nvec : GNC_THREADS;
+  float* sh_s = red;
+  float* sh_q = red + RL * C;
+
+  // affine parameters of this thread's column vector first: their latency hides behind the copy
+  float4 gpre[2], bpre[2];
+  {
+    const int c = (cv0 < nvec ? cv0 : 0) * 8;
+    gpre[0] = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    gpre[1] = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    bpre[0] = __ldg(reinterpret_cast<const float4*>(beta + c));
+    bpre[1] = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+  }
+  // phase 0: the whole chunk global -> shared, every 16-byte vector requested at once
+  const int total = rows_per_cta * nvec;
+  for (int idx = tid; idx < total; idx += GNC_THREADS) {
+    const int r = idx / nvec;
+    const int c = (idx - r * nvec) * 8;
+    const __half* src = (c < c1) ? (x1 + (row0 + r) * c1 + c) : (x2 + (row0 + r) * c2 + (c - c1));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(data + (size_t)r * C + c)), "l"(src)
+                 : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // phase 1: per-channel sums over the chunk (from shared memory), then per-group
+  {
+    if (rl < RL) {
+      for (int cv = cv0; cv < nvec; cv += cvstep) {
+        float sacc[8], qacc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sacc[e] = qacc[e] = 0.f;
+        for (int r = rl; r < rows_per_cta; r += RL) {
+          const uint4 u = *reinterpret_cast<const uint4*>(data + (size_t)r * C + cv * 8);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            sacc[2 * e] += f.x;
+            sacc[2 * e + 1] += f.y;
+            qacc[2 * e] += f.x * f.x;
+            qacc[2 * e + 1] += f.y * f.y;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sh_s[rl * C + cv * 8 + e] = sacc[e];
+          sh_q[rl * C + cv * 8 + e] = qacc[e];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {  // 8 threads per (group, stat): fixed interleave + fixed shuffle order
+    const int item = tid >> 3, part = tid & 7;
+    float acc = 0.f;
+    if (item < groups * 2) {
+      const int g = item >> 1;
+      const float* base = (item & 1) ? sh_q : sh_s;
+      for (int i = part; i < RL * cg; i += 8) {
+        const int r = i / cg;
+        acc += base[r * C + g * cg + (i - r * cg)];
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (item < 64 && part == 0) s_part[item] = (item < groups * 2) ? acc : 0.f;
+  }
+  // rendezvous of the cluster, then every CTA sums the partials of all ranks in rank order
+  gn_cluster_arrive();
+  gn_cluster_wait();
+  if (tid < 64) {
+    float acc = 0.f;
+    for (int r = 0; r < cl; ++r) acc += gn_ld_remote(&s_part[tid], (uint32_t)r);
+    s_stats[tid] = acc;
+  }
+  gn_cluster_arrive();  // this CTA no longer reads remote shared memory (waited for at the very end)
+  __syncthreads();
+  // phase 2: normalise from shared memory; the thread keeps its column vector, scale / shift in 16 registers
+  const float inv_n = 1.f / ((float)rows_per_inst * (float)cg);
+  if (rl < RL) {
+    for (int cv = cv0; cv < nvec; cv += cvstep) {
+      const int c = cv * 8;
+      float ga[8], be[8];
+      if (cv == cv0) {
+        ga[0] = gpre[0].x; ga[1] = gpre[0].y; ga[2] = gpre[0].z; ga[3] = gpre[0].w;
+        ga[4] = gpre[1].x; ga[5] = gpre[1].y; ga[6] = gpre[1].z; ga[7] = gpre[1].w;
+        be[0] = bpre[0].x; be[1] = bpre[0].y; be[2] = bpre[0].z; be[3] = bpre[0].w;
+        be[4] = bpre[1].x; be[5] = bpre[1].y; be[6] = bpre[1].z; be[7] = bpre[1].w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          ga[e] = __ldg(gamma + c + e);
+          be[e] = __ldg(beta + c + e);
+        }
+      }
+      float sa8[8], sb8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int g = (c + e) / cg;
+        const float mean = s_stats[2 * g] * inv_n;
+        float var = s_stats[2 * g + 1] * inv_n - mean * mean;
+        var = fmaxf(var, 0.f);
+        sa8[e] = rsqrtf(var + eps) * ga[e];
+        sb8[e] = be[e] - mean * sa8[e];
+      }
+      for (int r = rl; r < rows_per_cta; r += RL) {
+        const uint4 u = *reinterpret_cast<const uint4*>(data + (size_t)r * C + c);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+        uint4 w;
+        __half2* o2 = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          float a = f.x * sa8[2 * e] + sb8[2 * e];
+          float b = f.y * sa8[2 * e + 1] + sb8[2 * e + 1];
+          if (silu) {
+            a = silu_f(a);
+            b = silu_f(b);
+          }
+          o2[e] = __floats2half2_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>(y + (row0 + r) * C + c) = w;
+      }
+    }
+  }
+  gn_cluster_wait();  // nobody reads this CTA's s_part any more: safe to exit
 }
 
 static void gn_chunking(int64_t rows, int rows_per_inst, int target_ctas, int& ninst, int& chunks, int& rpc) {
@@ -637,6 +824,80 @@ extern "C" int ls_groupnorm_apply(const void* x1, int32_t c1, const void* x2, in
   return 0;
 }
 
+
+namespace ls {
+// Cluster path of ls_groupnorm: returns 0 = launched, -1 = not applicable (the caller uses the global-rendezvous kernel)
+static int groupnorm_cluster_try(const void* x1, int c1, const void* x2, int c2, int64_t rows, int rows_per_inst,
+                                 int groups, const float* gamma, const float* beta, float eps, int silu, void* y,
+                                 cudaStream_t stream) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("LS_GN_CLUSTER");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return -1;
+  const int C = c1 + c2;
+  if (C > 5 * GNC_THREADS || groups * 2 > 64) return -1;
+  if (c2 != 0 && (c2 % 8) != 0) return -1;
+  const int64_t ninst = rows / rows_per_inst;
+  if (ninst > (1 << 20)) return -1;
+  const int nvec = C / 8;
+  const int RL = nvec <= GNC_THREADS ? GNC_THREADS / nvec : 1;
+  const size_t red_bytes = (size_t)2 * RL * C * sizeof(float);
+  const size_t inst_bytes = (size_t)rows_per_inst * C * 2;
+  // smallest cluster whose chunk fits ~96 KB (two CTAs per SM), else ~200 KB (one per SM); then widen while the grid
+  // is smaller than the GPU and chunks stay >= 8 rows
+  // Measured (tools/gn_bench.py): the cluster kernel wins when many small chunks cover the GPU (per-frame norms: 15.7
+  // vs 17.8 us at 32 x 1024 x 320, 8.2 vs 9.5 us at 32 x 64 x 1280) and loses when few CTAs stream > 100 KB each
+  // (8x8 joint norm on 16-CTA clusters: 24 vs 15 us), so: chunk <= 96 KB, cluster <= 8, at least 128 CTAs.
+  int cl = 0;
+  for (int c = 1; c <= 8 && !cl; c *= 2)
+    if (rows_per_inst % c == 0 && inst_bytes / c + red_bytes <= (size_t)96 * 1024) cl = c;
+  if (!cl) return -1;
+  while (cl < 8 && ninst * cl < 128 && (rows_per_inst % (cl * 2)) == 0 && rows_per_inst / (cl * 2) >= 8) cl *= 2;
+  if (ninst * cl < 128 && ninst * cl < 64) return -1;
+  const int rows_per_cta = rows_per_inst / cl;
+  const size_t smem = (size_t)rows_per_cta * C * 2 + red_bytes;
+  static bool attr_set = false;
+  static bool broken[5] = {false, false, false, false, false};  // per log2(cl): a launch failed once -> never retry
+  int lg = 0;
+  while ((1 << lg) < cl) ++lg;
+  if (broken[lg]) return -1;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      enabled = 0;
+      return -1;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ninst * cl));
+  cfg.blockDim = dim3(GNC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gn_cluster_kernel, (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst,
+                                     rows_per_cta, cl, groups, gamma, beta, eps, silu, (__half*)y);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    broken[lg] = true;
+    return -1;
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+}  // namespace ls
+
 // Fused single-launch GroupNorm (+SiLU): y = GN(x) [* sigmoid]; replaces the stats + apply pair when the grid fits the
 // GPU in one co-resident wave (always true for the UNet / VAE shapes); otherwise falls back to the two-kernel path.
 extern "C" int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows, int32_t rows_per_inst,
@@ -648,6 +909,9 @@ extern "C" int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t 
            "ls_groupnorm: bad args");
   LS_CHECK(groups > 0 && groups <= 32 && C % groups == 0 && C % 8 == 0 && c1 % 8 == 0,
            "ls_groupnorm: C=%d groups=%d unsupported", C, groups);
+  if (ls::groupnorm_cluster_try(x1, c1, x2, c2, rows, rows_per_inst, groups, gamma, beta, eps, silu, y,
+                                (cudaStream_t)stream) == 0)
+    return 0;
   const int threads = 256;
   const int nvec = C / 8;
   const int RL = nvec <= threads ? threads / nvec : 1;

@@ -202,7 +202,11 @@ def test_upsample2x():
 
 # --------------------------------------------------------------------------------------------------------- norms
 @pytest.mark.parametrize("c1,c2,rows_per_inst,ninst", [(320, 0, 16 * 1024, 2), (1280, 640, 64, 32), (640, 320, 256, 4),
-                                                       (128, 0, 65536, 2), (512, 0, 1024, 3)])
+                                                       (128, 0, 65536, 2), (512, 0, 1024, 3),
+                                                       # thread-block-cluster path (instance fits <= 16 CTAs' smem):
+                                                       # per-frame norms of each level, 4x4 concat, 8x8 joint (16 CTAs)
+                                                       (320, 0, 1024, 32), (640, 0, 256, 32), (1280, 0, 16, 32),
+                                                       (1280, 1280, 256, 2), (1280, 0, 1024, 2), (1280, 0, 8, 3)])
 @pytest.mark.parametrize("silu", [False, True])
 def test_groupnorm(c1, c2, rows_per_inst, ninst, silu):
     L = _ops()

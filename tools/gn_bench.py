@@ -5,7 +5,8 @@ from latentsync_b200 import _lib as L
 dev = "cuda"
 REPS = 20
 shapes = [(32768, 320, 16384, 1), (32768, 320, 1024, 0), (8192, 640, 4096, 1), (8192, 640, 256, 0), (2048, 1280, 1024, 1),
-          (512, 1280, 256, 1), (32768, 960, 16384, 1), (1048576, 128, 65536, 1)]
+          (2048, 1280, 64, 0), (512, 1280, 256, 1), (512, 1280, 16, 0), (512, 2560, 256, 1), (16384, 512, 1024, 1),
+          (32768, 960, 16384, 1), (1048576, 128, 65536, 1)]
 lib = L.lib()
 for rows, C, rpi, silu in shapes:
     xs = [torch.randn(rows, C, device=dev).half() for _ in range(3)]
@@ -32,4 +33,4 @@ for rows, C, rpi, silu in shapes:
     if silu: ref = torch.nn.functional.silu(ref)
     run(0); torch.cuda.synchronize()
     err = ((ys[0].float() - ref).norm() / ref.norm()).item()
-    print(f"rows={rows} C={C} rows_per_inst={rpi} silu={silu}: {us:7.1f} us  ({2*mb/us/1e3:5.2f} TB/s read+write of {mb:.1f} MB)  rel-L2 {err:.1e}", flush=True)
+    print(f"rows={rows} C={C} rows_per_inst={rpi} silu={silu}: {us:7.1f} us  ({2*mb/us:5.2f} TB/s read+write of {mb:.1f} MB)  rel-L2 {err:.1e}", flush=True)
