@@ -31,9 +31,9 @@ WORKLOAD = "configs[1]: one 16-frame 256x256 segment per step: 20x(UNet3D fwd, C
 
 
 # DRAM traffic of the dominant kernel (gemm_tc_kernel): sum of dram__bytes_read.sum + dram__bytes_write.sum over the 341
-# GEMM launches of ONE CFG-batched UNet forward, from the ncu capture profiles/r1_launches_unet.csv (joined table:
+# GEMM launches of ONE CFG-batched UNet forward, from the ncu capture profiles/r1b_launches_unet.csv (joined table:
 # profiles/r1_launch_table.txt).  Same unit of work as `achieved` (FLOPs of those 341 launches / their summed duration).
-GEMM_DRAM_BYTES_PER_UNET_FORWARD = 9.5814e9
+GEMM_DRAM_BYTES_PER_UNET_FORWARD = 9.4709e9
 
 
 def make_config(world: int, steps: int, spb: int = 1) -> dict:
@@ -350,7 +350,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": gemm_tf / peak_tf, "traffic": GEMM_DRAM_BYTES_PER_UNET_FORWARD,
-                         "traffic_unit": "bytes per UNet forward (341 launches, ncu profiles/r1_launches_unet.csv)",
+                         "traffic_unit": "bytes per UNet forward (341 launches, ncu profiles/r1b_launches_unet.csv)",
                          "algorithmic_bytes_per_unet_forward": uplan.bytes("gemm"),
                          "peak_source": peak_src,
                          "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
