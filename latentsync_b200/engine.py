@@ -155,6 +155,35 @@ class Plan:
             self.run()
         self.graph = g
 
+    def time_kind_in_graph(self, kind: str, reps: int = 5) -> float:
+        """ms per pass of ONLY the launches of one kind (e.g. "gemm"), captured in plan order into their own CUDA graph
+        and timed with CUDA events: kernel time without the host launch gap that the per-launch event pairs of
+        `run_timed` include (~3 us x launches).  Buffers keep whatever the last full run left in them (timing of these
+        kernels does not depend on the values)."""
+        fns = [fn for fn, k in zip(self.ops, self.kinds) if k == kind]
+        if not fns:
+            return 0.0
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for fn in fns:
+                fn()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for fn in fns:
+                fn()
+        g.replay()
+        torch.cuda.synchronize(self.device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize(self.device)
+        return a.elapsed_time(b) / reps
+
     def replay(self) -> None:
         if self.graph is None:
             self.run()
