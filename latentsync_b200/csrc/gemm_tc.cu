@@ -361,7 +361,12 @@ __device__ __forceinline__ void add_bias32(const GemmKParams& p, int64_t m, int 
 }
 
 // ----------------------------------------------------------------------------------------------------- kernel body
-template <int CTAS>
+// GEGLU is a template parameter: the plain instantiation carries no gate accumulator (161 instead of 168 registers - 168
+// is the limit with 10 warps, 3 on one SM sub-partition).  Tried on top of it and dropped: keeping the NEXT slab's
+// tcgen05.ld in flight while the current one is converted (needs ~190 registers: spills, 71 vs 50 us on the K = 64,
+// N = 2560 probe); setmaxnreg with a third, shrunken warpgroup for the producer / issuer (ptxas then spills in the
+// producer / issuer loops at every split tried: 224/64, 208/96, 200/112, 192/128).
+template <int CTAS, bool GEGLU>
 __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   const int BN = p.BN;
   const int b_rows = BN / CTAS;  // B rows staged by each CTA
@@ -541,7 +546,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int group = warp >> 2;  // 0: even slabs, 1: odd slabs
     const int r = q * 32 + lane;  // row of the tile == TMEM lane
-    const bool geglu = (p.flags & LS_EPI_GEGLU) != 0;
+    constexpr bool geglu = GEGLU;
     if (p.tma_store) {
       // Latency-tolerant epilogue: the tile's bias row goes to smem and ALL residual fragments of the group's slabs
       // are requested before waiting for the accumulator, so global-load latency hides behind the main loop.
@@ -951,12 +956,14 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   if (warp == MMA_WARP) tmem_dealloc_g<CTAS>(tmem_base, TMEM_COLS);
 }
 
+template <bool GEGLU>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-  gemm_body<1>(p);
+  gemm_body<1, GEGLU>(p);
 }
+template <bool GEGLU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_pair_kernel(const __grid_constant__ GemmKParams p) {
-  gemm_body<2>(p);
+  gemm_body<2, GEGLU>(p);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1240,14 +1247,18 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   const int grid = (int)(total < units ? total : units) * CTAS;
   static bool attr_set = false;
   if (!attr_set) {
-    LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    LS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    LS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    LS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     attr_set = true;
   }
   if (CTAS == 1)
-    LS_CUDA(launch_k(gemm_tc_kernel, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), (cudaStream_t)(stream), p));
+    LS_CUDA(launch_k(geglu ? gemm_tc_kernel<true> : gemm_tc_kernel<false>, dim3(grid), dim3(GEMM_THREADS),
+                     (size_t)(smem), (cudaStream_t)(stream), p));
   else
-    LS_CUDA(launch_k(gemm_tc_pair_kernel, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), (cudaStream_t)(stream), p));
+    LS_CUDA(launch_k(geglu ? gemm_tc_pair_kernel<true> : gemm_tc_pair_kernel<false>, dim3(grid), dim3(GEMM_THREADS),
+                     (size_t)(smem), (cudaStream_t)(stream), p));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
