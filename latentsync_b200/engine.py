@@ -614,7 +614,7 @@ class UNetPlan(Plan):
                 ab = f"{blk}.attention_blocks.{k}"
                 pe = None
                 if w.has(ab + ".pos_encoder.pe"):
-                    name = ab + "#pe"
+                    name = f"{ab}#pe{self.F}"  # one table per segment length (plans with different F share the engine)
                     if name not in w.t:
                         w.put(name, w.raw(ab + ".pos_encoder.pe")[0, : self.F].contiguous())
                     pe = w.t[name]

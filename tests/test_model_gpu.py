@@ -148,6 +148,27 @@ def test_loop_50_steps_cfg2_vs_oracle():
     assert max(errs) < TOL and e_lat < TOL
 
 
+@pytest.mark.parametrize("frames,guidance", [(16, 1.0), (8, 1.5)])
+def test_loop_without_cfg_and_short_segment(frames, guidance):
+    """guidance_scale <= 1 disables classifier-free guidance (batch 1, lipsync_pipeline.py:446,542) and a segment may
+    hold fewer than 16 frames (num_frames argument, :371); 3 free-running steps vs the oracle loop"""
+    from latentsync_b200 import synthetic as syn
+    from oracle import pipeline_ref as P
+    from oracle.unet_ref import unet_forward
+
+    pipe, _ = get_pipe("tiny")
+    unet, sd, cfg = get_unet("tiny")
+    seg = syn.segment_inputs(INPUT_SEED, 5, frames, 128, 128)
+    trace, want = {}, {}
+    lat = pipe.denoise_segment(seg["latents"], seg["audio_embeds"], seg["mask_latents"], seg["masked_image_latents"],
+                               seg["ref_latents"], num_inference_steps=3, guidance_scale=guidance, trace=trace)
+    want_lat = P.denoise_segment(lambda x, t, a: unet_forward(sd, cfg, x, t, a), seg, steps=3, guidance=guidance,
+                                 trace=want)
+    errs = [rel_l2(trace["noise_pred"][j], want["noise_pred"][j]) for j in range(3)]
+    print(f"frames={frames} guidance={guidance}: noise rel-L2 {max(errs):.3e}, latents {rel_l2(lat, want_lat):.3e}")
+    assert lat.shape == (1, 4, frames, 16, 16) and max(errs) < TOL and rel_l2(lat, want_lat) < TOL
+
+
 def test_unet_512px_shape_batched_segments_vs_oracle():
     """BASELINE.json configs[4] geometry: 13 x 16 x 64 x 64 UNet input (512 x 512 pixels), temporal layers on, several
     segments in one launch (CFG batch 2 x 2 segments here) - quarter-width weights so that the CPU oracle stays in
