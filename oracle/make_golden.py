@@ -4,6 +4,7 @@ weights / inputs of latentsync_b200/synthetic.py.  Runs only in the build contai
 travel to the GPU box); the fixtures it writes are what the GPU parity tests compare against.
 
     python -m oracle.make_golden tiny        # seconds
+    python -m oracle.make_golden tiny_stage1 # seconds: stage1.yaml variant (use_motion_module = false)
     python -m oracle.make_golden stage2      # ~12 min on 8 cores: one forward + the 20-step loop trace (config 1)
 
 It also pins the CPU port (oracle/unet_ref.py) to the reference: rel-L2 between the two is asserted < 1e-5.
@@ -71,6 +72,21 @@ def make_tiny():
                os.path.join(GOLDEN, "unet_tiny.pt"))
 
 
+def make_tiny_stage1():
+    """configs/unet/stage1.yaml variant: use_motion_module = false (no temporal layers), quarter width"""
+    cfg = dict(TINY_CONFIG)
+    cfg["use_motion_module"] = False
+    ref, sd = reference_model(cfg)
+    seg = syn.segment_inputs(INPUT_SEED, 1, 16, 128, 128)
+    x, a = unet_inputs(seg)
+    with torch.no_grad():
+        y = ref(x, 701, encoder_hidden_states=a).sample
+    err = rel_l2(unet_forward(sd, cfg, x, 701, a), y)
+    print("tiny stage1 (no motion modules): port vs reference rel-L2", err)
+    assert err < 1e-5
+    torch.save({"config": "tiny_stage1", "noise_pred": y, "t": 701}, os.path.join(GOLDEN, "unet_tiny_stage1.pt"))
+
+
 def make_stage2():
     t0 = time.time()
     cfg = STAGE2_UNET_CONFIG
@@ -108,6 +124,8 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "tiny"
     if which == "tiny":
         make_tiny()
+    elif which == "tiny_stage1":
+        make_tiny_stage1()
     elif which == "stage2":
         make_stage2()
     else:

@@ -90,6 +90,29 @@ def test_unet_tiny_forward_vs_reference_golden_and_port(monkeypatch):
     assert e_gold < TOL and e_port < TOL
 
 
+def test_unet_stage1_variant_without_motion_modules_vs_reference_golden():
+    """configs/unet/stage1.yaml: use_motion_module = false - the same drop-in class without temporal layers, against a
+    golden vector produced by the reference's own modules (oracle/make_golden.py tiny_stage1)"""
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.spec import TINY_UNET_CONFIG
+    from latentsync_b200.unet import UNet3DConditionModel
+
+    cfg = dict(TINY_UNET_CONFIG)
+    cfg["use_motion_module"] = False
+    sd = syn.unet_state_dict(cfg, seed=WEIGHT_SEED)
+    assert not any("motion_modules" in k for k in sd)
+    unet = UNet3DConditionModel.from_config(cfg)
+    unet.load_state_dict(sd, strict=True)
+    unet = unet.to("cuda").eval()
+    gold = torch.load(os.path.join(GOLDEN, "unet_tiny_stage1.pt"))
+    seg = syn.segment_inputs(INPUT_SEED, 1, 16, 128, 128)
+    x, a = cfg_batch(seg)
+    y = unet(x.cuda(), gold["t"], encoder_hidden_states=a.cuda()).sample
+    e = rel_l2(y, gold["noise_pred"])
+    print(f"tiny stage1 variant (no motion modules): rel-L2 vs reference golden {e:.3e}")
+    assert e < TOL
+
+
 def test_unet_forward_signature_variants():
     """timestep as int / 0-d tensor / (B,) tensor, 4-D vs 3-D encoder_hidden_states, fp16 sample, return_dict=False"""
     from latentsync_b200 import synthetic as syn
