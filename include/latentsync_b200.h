@@ -171,6 +171,20 @@ int ls_im2col_s2_pad(const void* x, int32_t nimg, int32_t H, int32_t W, int32_t 
  * noise fp32 [n][C][HW] (NULL = the mode); z fp32 [n][C][HW]. */
 int ls_gaussian_sample(const float* moments_cl, int32_t ld, const float* noise, int32_t n, int32_t C, int32_t HW,
                        float shift, float scale, float* z, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Pixel-space pre / post processing around the hot path.
+ * ------------------------------------------------------------------------------------------------------- */
+/* ImageProcessor.preprocess_fixed_mask_image for faces already at the working resolution (the resize is then the
+ * identity; image_processor.py:145-151, called per frame from prepare_masks_and_masked_images :153-165):
+ * pixel = (u8 / 255 - 0.5) / 0.5, masked = pixel * mask.  img uint8 [n][H][W][3] (hwc != 0) or [n][3][H][W];
+ * mask fp32 [mask_c][H][W], mask_c in {1, 3}; pixel, masked fp32 [n][3][H][W]. */
+int ls_preprocess_u8(const void* img, int32_t n, int32_t H, int32_t W, int32_t hwc, const float* mask, int32_t mask_c,
+                     float* pixel, float* masked, void* stream);
+/* restore_video's per-face front half (lipsync_pipeline.py:350-355): torchvision resize(face, (oh, ow),
+ * antialias=True) [bilinear, align_corners = false] -> (x / 2 + 0.5).clamp(0, 1) * 255 -> uint8 (truncation),
+ * "c h w -> h w c".  x fp32 [n][3][H][W]; out uint8 [n][oh][ow][3]. */
+int ls_resize_aa_u8(const float* x, int32_t n, int32_t H, int32_t W, int32_t oh, int32_t ow, void* out, void* stream);
 /* paste_surrounding_pixels_back (lipsync_pipeline.py:328-333, called with 1-masks at :572-574):
  *   out = decoded*(1-m) + ref*m.  decoded_cl: fp32 channels-last [n*HW][ld] (VAE conv_out, 3 real channels);
  *   ref fp32 [n][3][HW]; mask fp32 [n][1][HW]; out fp32 [n][3][HW]. */

@@ -99,6 +99,8 @@ SYMBOLS = {
     "ls_im2col_s2": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ls_im2col_s2_pad": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ls_gaussian_sample": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
+    "ls_preprocess_u8": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "ls_resize_aa_u8": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ls_paste_back": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "ls_small_linear": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "ls_timestep_embedding": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
@@ -322,6 +324,23 @@ def im2col_s2(x, nimg, H, W, Cc, y) -> None:
 
 def im2col_s2_pad(x, nimg, H, W, Cc, pad_before, y) -> None:
     _check(lib().ls_im2col_s2_pad(_ptr(x), nimg, H, W, Cc, pad_before, _ptr(y), _stream()), "ls_im2col_s2_pad")
+
+
+def preprocess_u8(img, mask, pixel, masked) -> None:
+    """img uint8 (n,H,W,3) or (n,3,H,W); mask fp32 (1|3,H,W); pixel / masked fp32 (n,3,H,W)"""
+    assert img.dtype == torch.uint8 and mask.dtype == torch.float32 and img.is_contiguous() and mask.is_contiguous()
+    hwc = int(img.shape[-1] == 3 and img.shape[1] != 3)
+    n = img.shape[0]
+    H, W = (img.shape[1], img.shape[2]) if hwc else (img.shape[2], img.shape[3])
+    _check(lib().ls_preprocess_u8(_ptr(img), n, H, W, hwc, _ptr(mask), mask.shape[0], _ptr(pixel), _ptr(masked),
+                                  _stream()), "ls_preprocess_u8")
+
+
+def resize_aa_u8(x, oh, ow, out) -> None:
+    """x fp32 (n,3,H,W) in [-1,1] -> out uint8 (n,oh,ow,3)"""
+    assert x.dtype == torch.float32 and out.dtype == torch.uint8 and x.is_contiguous()
+    n, _, H, W = x.shape
+    _check(lib().ls_resize_aa_u8(_ptr(x), n, H, W, oh, ow, _ptr(out), _stream()), "ls_resize_aa_u8")
 
 
 def gaussian_sample(moments_cl, ld, noise, n, Cc, HW, shift, scale, z) -> None:

@@ -353,6 +353,108 @@ extern "C" int ls_gaussian_sample(const float* moments_cl, int32_t ld, const flo
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pixel-space pre / post processing around the hot path.
+// ---------------------------------------------------------------------------------------------------------------
+// ImageProcessor.preprocess_fixed_mask_image without the (identity-size) resize (image_processor.py:145-151):
+// pixel = (u8 / 255 - 0.5) / 0.5 ; masked = pixel * mask.  img: uint8 [n][H][W][3] (hwc != 0) or [n][3][H][W];
+// mask: fp32 [mask_c][H][W] with mask_c in {1, 3}; pixel, masked: fp32 [n][3][H][W].
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, int n, int HW, int hwc,
+                                     const float* __restrict__ mask, int mask_c, float* __restrict__ pixel,
+                                     float* __restrict__ masked) {
+  pdl_prologue();
+  const int64_t total = (int64_t)n * 3 * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int p = (int)(idx % HW);
+  const int c = (int)((idx / HW) % 3);
+  const int64_t i = idx / ((int64_t)3 * HW);
+  const uint8_t u = hwc ? img[(i * HW + p) * 3 + c] : img[idx];
+  const float x = (float)u / 255.0f;
+  const float v = (x - 0.5f) / 0.5f;
+  pixel[idx] = v;
+  masked[idx] = v * mask[(mask_c == 3 ? c : 0) * (int64_t)HW + p];
+}
+
+extern "C" int ls_preprocess_u8(const void* img, int32_t n, int32_t H, int32_t W, int32_t hwc, const float* mask,
+                                int32_t mask_c, float* pixel, float* masked, void* stream) {
+  LS_CHECK(img && mask && pixel && masked && n > 0 && H > 0 && W > 0 && (mask_c == 1 || mask_c == 3),
+           "ls_preprocess_u8: bad args");
+  const int64_t total = (int64_t)n * 3 * H * W;
+  LS_CUDA(launch_k(preprocess_u8_kernel, dim3(blocks_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream,
+                   (const uint8_t*)img, n, H * W, hwc, mask, mask_c, pixel, masked));
+  LS_LAUNCHED();
+  return 0;
+}
+
+// torchvision resize(face, (oh, ow), antialias=True) [= aten::_upsample_bilinear2d_aa, align_corners = false] followed
+// by (x / 2 + 0.5).clamp(0, 1) * 255 -> uint8 and "c h w -> h w c" (lipsync_pipeline.py:350-355).
+// Separable triangle filter whose support grows with the down-scale factor; weights normalised per output index.
+__device__ __forceinline__ void aa_window(int i, float scale, int in_size, int& lo, int& size, float& center,
+                                          float& invscale) {
+  const float support = scale >= 1.0f ? scale : 1.0f;  // interp_size / 2 * scale, interp_size = 2
+  center = scale * ((float)i + 0.5f);
+  invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  lo = max((int)(center - support + 0.5f), 0);
+  size = min((int)(center + support + 0.5f), in_size) - lo;
+}
+__device__ __forceinline__ float aa_weight(int j, int lo, float center, float invscale) {
+  const float x = fabsf(((float)(j + lo) - center + 0.5f) * invscale);
+  return x < 1.0f ? 1.0f - x : 0.0f;
+}
+
+constexpr int AA_MAX_TAPS = 16;  // support of a 7x down-scale
+
+__global__ void resize_aa_u8_kernel(const float* __restrict__ x, int n, int H, int W, int oh, int ow, float sy,
+                                    float sx, uint8_t* __restrict__ out) {
+  pdl_prologue();
+  const int64_t total = (int64_t)n * oh * ow;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % ow);
+  const int oy = (int)((idx / ow) % oh);
+  const int64_t i = idx / ((int64_t)ow * oh);
+  int xlo, xn, ylo, yn;
+  float xc, xi, yc, yi;
+  aa_window(ox, sx, W, xlo, xn, xc, xi);
+  aa_window(oy, sy, H, ylo, yn, yc, yi);
+  xn = min(xn, AA_MAX_TAPS);
+  yn = min(yn, AA_MAX_TAPS);
+  float wx[AA_MAX_TAPS];
+  float wxs = 0.f, wys = 0.f;
+  for (int j = 0; j < xn; ++j) {
+    wx[j] = aa_weight(j, xlo, xc, xi);
+    wxs += wx[j];
+  }
+  for (int j = 0; j < yn; ++j) wys += aa_weight(j, ylo, yc, yi);
+  const float wxn = wxs != 0.f ? 1.0f / wxs : 0.f, wyn = wys != 0.f ? 1.0f / wys : 0.f;
+  for (int c = 0; c < 3; ++c) {
+    const float* plane = x + (i * 3 + c) * (int64_t)H * W;
+    float acc = 0.f;
+    for (int r = 0; r < yn; ++r) {
+      const float* row = plane + (int64_t)(ylo + r) * W + xlo;
+      float h = 0.f;  // horizontal pass first, like the separable ATen kernel
+      for (int j = 0; j < xn; ++j) h += row[j] * (wx[j] * wxn);
+      acc += h * (aa_weight(r, ylo, yc, yi) * wyn);
+    }
+    const float v = fminf(fmaxf(acc / 2.0f + 0.5f, 0.0f), 1.0f) * 255.0f;
+    out[idx * 3 + c] = (uint8_t)v;  // truncation, as tensor.to(torch.uint8)
+  }
+}
+
+extern "C" int ls_resize_aa_u8(const float* x, int32_t n, int32_t H, int32_t W, int32_t oh, int32_t ow, void* out,
+                               void* stream) {
+  LS_CHECK(x && out && n > 0 && H > 0 && W > 0 && oh > 0 && ow > 0, "ls_resize_aa_u8: bad args");
+  const float sy = (float)H / (float)oh, sx = (float)W / (float)ow;
+  LS_CHECK(2.f * (sy > 1.f ? sy : 1.f) + 1.f <= (float)AA_MAX_TAPS && 2.f * (sx > 1.f ? sx : 1.f) + 1.f <= (float)AA_MAX_TAPS,
+           "ls_resize_aa_u8: down-scale factor beyond %d taps", AA_MAX_TAPS);
+  const int64_t total = (int64_t)n * oh * ow;
+  LS_CUDA(launch_k(resize_aa_u8_kernel, dim3(blocks_for(total, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, x, n,
+                   H, W, oh, ow, sy, sx, (uint8_t*)out));
+  LS_LAUNCHED();
+  return 0;
+}
+
 extern "C" int ls_paste_back(const float* decoded_cl, int32_t ld, const float* ref, const float* mask, int32_t n,
                              int32_t HW, float* out, void* stream) {
   LS_CHECK(decoded_cl && ref && mask && out && ld >= 3, "ls_paste_back: bad args");

@@ -68,6 +68,40 @@ class LipsyncPipeline:
         latents = latents.repeat(1, 1, num_frames, 1, 1)
         return latents * self.scheduler.init_noise_sigma
 
+    # ------------------------------------------------------------------- pixel-space pre / post
+    @torch.no_grad()
+    def prepare_masks_and_masked_images(self, images, mask_image: torch.Tensor):
+        """ImageProcessor.prepare_masks_and_masked_images for mask="fix_mask", affine_transform=False and faces that are
+        already at the working resolution (image_processor.py:145-165; the reference's per-frame Python loop):
+        uint8 (f,H,W,3) / (f,3,H,W) frames -> (pixel_values, masked_pixel_values, masks), fp32 on the device.
+        `mask_image`: (3,H,W) or (1,H,W) as returned by load_fixed_mask (1 = keep)."""
+        dev = self.device
+        if not isinstance(images, torch.Tensor):
+            images = torch.from_numpy(images)
+        img = images.to(dev).contiguous()
+        if img.dtype != torch.uint8:
+            raise TypeError("expected uint8 frames")
+        hwc = img.shape[-1] == 3 and img.shape[1] != 3
+        n = img.shape[0]
+        H, W = (img.shape[1], img.shape[2]) if hwc else (img.shape[2], img.shape[3])
+        m = mask_image.to(dev, torch.float32).contiguous()
+        if tuple(m.shape[-2:]) != (H, W):
+            raise ValueError(f"frames are {H}x{W} but the mask is {tuple(m.shape[-2:])}: resize the faces first")
+        pixel = torch.empty(n, 3, H, W, dtype=torch.float32, device=dev)
+        masked = torch.empty_like(pixel)
+        L.preprocess_u8(img, m, pixel, masked)
+        return pixel, masked, m[0:1].unsqueeze(0).expand(n, 1, H, W).contiguous()
+
+    @torch.no_grad()
+    def faces_to_uint8(self, faces: torch.Tensor, height: int, width: int) -> torch.Tensor:
+        """front half of restore_video for faces that share one box size (lipsync_pipeline.py:350-355): anti-aliased
+        bilinear resize to (height, width), [-1, 1] -> uint8, "c h w -> h w c".  Returns (f, height, width, 3) uint8 on
+        the device (one D2H copy for the whole clip instead of one per frame)."""
+        x = faces.to(self.device, torch.float32).contiguous()
+        out = torch.empty(x.shape[0], height, width, 3, dtype=torch.uint8, device=x.device)
+        L.resize_aa_u8(x, height, width, out)
+        return out
+
     # ------------------------------------------------------------------- VAE encode of the conditioning frames
     def _encode_scaled(self, images: torch.Tensor, device, dtype, generator) -> torch.Tensor:
         """(vae.encode(x).latent_dist.sample(generator) - shift_factor) * scaling_factor -> (f, 4, h, w) fp32"""
@@ -416,8 +450,11 @@ class LipsyncPipeline:
                 audio_embeds = torch.stack(whisper_chunks[i * num_frames:(i + 1) * num_frames]).to(device)
             inference_faces = faces[i * num_frames:(i + 1) * num_frames]
             latents = all_latents[:, :, i * num_frames:(i + 1) * num_frames]
-            ref_px, masked_px, masks = self.image_processor.prepare_masks_and_masked_images(inference_faces,
-                                                                                            affine_transform=False)
+            if mask == "fix_mask" and tuple(inference_faces.shape[-2:]) == (height, width):
+                ref_px, masked_px, masks = self.prepare_masks_and_masked_images(inference_faces, mask_image)
+            else:  # other mask modes need landmarks; other sizes need torchvision's uint8 resize
+                ref_px, masked_px, masks = self.image_processor.prepare_masks_and_masked_images(
+                    inference_faces, affine_transform=False)
             # VAE encode of the masked / reference frames (:525-535), fp32 latents for the loop
             mask_lat, masked_lat = self.prepare_mask_latents(masks, masked_px, height, width, weight_dtype, device,
                                                              generator, False)
@@ -448,17 +485,21 @@ class LipsyncPipeline:
         subprocess.run(command, shell=True)
 
     def _restore_video(self, faces, video_frames, boxes, affine_matrices):
-        """lipsync_pipeline.py:343-358 (untouched stage: per-frame resize -> uint8 -> cv2 inverse affine paste)"""
+        """lipsync_pipeline.py:343-358: resize -> uint8 on the GPU (faces_to_uint8), then the reference's own cv2 inverse
+        affine paste per frame (AlignRestore.restore_img, untouched)"""
         import numpy as np
-        import torchvision
 
         video_frames = video_frames[: len(faces)]
         out_frames = []
-        for index, face in enumerate(faces):
-            x1, y1, x2, y2 = boxes[index]
-            face = torchvision.transforms.functional.resize(face, size=(int(y2 - y1), int(x2 - x1)), antialias=True)
-            face = (face.permute(1, 2, 0) / 2 + 0.5).clamp(0, 1)
-            face = (face * 255).to(torch.uint8).cpu().numpy()
-            out_frames.append(self.image_processor.restorer.restore_img(video_frames[index], face,
+        # resize + uint8 conversion on the GPU, batched over the frames that share a box size (usually all of them)
+        sizes = [(int(b[3] - b[1]), int(b[2] - b[0])) for b in boxes[: len(faces)]]
+        u8 = [None] * len(faces)
+        for hw in sorted(set(sizes)):
+            idx = [i for i, s in enumerate(sizes) if s == hw]
+            batch = self.faces_to_uint8(torch.stack([faces[i] for i in idx]), hw[0], hw[1]).cpu().numpy()
+            for k, i in enumerate(idx):
+                u8[i] = batch[k]
+        for index in range(len(faces)):
+            out_frames.append(self.image_processor.restorer.restore_img(video_frames[index], u8[index],
                                                                         affine_matrices[index]))
         return np.stack(out_frames, axis=0)

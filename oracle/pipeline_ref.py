@@ -188,6 +188,36 @@ def decode_and_paste(vae_sd: SD, lat: torch.Tensor, seg: Dict[str, torch.Tensor]
     return dec * m + seg["ref_pixel_values"] * (1 - m)
 
 
+# ------------------------------------------------------------------------------------- pixel-space pre / post
+def preprocess_fixed_mask(images_u8: torch.Tensor, mask_image: torch.Tensor):
+    """ImageProcessor.prepare_masks_and_masked_images, fix_mask, affine_transform=False, faces already at the working
+    resolution so that transforms.Resize is the identity (image_processor.py:145-165): per frame
+    pixel = Normalize([0.5], [0.5])(image / 255.0), masked = pixel * mask_image, mask = mask_image[0:1].
+    images_u8: (f,3,H,W) or (f,H,W,3) uint8; mask_image (3,H,W) (float64 in the reference: cv2 resize / 255.0)."""
+    if images_u8.shape[3] == 3 and images_u8.shape[1] != 3:
+        images_u8 = images_u8.permute(0, 3, 1, 2)
+    px, masked, masks = [], [], []
+    for img in images_u8:
+        p = (img.to(torch.float32) / 255.0 - 0.5) / 0.5
+        px.append(p)
+        masked.append(p * mask_image)
+        masks.append(mask_image[0:1])
+    return torch.stack(px), torch.stack(masked), torch.stack(masks)
+
+
+def restore_faces_u8(faces: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """front half of LipsyncPipeline.restore_video per face (lipsync_pipeline.py:350-355):
+    torchvision.transforms.functional.resize(face, (h, w), antialias=True) - which is aten's bilinear anti-aliased
+    interpolate, align_corners=False - then "c h w -> h w c", (x / 2 + 0.5).clamp(0, 1) * 255 -> uint8."""
+    out = []
+    for face in faces:
+        r = F.interpolate(face[None].float(), size=(height, width), mode="bilinear", align_corners=False,
+                          antialias=True)[0]
+        r = (r.permute(1, 2, 0) / 2 + 0.5).clamp(0, 1)
+        out.append((r * 255).to(torch.uint8))
+    return torch.stack(out)
+
+
 def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 2.0) -> float:
     """frames live in [-1, 1] => peak-to-peak 2"""
     mse = (a.double() - b.double()).pow(2).mean().item()

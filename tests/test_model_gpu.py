@@ -278,6 +278,35 @@ def test_vae_encode_vs_oracle(nimg, H):
     assert rel_l2(masked_lat[:1], want_masked) < TOL and rel_l2(ref_lat[:1], want_ref) < TOL
 
 
+def test_pixel_pre_and_post_processing_vs_oracle():
+    """prepare_masks_and_masked_images (image_processor.py:145-165) and the resize -> uint8 front
+    half of restore_video (lipsync_pipeline.py:350-355) on the GPU against their torch / torchvision statements"""
+    from latentsync_b200 import synthetic as syn
+    from oracle import pipeline_ref as P
+
+    pipe, _ = get_pipe("tiny")
+    g = torch.Generator().manual_seed(31)
+    faces = torch.randint(0, 256, (5, 256, 256, 3), generator=g, dtype=torch.uint8)
+    mask3 = syn.fixed_mask(256, 256).repeat(3, 1, 1).double()
+    mask3[:, 94:96] = 0.37  # the Lanczos-resized mask.png has fractional rows at the box edges
+    for frames in (faces, faces.permute(0, 3, 1, 2).contiguous()):
+        px, masked, masks = pipe.prepare_masks_and_masked_images(frames, mask3)
+        wpx, wmasked, wmasks = P.preprocess_fixed_mask(frames, mask3)
+        assert torch.equal(px.cpu(), wpx)  # same fp32 operations: bit-exact
+        assert torch.allclose(masked.cpu().double(), wmasked, atol=1e-6) and masked.shape == (5, 3, 256, 256)
+        assert torch.allclose(masks.cpu().double(), wmasks, atol=1e-7) and masks.shape == (5, 1, 256, 256)
+    # post: decoded faces in [-1.2, 1.2] (clamp exercised) -> box-sized uint8 HWC
+    dec = (torch.rand(4, 3, 256, 256, generator=g) * 2.4 - 1.2)
+    for (h, w) in ((210, 280), (256, 256), (311, 287), (96, 128)):
+        got = pipe.faces_to_uint8(dec, h, w).cpu()
+        want = P.restore_faces_u8(dec, h, w)
+        diff = (got.int() - want.int()).abs()
+        frac = (diff > 0).float().mean().item()
+        print(f"resize 256x256 -> {h}x{w}: max |diff| {diff.max().item()} LSB, {100 * frac:.4f} % of bytes differ")
+        # float rounding can move a value across an integer boundary before the truncating cast: <= 1 LSB, rare
+        assert got.shape == (4, h, w, 3) and diff.max().item() <= 1 and frac < 2e-3
+
+
 def _need(path):
     if not os.path.exists(path):
         pytest.skip(f"{os.path.basename(path)} not generated yet (python -m oracle.make_golden stage2)")
