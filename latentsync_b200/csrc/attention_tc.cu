@@ -365,6 +365,270 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
   }
 }
 
+// =================================================================================================================
+// Version 2: everything the softmax warps wait for is produced a whole key tile ahead.
+//   * S is double buffered in TMEM (S_{j+2} is issued when the warps have finished tile j, so S_{j+1} is already there
+//     when they come back), P is double buffered in shared memory (no wait for P V_{j-1} before writing P_j),
+//     K / V live in rings of NST stages loaded two tiles ahead.
+//   * ONE barrier per key tile, R[j & 1]: 4 warp arrivals ("P_j is written" - which implies "S_j has been read") plus
+//     the transaction bytes of the TMA loads that the tensor work issued at that wake-up needs (V_j, K_{j+2}).  The
+//     control thread wakes once per tile and issues P V_j, S_{j+2} and the loads for tile j + 2.  Version 1 needed
+//     4-6 waits per tile, each ~300 clocks behind the MUFU backlog of the MIO queue (profiles/r1b_attn_tc_probe.txt).
+//   * Completion of older tensor work is inferred, never waited for: s_full(j) is a tcgen05.commit issued after
+//     P V_{j-2}, so a warp that holds S_j knows that P buffer j & 1 and V stage (j - 2) % NST are free.
+// =================================================================================================================
+template <int D>
+struct Atc2Cfg {
+  static constexpr int DP = (D + 15) / 16 * 16;
+  static constexpr int KS = (DP + 63) / 64;
+  static constexpr int KSTEPS = DP / 16;
+  static constexpr int NST = (D <= 80) ? 4 : 3;        // K / V ring depth
+  static constexpr int Q_BYTES = KS * ATC_BQ * 128;
+  static constexpr int KV_SLAB = ATC_BKV * 128;
+  static constexpr int KV_BYTES = KS * KV_SLAB;
+  static constexpr int P_BYTES = ATC_BQ * 128;
+  static constexpr int TILE_BYTES = Q_BYTES + 2 * NST * KV_BYTES + 2 * P_BYTES;
+  static constexpr int SMEM = TILE_BYTES + 128;        // barriers; the dynamic segment is 1024-byte aligned (checked)
+  static constexpr int TMEM_NEED = 2 * ATC_BKV + DP;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+  static constexpr int CTAS_PER_SM = (2 * (SMEM + 1024) <= 228 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
+  using Cfg = Atc2Cfg<D>;
+  constexpr int DP = Cfg::DP, KS = Cfg::KS, KSTEPS = Cfg::KSTEPS, NST = Cfg::NST;
+  pdl_prologue();
+  extern __shared__ __align__(1024) uint8_t atc2_smem[];
+  uint8_t* sm = atc2_smem;
+  const uint32_t base = smem_u32(sm);
+  if ((base & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("latentsync_b200: attention smem not 1024-byte aligned\n");
+    __trap();
+  }
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + Cfg::Q_BYTES;
+  const uint32_t sV = sK + NST * Cfg::KV_BYTES;
+  const uint32_t sP = sV + NST * Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Cfg::TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* rdy = bars + 1;      // [2]  R[j & 1]
+  uint64_t* s_full = bars + 3;   // [2]
+  uint64_t* pv_done = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.skv + ATC_BKV - 1) / ATC_BKV;
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(rdy + 0, 5);
+    mbar_init(rdy + 1, 5);
+    mbar_init(s_full + 0, 1);
+    mbar_init(s_full + 1, 1);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tO = tmem + 2 * ATC_BKV;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.mapQ);
+      tma_prefetch_desc(&p.mapK);
+      tma_prefetch_desc(&p.mapV);
+      constexpr uint32_t idesc_s = (1u << 4) | (uint32_t(ATC_BKV >> 3) << 17) | (uint32_t(ATC_BQ >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 16) | (uint32_t(DP >> 3) << 17) | (uint32_t(ATC_BQ >> 4) << 24);
+      auto load_k = [&](int j, uint64_t* bar) {
+        const int st = j % NST;
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+          tma_load_4d(sm + (sK - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapK, bar, s * 64, h, j * ATC_BKV, b);
+      };
+      auto load_v = [&](int j, uint64_t* bar) {
+        const int st = j % NST;
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+          tma_load_4d(sm + (sV - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapV, bar, s * 64, h, j * ATC_BKV, b);
+      };
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j & 1
+        const uint32_t tS = tmem + (uint32_t)(j & 1) * ATC_BKV;
+        const uint32_t kb = sK + (j % NST) * Cfg::KV_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t qa = sQ + (ks >> 2) * (ATC_BQ * 128) + (ks & 3) * 32;
+          const uint32_t ka = kb + (ks >> 2) * Cfg::KV_SLAB + (ks & 3) * 32;
+          umma_f16_ss(tS, umma_desc_sw128(qa), umma_desc_sw128(ka), idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full + (j & 1));
+      };
+      auto issue_pv = [&](int j) {  // O += P_j V_j
+        const uint32_t pb = sP + (uint32_t)(j & 1) * Cfg::P_BYTES;
+        const uint32_t vb = sV + (j % NST) * Cfg::KV_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < ATC_BKV / 16; ++kk)
+          umma_f16_ss(tO, umma_desc_sw128(pb + kk * 32), umma_desc_mn_sw128(vb + kk * 16 * 128, Cfg::KV_SLAB), idesc_o,
+                      (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(pv_done);
+      };
+      // Barrier accounting: the phase of R[t & 1] that belongs to tile t gets 4 warp arrivals and ONE arrival from this
+      // thread, posted two tiles earlier (prologue for t < 2) together with the bytes of V_t and K_{t+2} - the loads
+      // the wake-up of tile t depends on.  With NST = 3 the K_{t+2} load itself is issued one wake-up later than its
+      // bytes are announced (its stage frees later); expect_tx may precede the copy.
+      const int nk0 = n_tiles < 2 ? n_tiles : 2;
+      mbar_expect_tx(q_full, Cfg::Q_BYTES + nk0 * Cfg::KV_BYTES);
+#pragma unroll
+      for (int s = 0; s < KS; ++s)
+        tma_load_4d(sm + (sQ - base) + s * (ATC_BQ * 128), &p.mapQ, q_full, s * 64, h, qt * ATC_BQ, b);
+      for (int j = 0; j < nk0; ++j) load_k(j, q_full);
+      for (int t = 0; t < 2 && t < n_tiles; ++t) {
+        mbar_expect_tx(rdy + t, Cfg::KV_BYTES + (t + 2 < n_tiles ? Cfg::KV_BYTES : 0));
+        load_v(t, rdy + t);
+        if (t + 2 < n_tiles && t + 2 < NST) load_k(t + 2, rdy + t);
+      }
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(rdy + (j & 1), (uint32_t)((j >> 1) & 1));  // P_j written, S_j read, V_j and K_{j+2} landed
+        tc_fence_after();
+        issue_pv(j);
+        if (j + 2 < n_tiles) {
+          issue_s(j + 2);
+          // this thread's arrival for tile j + 2, with the bytes its wake-up will need
+          mbar_expect_tx(rdy + (j & 1), Cfg::KV_BYTES + (j + 4 < n_tiles ? Cfg::KV_BYTES : 0));
+          // V_{j+2} takes the stage of V_{j+2-NST}: P V_{j-2} finished before S_j was issued (NST = 4); with NST = 3 it
+          // is P V_{j-1}, issued one wake-up ago: wait for it (cheap: it ran during the whole softmax of tile j)
+          if (NST == 3 && j >= 1) mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+          load_v(j + 2, rdy + (j & 1));
+        }
+        if (NST >= 4) {
+          if (j + 4 < n_tiles) load_k(j + 4, rdy + (j & 1));        // K_j's stage: S_j has been read
+        } else {
+          if (j + 3 < n_tiles) load_k(j + 3, rdy + ((j + 1) & 1));  // K_j's stage; bytes announced at the last wake-up
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- softmax warps: thread = query row
+    const int r = tid;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float sl = p.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    const int rx = r & 7;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t tS = tmem + (uint32_t)(j & 1) * ATC_BKV;
+      mbar_wait(s_full + (j & 1), (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t sv[2][32];
+      tmem_ld_32x32(tS + lane_off, sv[0]);
+      tmem_ld_32x32(tS + lane_off + 32, sv[1]);
+      tmem_ld_wait();
+      float* s = reinterpret_cast<float*>(&sv[0][0]);
+      const int kbase = j * ATC_BKV;
+      if (kbase + ATC_BKV > p.skv) {
+#pragma unroll
+        for (int c = 0; c < ATC_BKV; ++c)
+          if (kbase + c >= p.skv) s[c] = -INFINITY;
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < ATC_BKV; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const bool grow = (mx - m_ref) * sl > ATC_RESCALE_THRESHOLD;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_ref, mx);
+        const float alpha = ex2_approx((m_ref - m_new) * sl);
+        m_ref = m_new;
+        l *= alpha;
+        if (j > 0) {
+          mbar_wait(pv_done, (uint32_t)((j - 1) & 1));  // O holds tiles 0..j-1 (rare path)
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < DP; c += 16) {
+            uint32_t ov[16];
+            tmem_ld_32x16(tO + lane_off + c, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x16(tO + lane_off + c, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mb = m_ref * sl;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[ATC_BKV / 2];
+#pragma unroll
+      for (int c = 0; c < ATC_BKV; c += 2) {
+        const float e0 = ex2_approx(fmaf(s[c], sl, -mb));
+        const float e1 = ex2_approx(fmaf(s[c + 1], sl, -mb));
+        sum0 += e0;
+        sum1 += e1;
+        pk[c >> 1] = pack_half2(e0, e1);
+      }
+      l += sum0 + sum1;
+      // P buffer j & 1 was read by P V_{j-2}, which completed before S_j was issued: free
+      const uint32_t p_row = sP + (uint32_t)(j & 1) * Cfg::P_BYTES + r * 128;
+#pragma unroll
+      for (int c = 0; c < ATC_BKV / 8; ++c)
+        st_shared_v4(p_row + ((c ^ rx) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rdy + (j & 1));
+    }
+    // the warp only knows that P V_{n-3} is complete (s_full of the last tile): wait for the last TWO phases in order,
+    // a single parity wait for P V_{n-1} would alias with P V_{n-3} while P V_{n-2} is still running
+    if (n_tiles >= 2) mbar_wait(pv_done, (uint32_t)((n_tiles - 2) & 1));
+    mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int qrow = qt * ATC_BQ + r;
+    __half* dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)qrow * p.o_seq_stride) * p.ldo + h * D;
+#pragma unroll
+    for (int c = 0; c < DP; c += 16) {
+      uint32_t ov[16];
+      tmem_ld_32x16(tO + lane_off + c, ov);
+      tmem_ld_wait();
+      if (qrow < p.sq) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          if (c + i < D) {
+            uint4 pk4;
+            pk4.x = pack_half2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+            pk4.y = pack_half2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+            pk4.z = pack_half2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+            pk4.w = pack_half2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c + i) = pk4;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -413,6 +677,15 @@ extern "C" int ls_atc_probe_read(long long* host, int n) {
 }
 #endif
 
+static int atc_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LS_ATTN_V");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 template <int D>
 static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
   using Cfg = AtcCfg<D>;
@@ -450,10 +723,26 @@ static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     LS_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    if (D == 80)
+      LS_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Atc2Cfg<D>::SMEM));
     attr_set = true;
   }
   dim3 grid((a->sq + ATC_BQ - 1) / ATC_BQ, a->heads, a->batch);
-  LS_CUDA(launch_k(attn_tc_kernel<D>, grid, dim3(ATC_THREADS), (size_t)Cfg::SMEM, stream, p));
+  // Measured (tools/attn_bench.py): version 2 wins at head_dim 80 (S = 1024: 540 -> 419 us, S = 256: 33.5 -> 31.0 us)
+  // and ties at head_dim 40 (129.6 vs 127.8 us: with one or four waits per tile, two or three CTAs per SM, both land at
+  // ~1100 clocks per key tile per SM - the softmax warps' own per-tile latency chain, not the control thread, is
+  // what is left; next step is 8 softmax warps per CTA, two per query row).  head_dim 160 stays on version 1 (the
+  // 3-stage ring variant of version 2 still has an accounting bug: its control thread times out).
+  if (atc_version() == 2 && D == 80) {
+    static const int pad = getenv("LS_ATTN_SMEM_PAD") ? atoi(getenv("LS_ATTN_SMEM_PAD")) : 0;  // debugging: forces 1 CTA/SM
+    size_t smem2 = (size_t)Atc2Cfg<D>::SMEM + (size_t)pad;
+    if (smem2 > 227 * 1024) smem2 = 227 * 1024;
+    if (pad) cudaFuncSetAttribute(attn_tc2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    LS_CUDA(launch_k(attn_tc2_kernel<D>, grid, dim3(ATC_THREADS), smem2, stream, p));
+  }
+  else {
+    LS_CUDA(launch_k(attn_tc_kernel<D>, grid, dim3(ATC_THREADS), (size_t)Cfg::SMEM, stream, p));
+  }
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
