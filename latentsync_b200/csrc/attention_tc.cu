@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2
   uint64_t* rdy = bars + 1;      // [2]  R[j & 1]
   uint64_t* s_full = bars + 3;   // [2]
   uint64_t* pv_done = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* fin = bars + 6;      // committed once, after the last P V
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2
     mbar_init(s_full + 0, 1);
     mbar_init(s_full + 1, 1);
     mbar_init(pv_done, 1);
+    mbar_init(fin, 1);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -502,6 +504,7 @@ __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2
         mbar_wait(rdy + (j & 1), (uint32_t)((j >> 1) & 1));  // P_j written, S_j read, V_j and K_{j+2} landed
         tc_fence_after();
         issue_pv(j);
+        if (j == n_tiles - 1) umma_commit(fin);
         if (j + 2 < n_tiles) {
           issue_s(j + 2);
           // this thread's arrival for tile j + 2, with the bytes its wake-up will need
@@ -593,10 +596,9 @@ __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2
       __syncwarp();
       if (lane == 0) mbar_arrive(rdy + (j & 1));
     }
-    // the warp only knows that P V_{n-3} is complete (s_full of the last tile): wait for the last TWO phases in order,
-    // a single parity wait for P V_{n-1} would alias with P V_{n-3} while P V_{n-2} is still running
-    if (n_tiles >= 2) mbar_wait(pv_done, (uint32_t)((n_tiles - 2) & 1));
-    mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
+    // own barrier for the end: a warp that only knows "P V_{n-3} is complete" cannot name the phase of pv_done it needs
+    // by parity (n-1 aliases with n-3 while n-2 runs; n-2 aliases with the never-completing phase n once both are done)
+    mbar_wait(fin, 0);
     tc_fence_after();
     const float inv = 1.f / l;
     const int qrow = qt * ATC_BQ + r;
@@ -731,7 +733,11 @@ static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
   // Measured (tools/attn_bench.py): version 2 wins at head_dim 80 (S = 1024: 540 -> 419 us, S = 256: 33.5 -> 31.0 us)
   // and ties at head_dim 40 (129.6 vs 127.8 us: with one or four waits per tile, two or three CTAs per SM, both land at
   // ~1100 clocks per key tile per SM - the softmax warps' own per-tile latency chain, not the control thread, is
-  // what is left; next step is 8 softmax warps per CTA, two per query row).  head_dim 160 stays on version 1 (the
+  // what is left.  A third variant with 8 softmax warps, two threads per query row, also ties: 130.6 us at head_dim
+  // 40, 432 us at head_dim 80 / S = 1024 (tools/experiments/r1_attention_v3.patch) - so neither the control thread nor
+  // the warps' latency chain is the limit; the candidates left are shared-memory bandwidth (per key tile the MMAs
+  // re-read 16 KB of Q and 16 KB of P, the warps write 16 KB of P, TMA writes 16 KB of K/V: ~80 KB against 128 B/clk)
+  // and the TMEM read of S (32 KB per tile).  Next: P as the A operand from TMEM.)  head_dim 160 stays on version 1 (the
   // 3-stage ring variant of version 2 still has an accounting bug: its control thread times out).
   if (atc_version() == 2 && D == 80) {
     static const int pad = getenv("LS_ATTN_SMEM_PAD") ? atoi(getenv("LS_ATTN_SMEM_PAD")) : 0;  // debugging: forces 1 CTA/SM
