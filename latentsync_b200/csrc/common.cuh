@@ -214,20 +214,38 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// exact-erf GELU (diffusers GEGLU uses F.gelu, approximate="none").  erf by Abramowitz-Stegun 7.1.26 (|abs err| <=
-// 1.5e-7, far below the fp16 store): 2 MUFU + ~12 FMA instead of erff's ~35 instructions - the GEGLU epilogue of the
-// level-0 feed-forward GEMM was bound by erff (ncu: 115 us per launch against 30 us of main loop).
+// MUFU ops in their .ftz form: the default (non-ftz) ex2.approx / division intrinsics expand to FSETP + two predicated
+// FMUL range fix-ups around every MUFU (ncu source view of the GEGLU GEMM: 36 warp instructions per output element,
+// 27 % of them FMUL).  Denormal inputs / results flushed to zero are far below the fp16 store.
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x): 2 MUFU + 3 FP (the plain `x / (1 + __expf(-x))` is a full-precision division: ~10 instructions)
+__device__ __forceinline__ float silu_f(float x) {
+  return x * mufu_rcp(1.0f + mufu_ex2(x * -1.4426950408889634f));
+}
+// exact-erf GELU (diffusers GEGLU uses F.gelu, approximate="none").  erfc by Abramowitz-Stegun 7.1.26 (|abs err| <=
+// 1.5e-7, far below the fp16 store): with z = |x| / sqrt(2), t = 1 / (1 + p z), q = poly(t) t exp(-z^2) = erfc(z):
+//   x >= 0: 0.5 x (2 - q) = x - 0.5 x q        x < 0: 0.5 x q
+// i.e. gelu(x) = max(x, 0) - |0.5 x q|.  The 0.5 is folded into the polynomial: 2 MUFU + 13 FP instructions (erff is
+// ~35; the GEGLU epilogue of the level-0 feed-forward GEMM was bound by it: 115 us per launch against 30 us of main loop).
 __device__ __forceinline__ float gelu_erf_f(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));  // MUFU.RCP (rcp.rn would be a software sequence)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float t = mufu_rcp(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float e = mufu_ex2(x * x * -0.72134752044448170f);  // exp(-x^2 / 2)
+  const float r = x * (poly * t) * e;                        // 0.5 x erfc(|x| / sqrt 2)
+  return fmaxf(x, 0.0f) - fabsf(r);
 }
 
 }  // namespace ls
