@@ -190,6 +190,32 @@ int ls_resize_aa_u8(const float* x, int32_t n, int32_t H, int32_t W, int32_t oh,
  *   ref fp32 [n][3][HW]; mask fp32 [n][1][HW]; out fp32 [n][3][HW]. */
 int ls_paste_back(const float* decoded_cl, int32_t ld, const float* ref, const float* mask, int32_t n, int32_t HW,
                   float* out, void* stream);
+/* ---------------------------------------------------------------------------------------------------------
+ * Inverse-affine paste-back of the generated faces into the video frames.
+ *
+ * Replaces AlignRestore.restore_img (latentsync/utils/affine_transform.py:85-115; called per frame from
+ * LipsyncPipeline.restore_video, lipsync_pipeline.py:343-358), i.e. OpenCV's warpAffine(INTER_LANCZOS4) of the
+ * face, warpAffine of the all-ones mask, erode 2x2, erode (2w x 2w), GaussianBlur(2w+1) and the float blend, for
+ * F frames of one size in one call.  Output bytes equal the reference's (OpenCV 4.13 fixed-point arithmetic
+ * restated, see csrc/restore.cu).  All pointers are device pointers.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct LsRestoreArgs {
+  const void* frames;         /* uint8 [F][H][W][3] video frames */
+  void* out;                  /* uint8 [F][H][W][3]; may alias frames (in place) */
+  const void* faces;          /* uint8 [F][hf][wf][3] generated faces at the box size (restore_video :350-355) */
+  const double* mats;         /* [F][6] dst->src matrices: what cv::warpAffine derives from `inverse_affine` (its
+                                 own double-precision inversion), row-major 2x3 */
+  const int32_t* rois;        /* [F][4] x0, y0, x1, y1: frame rectangle that contains every pixel the face touches */
+  const int16_t* lanczos_tab; /* [32][32][8][8] OpenCV fixed-point Lanczos-4 weights (sum 32768 per entry) */
+  const float* gauss_tab;     /* [gmax + 1][2 gmax + 1]: row w = cv2.getGaussianKernel(2 w + 1, 0, CV_32F) */
+  float* work;                /* 3 * F * RH * RW floats */
+  void* scratch;              /* 12 * F + 4 bytes: uint64 area[F] (sum of the eroded mask * 1024), int32 w_edge[F],
+                                 int32 status (set to 1 when some w_edge > gmax: output then invalid) */
+  int32_t F, H, W, hf, wf;
+  int32_t RW, RH;             /* >= width / height of every ROI */
+  int32_t gmax;
+} LsRestoreArgs;
+int ls_restore_faces(const LsRestoreArgs* args, void* stream);
 /* timestep path (unet.py:361-382, resnet.py:190-205): small dense layers on (B, 1280) vectors.
  *   y[b][n] = act_out( sum_k act_in(x[b][k]) * W[n][k] + bias[n] ) (+ add[n]);  x, y, bias, add fp32; W fp16. */
 int ls_small_linear(const float* x, int32_t B, int32_t K, const void* W, const float* bias, const float* add,

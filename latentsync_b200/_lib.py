@@ -76,6 +76,28 @@ class LsAttnArgs(C.Structure):
     ]
 
 
+class LsRestoreArgs(C.Structure):
+    _fields_ = [
+        ("frames", C.c_void_p),
+        ("out", C.c_void_p),
+        ("faces", C.c_void_p),
+        ("mats", C.c_void_p),
+        ("rois", C.c_void_p),
+        ("lanczos_tab", C.c_void_p),
+        ("gauss_tab", C.c_void_p),
+        ("work", C.c_void_p),
+        ("scratch", C.c_void_p),
+        ("F", C.c_int32),
+        ("H", C.c_int32),
+        ("W", C.c_int32),
+        ("hf", C.c_int32),
+        ("wf", C.c_int32),
+        ("RW", C.c_int32),
+        ("RH", C.c_int32),
+        ("gmax", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/latentsync_b200.h declares (tests check this)
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
@@ -105,6 +127,7 @@ SYMBOLS = {
     "ls_small_linear": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "ls_timestep_embedding": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "ls_fill_zero": (C.c_int, [_vp, _i64, _vp]),
+    "ls_restore_faces": (C.c_int, [C.POINTER(LsRestoreArgs), _vp]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -341,6 +364,26 @@ def resize_aa_u8(x, oh, ow, out) -> None:
     assert x.dtype == torch.float32 and out.dtype == torch.uint8 and x.is_contiguous()
     n, _, H, W = x.shape
     _check(lib().ls_resize_aa_u8(_ptr(x), n, H, W, oh, ow, _ptr(out), _stream()), "ls_resize_aa_u8")
+
+
+def restore_faces(frames, out, faces, mats, rois, lanczos_tab, gauss_tab, work, scratch, RW, RH, gmax) -> None:
+    """frames / out uint8 (F,H,W,3); faces uint8 (F,hf,wf,3); mats float64 (F,6); rois int32 (F,4); see LsRestoreArgs"""
+    assert frames.dtype == torch.uint8 and out.dtype == torch.uint8 and faces.dtype == torch.uint8
+    assert mats.dtype == torch.float64 and rois.dtype == torch.int32 and lanczos_tab.dtype == torch.int16
+    assert gauss_tab.dtype == torch.float32 and work.dtype == torch.float32
+    for t in (frames, out, faces, mats, rois, lanczos_tab, gauss_tab, work, scratch):
+        assert t.is_contiguous()
+    a = LsRestoreArgs()
+    a.frames, a.out, a.faces = _ptr(frames), _ptr(out), _ptr(faces)
+    a.mats, a.rois = _ptr(mats), _ptr(rois)
+    a.lanczos_tab, a.gauss_tab = _ptr(lanczos_tab), _ptr(gauss_tab)
+    a.work, a.scratch = _ptr(work), _ptr(scratch)
+    a.F, a.H, a.W = frames.shape[0], frames.shape[1], frames.shape[2]
+    a.hf, a.wf = faces.shape[1], faces.shape[2]
+    a.RW, a.RH, a.gmax = RW, RH, gmax
+    assert work.numel() >= 3 * a.F * RW * RH and scratch.numel() * scratch.element_size() >= 12 * a.F + 4
+    assert gauss_tab.shape == (gmax + 1, 2 * gmax + 1) and lanczos_tab.numel() == 32 * 32 * 64
+    _check(lib().ls_restore_faces(C.byref(a), _stream()), "ls_restore_faces")
 
 
 def gaussian_sample(moments_cl, ld, noise, n, Cc, HW, shift, scale, z) -> None:

@@ -174,16 +174,16 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
     const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
-    const float al_lo = exp2f((m_lo - mn_lo) * sl), al_hi = exp2f((m_hi - mn_hi) * sl);
+    const float al_lo = mufu_ex2((m_lo - mn_lo) * sl), al_hi = mufu_ex2((m_hi - mn_hi) * sl);
     m_lo = mn_lo;
     m_hi = mn_hi;
     float rs_lo = 0.f, rs_hi = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f((s[nt][0] - mn_lo) * sl);
-      s[nt][1] = exp2f((s[nt][1] - mn_lo) * sl);
-      s[nt][2] = exp2f((s[nt][2] - mn_hi) * sl);
-      s[nt][3] = exp2f((s[nt][3] - mn_hi) * sl);
+      s[nt][0] = mufu_ex2((s[nt][0] - mn_lo) * sl);
+      s[nt][1] = mufu_ex2((s[nt][1] - mn_lo) * sl);
+      s[nt][2] = mufu_ex2((s[nt][2] - mn_hi) * sl);
+      s[nt][3] = mufu_ex2((s[nt][3] - mn_hi) * sl);
       rs_lo += s[nt][0] + s[nt][1];
       rs_hi += s[nt][2] + s[nt][3];
     }
@@ -304,10 +304,10 @@ __global__ void __launch_bounds__(128) attn_short_kernel(const AttnKParams p) {
   float l_lo = 0.f, l_hi = 0.f;
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
-    s[nt][0] = exp2f((s[nt][0] - mx_lo) * sl);
-    s[nt][1] = exp2f((s[nt][1] - mx_lo) * sl);
-    s[nt][2] = exp2f((s[nt][2] - mx_hi) * sl);
-    s[nt][3] = exp2f((s[nt][3] - mx_hi) * sl);
+    s[nt][0] = mufu_ex2((s[nt][0] - mx_lo) * sl);
+    s[nt][1] = mufu_ex2((s[nt][1] - mx_lo) * sl);
+    s[nt][2] = mufu_ex2((s[nt][2] - mx_hi) * sl);
+    s[nt][3] = mufu_ex2((s[nt][3] - mx_hi) * sl);
     l_lo += s[nt][0] + s[nt][1];
     l_hi += s[nt][2] + s[nt][3];
   }

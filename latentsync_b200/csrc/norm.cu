@@ -708,7 +708,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, int64_t rows, i
     if (vi < nvec) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        v[i][e] = exp2f((v[i][e] - mx) * sl);
+        v[i][e] = mufu_ex2((v[i][e] - mx) * sl);
         sum += v[i][e];
       }
     }

@@ -1,0 +1,296 @@
+// Inverse-affine paste-back of the generated faces into the video frames, batched over frames.
+//
+// Replaces AlignRestore.restore_img (latentsync/utils/affine_transform.py:85-115), which the reference runs per frame on
+// the CPU through OpenCV (opencv-python 4.x; 4.13.0 in this image): cv2.warpAffine(face, INTER_LANCZOS4),
+// cv2.warpAffine(ones) (bilinear), two cv2.erode, cv2.GaussianBlur and a float blend truncated to uint8.  The kernels
+// restate OpenCV's published algorithms so that the result is the same BYTES (tests/test_restore_gpu.py):
+//   * source coordinates in fixed point exactly as cv::warpAffine computes them: dst->src matrix in double,
+//     X = (rint((M1 y + M2) 1024) + 16 + rint(M0 x 1024)) >> 5, integer part X >> 5, 5-bit fraction X & 31;
+//   * Lanczos-4 (8 x 8 taps) with OpenCV's 32 x 32 table of int16 weights (sum 32768 per entry, built on the host by
+//     latentsync_b200/restore.py the way initInterTab2D does), int32 accumulation, (sum + 2^14) >> 15, saturate;
+//     taps outside the face contribute 0 (BORDER_CONSTANT, value 0);
+//   * the all-ones mask warped bilinearly has the closed form sum of in-bounds (1 - fy | fy)(1 - fx | fx);
+//   * erode = min over the structuring rectangle, pixels outside the frame ignored; separable;
+//   * GaussianBlur (float, BORDER_REFLECT_101): rows accumulate left to right with FMA, columns accumulate
+//     k[0] p0 + sum_j k[j] (p[+j] + p[-j]) with FMA - the order of OpenCV's AVX2 row / symmetric column filters, which is
+//     what makes the plateau of the soft mask come out as the same float (1.0 or 1.0000001) as on the CPU;
+//   * blend m (e r) + (1 - m) u with separately rounded float32 operations (numpy), truncation to uint8.
+// Everything but the final blend only exists inside the face's bounding box in the frame (the ROI, computed on the
+// host); outside it the output is the input frame, copied with one cudaMemcpyAsync (or nothing when in place).
+//
+// Memory-bound byte / float work: no tensor cores.  Per 1080p frame: 6.2 MB frame copy + ~12 B per ROI pixel of mask
+// planes + the 176 KB face read through L1/L2.
+#include "common.cuh"
+#include "../../include/latentsync_b200.h"
+
+#include <atomic>
+
+namespace ls {
+
+extern std::atomic<int64_t> g_launch_count;
+
+struct RestoreP {
+  const uint8_t* frames;   // [F][H][W][3]
+  uint8_t* out;            // [F][H][W][3]
+  const uint8_t* faces;    // [F][hf][wf][3]
+  const double* mats;      // [F][6] dst -> src
+  const int* rois;         // [F][4] x0, y0, x1, y1 (inside the frame)
+  const int16_t* ltab;     // [32][32][8][8]
+  const float* gtab;       // [gmax + 1][2 gmax + 1]
+  float* e2;               // [F][RH][RW]
+  float* t0;               // [F][RH][RW]
+  float* t1;               // [F][RH][RW]
+  unsigned long long* area;  // [F] sum of e2 * 1024
+  int* wedge;              // [F]
+  int* status;             // [1] != 0: w_edge beyond the Gaussian table
+  int F, H, W, hf, wf, RW, RH, gmax;
+};
+
+// cv::saturate_cast<int>(double) == cvRound: round half to even
+__device__ __forceinline__ int cv_round(double v) { return __double2int_rn(v); }
+
+// fixed-point source coordinate of dst pixel (x, y): integer parts and 5-bit fractions (imgwarp.cpp, WarpAffineInvoker)
+__device__ __forceinline__ void src_coord(const double* M, int x, int y, int& sx, int& sy, int& fx, int& fy) {
+  const int adelta = cv_round(__dmul_rn(__dmul_rn(M[0], (double)x), 1024.0));
+  const int bdelta = cv_round(__dmul_rn(__dmul_rn(M[3], (double)x), 1024.0));
+  const int X0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]), 1024.0)) + 16;
+  const int Y0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]), 1024.0)) + 16;
+  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  sx = max(-32768, min(32767, X >> 5));  // saturate_cast<short>
+  sy = max(-32768, min(32767, Y >> 5));
+  fx = X & 31;
+  fy = Y & 31;
+}
+
+// cv2.warpAffine(ones(hf, wf) float32, ...) at dst pixel (x, y): in-bounds bilinear weights
+__device__ __forceinline__ float mask_at(const double* M, int x, int y, int wf, int hf) {
+  int sx, sy, fx, fy;
+  src_coord(M, x, y, sx, sy, fx, fy);
+  if (sx < -1 || sy < -1 || sx >= wf || sy >= hf) return 0.f;
+  const float tx = (float)fx * 0.03125f, ty = (float)fy * 0.03125f;
+  const float wx[2] = {1.0f - tx, tx}, wy[2] = {1.0f - ty, ty};
+  float s = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 2; ++kx) {
+      const int xx = sx + kx, yy = sy + ky;
+      if (xx >= 0 && xx < wf && yy >= 0 && yy < hf) s = __fadd_rn(s, __fmul_rn(wy[ky], wx[kx]));
+    }
+  return s;
+}
+
+// (1) e2 = erode(mask, 2 x 2) (anchor (1, 1): window {y - 1, y} x {x - 1, x}) and the exact sum of e2 per frame
+__global__ void __launch_bounds__(256) restore_mask_kernel(const RestoreP p) {
+  pdl_prologue();
+  const int f = blockIdx.z;
+  const int* roi = p.rois + 4 * f;
+  const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
+  const int x = roi[0] + rx, y = roi[1] + ry;
+  unsigned int fix = 0;
+  if (x < roi[2] && y < roi[3]) {
+    double M[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) M[i] = p.mats[6 * f + i];
+    float e = INFINITY;
+#pragma unroll
+    for (int dy = -1; dy <= 0; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 0; ++dx) {
+        const int xx = x + dx, yy = y + dy;
+        if (xx >= 0 && yy >= 0) e = fminf(e, mask_at(M, xx, yy, p.wf, p.hf));
+      }
+    p.e2[((size_t)f * p.RH + ry) * p.RW + rx] = e;
+    fix = (unsigned int)(e * 1024.0f);  // multiples of 1 / 1024: exact
+  }
+  // block sum -> one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fix += __shfl_xor_sync(0xffffffffu, fix, o);
+  if (threadIdx.x == 0 && fix != 0) atomicAdd(p.area + f, (unsigned long long)fix);
+}
+
+// (2) w_edge = int(sqrt(float32 sum)) // 20 (affine_transform.py:101-102)
+__global__ void restore_wedge_kernel(const RestoreP p) {
+  pdl_prologue();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.F) return;
+  const float area = (float)((double)p.area[f] * (1.0 / 1024.0));
+  const int w = (int)sqrtf(area) / 20;
+  p.wedge[f] = w;
+  if (w > p.gmax) atomicExch(p.status, 1);
+}
+
+// value of a ROI plane at absolute frame position (x, y), y / x inside the frame: 0 outside the ROI
+__device__ __forceinline__ float plane_at(const float* pl, const int* roi, int RW, int x, int y) {
+  if (x < roi[0] || x >= roi[2] || y < roi[1] || y >= roi[3]) return 0.f;
+  return pl[(size_t)(y - roi[1]) * RW + (x - roi[0])];
+}
+
+// (3) erode with ones(2 w, 2 w) (anchor (w, w): offsets -w .. w - 1), rows then columns.  w == 0: cv2 substitutes a
+// 3 x 3 rectangle for the empty kernel (offsets -1 .. 1).
+template <bool ROWS>
+__global__ void __launch_bounds__(256) restore_erode_kernel(const RestoreP p, const float* __restrict__ src,
+                                                            float* __restrict__ dst) {
+  pdl_prologue();
+  const int f = blockIdx.z;
+  const int* roi = p.rois + 4 * f;
+  const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
+  const int x = roi[0] + rx, y = roi[1] + ry;
+  if (x >= roi[2] || y >= roi[3]) return;
+  const int w = p.wedge[f];
+  const int lo = (w == 0) ? -1 : -w, hi = (w == 0) ? 1 : w - 1;
+  const float* pl = src + (size_t)f * p.RH * p.RW;
+  float e = INFINITY;
+  for (int d = lo; d <= hi; ++d) {
+    const int xx = ROWS ? x + d : x, yy = ROWS ? y : y + d;
+    if (xx < 0 || yy < 0 || xx >= p.W || yy >= p.H) continue;  // outside the frame: ignored
+    e = fminf(e, plane_at(pl, roi, p.RW, xx, yy));
+    if (e == 0.f) break;
+  }
+  dst[((size_t)f * p.RH + ry) * p.RW + rx] = e;
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+// (4) GaussianBlur (2 w + 1) x (2 w + 1), sigma from the kernel size; rows: sequential FMA; columns: symmetric FMA
+template <bool ROWS>
+__global__ void __launch_bounds__(256) restore_blur_kernel(const RestoreP p, const float* __restrict__ src,
+                                                           float* __restrict__ dst) {
+  pdl_prologue();
+  const int f = blockIdx.z;
+  const int* roi = p.rois + 4 * f;
+  const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
+  const int x = roi[0] + rx, y = roi[1] + ry;
+  if (x >= roi[2] || y >= roi[3]) return;
+  const int w = p.wedge[f];
+  const float* pl = src + (size_t)f * p.RH * p.RW;
+  const size_t o = ((size_t)f * p.RH + ry) * p.RW + rx;
+  if (w == 0 || w > p.gmax) {  // 1 x 1 kernel: identity
+    dst[o] = pl[(size_t)ry * p.RW + rx];
+    return;
+  }
+  const float* k = p.gtab + (size_t)w * (2 * p.gmax + 1);
+  float s;
+  if (ROWS) {
+    s = __fmul_rn(plane_at(pl, roi, p.RW, reflect101(x - w, p.W), y), k[0]);
+    for (int j = 1; j <= 2 * w; ++j) s = __fmaf_rn(plane_at(pl, roi, p.RW, reflect101(x - w + j, p.W), y), k[j], s);
+  } else {
+    s = __fmul_rn(plane_at(pl, roi, p.RW, x, y), k[w]);
+    for (int j = 1; j <= w; ++j) {
+      const float a = plane_at(pl, roi, p.RW, x, reflect101(y + j, p.H));
+      const float b = plane_at(pl, roi, p.RW, x, reflect101(y - j, p.H));
+      s = __fmaf_rn(__fadd_rn(a, b), k[w + j], s);
+    }
+  }
+  dst[o] = s;
+}
+
+// (5) Lanczos-4 warp of the face + blend, ROI pixels only
+__global__ void __launch_bounds__(256) restore_blend_kernel(const RestoreP p, const float* __restrict__ soft) {
+  pdl_prologue();
+  const int f = blockIdx.z;
+  const int* roi = p.rois + 4 * f;
+  const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
+  const int x = roi[0] + rx, y = roi[1] + ry;
+  if (x >= roi[2] || y >= roi[3]) return;
+  const size_t o = ((size_t)f * p.RH + ry) * p.RW + rx;
+  const float m = soft[o], e = p.e2[o];
+  const size_t pix = (((size_t)f * p.H + y) * p.W + x) * 3;
+  if (m == 0.f) {  // 0 * (e r) + 1 * u == u
+    if (p.out != p.frames) {
+      p.out[pix] = p.frames[pix];
+      p.out[pix + 1] = p.frames[pix + 1];
+      p.out[pix + 2] = p.frames[pix + 2];
+    }
+    return;
+  }
+  int acc[3] = {0, 0, 0};
+  if (e != 0.f) {
+    double M[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) M[i] = p.mats[6 * f + i];
+    int sx, sy, fx, fy;
+    src_coord(M, x, y, sx, sy, fx, fy);
+    const int16_t* wt = p.ltab + (size_t)(fy * 32 + fx) * 64;
+    const uint8_t* face = p.faces + (size_t)f * p.hf * p.wf * 3;
+    for (int ky = 0; ky < 8; ++ky) {
+      const int yy = sy - 3 + ky;
+      if (yy < 0 || yy >= p.hf) continue;
+      const uint8_t* row = face + (size_t)yy * p.wf * 3;
+#pragma unroll
+      for (int kx = 0; kx < 8; ++kx) {
+        const int xx = sx - 3 + kx;
+        if (xx < 0 || xx >= p.wf) continue;
+        const int wv = wt[ky * 8 + kx];
+        acc[0] += wv * row[xx * 3];
+        acc[1] += wv * row[xx * 3 + 1];
+        acc[2] += wv * row[xx * 3 + 2];
+      }
+    }
+  }
+  const float om = __fsub_rn(1.0f, m);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int r8 = max(0, min(255, (acc[c] + (1 << 14)) >> 15));
+    const float v = __fadd_rn(__fmul_rn(m, __fmul_rn(e, (float)r8)), __fmul_rn(om, (float)p.frames[pix + c]));
+    p.out[pix + c] = (uint8_t)(int)v;  // numpy astype(uint8): truncation
+  }
+}
+
+static int restore_impl(const LsRestoreArgs* a, cudaStream_t stream) {
+  LS_CHECK(a != nullptr, "ls_restore_faces: null args");
+  LS_CHECK(a->F >= 1 && a->H >= 1 && a->W >= 1 && a->hf >= 8 && a->wf >= 8, "ls_restore_faces: bad geometry");
+  LS_CHECK(a->H < 32768 && a->W < 32768, "ls_restore_faces: frame larger than OpenCV's short coordinates");
+  LS_CHECK(a->RW >= 1 && a->RH >= 1 && a->gmax >= 1, "ls_restore_faces: bad ROI / table size");
+  LS_CHECK(a->frames && a->out && a->faces && a->mats && a->rois && a->lanczos_tab && a->gauss_tab && a->work &&
+               a->scratch,
+           "ls_restore_faces: null pointer");
+  RestoreP p;
+  p.frames = reinterpret_cast<const uint8_t*>(a->frames);
+  p.out = reinterpret_cast<uint8_t*>(a->out);
+  p.faces = reinterpret_cast<const uint8_t*>(a->faces);
+  p.mats = a->mats;
+  p.rois = a->rois;
+  p.ltab = a->lanczos_tab;
+  p.gtab = a->gauss_tab;
+  const size_t plane = (size_t)a->F * a->RH * a->RW;
+  p.e2 = a->work;
+  p.t0 = a->work + plane;
+  p.t1 = a->work + 2 * plane;
+  // scratch: F x uint64 area | F x int32 w_edge | int32 status
+  p.area = reinterpret_cast<unsigned long long*>(a->scratch);
+  p.wedge = reinterpret_cast<int*>(p.area + a->F);
+  p.status = p.wedge + a->F;
+  p.F = a->F;
+  p.H = a->H;
+  p.W = a->W;
+  p.hf = a->hf;
+  p.wf = a->wf;
+  p.RW = a->RW;
+  p.RH = a->RH;
+  p.gmax = a->gmax;
+  LS_CUDA(cudaMemsetAsync(a->scratch, 0, (size_t)a->F * 12 + 4, stream));
+  if (p.out != p.frames)
+    LS_CUDA(cudaMemcpyAsync(p.out, p.frames, (size_t)a->F * a->H * a->W * 3, cudaMemcpyDeviceToDevice, stream));
+  const dim3 block(32, 8), grid((a->RW + 31) / 32, (a->RH + 7) / 8, a->F);
+  LS_CUDA(launch_k(restore_mask_kernel, grid, block, (size_t)0, stream, p));
+  LS_CUDA(launch_k(restore_wedge_kernel, dim3((a->F + 127) / 128), dim3(128), (size_t)0, stream, p));
+  LS_CUDA(launch_k(restore_erode_kernel<true>, grid, block, (size_t)0, stream, p, (const float*)p.e2, p.t0));
+  LS_CUDA(launch_k(restore_erode_kernel<false>, grid, block, (size_t)0, stream, p, (const float*)p.t0, p.t1));
+  LS_CUDA(launch_k(restore_blur_kernel<true>, grid, block, (size_t)0, stream, p, (const float*)p.t1, p.t0));
+  LS_CUDA(launch_k(restore_blur_kernel<false>, grid, block, (size_t)0, stream, p, (const float*)p.t0, p.t1));
+  LS_CUDA(launch_k(restore_blend_kernel, grid, block, (size_t)0, stream, p, (const float*)p.t1));
+  LS_CUDA(cudaGetLastError());
+  g_launch_count.fetch_add(7, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // namespace ls
+
+extern "C" int ls_restore_faces(const LsRestoreArgs* args, void* stream) {
+  return ls::restore_impl(args, reinterpret_cast<cudaStream_t>(stream));
+}
