@@ -334,6 +334,61 @@ def main():
                        "what": "encode(masked) + encode(ref) + 20-step loop + decode + paste, pixels from pinned host "
                                "memory, frames back to host"}
 
+    # ---- informational: inverse-affine paste-back of 16 faces into 1080p frames, device-resident
+    # and from / to pinned host memory; the reference's per-frame OpenCV path timed on the host cores beside it
+    restore = None
+    if rank == 0 and world == 1:
+        import numpy as np
+        from latentsync_b200.restore import FaceRestorer
+        from oracle import restore_ref as RR
+
+        cases = [RR.synthetic_case(500 + i, 1080, 1920, (0.45, 0.6), (500.0, 700.0)) for i in range(FRAMES)]
+        frames_h = torch.from_numpy(np.stack([c[0] for c in cases])).pin_memory()
+        faces_h = torch.from_numpy(np.stack([c[1] for c in cases])).pin_memory()
+        mats = [c[2] for c in cases]
+        fr_out_h = torch.empty_like(frames_h).pin_memory()
+        restorer = FaceRestorer(dev)
+        frames_d, faces_d = frames_h.to(dev), faces_h.to(dev)
+        out_d = torch.empty_like(frames_d)
+
+        def timed_ms(fn, n=5):
+            fn(); fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        ms_dev = timed_ms(lambda: restorer.restore_imgs(frames_d, faces_d, mats, out=out_d))
+        ms_host = timed_ms(lambda: fr_out_h.copy_(restorer.restore_imgs(frames_h, faces_h, mats), non_blocking=True))
+        _, rois, _, _ = restorer.plan(mats, RR.FACE_W, RR.FACE_H, 1920, 1080)
+        roi_px = int(((rois[:, 2] - rois[:, 0]) * (rois[:, 3] - rois[:, 1])).sum())
+        # algorithmic bytes: frame read + write (u8 x 3), the face once, per ROI pixel the e2 / soft-mask planes once each
+        # way (2 x 2 x 4 B) and the ROI frame bytes once more each way for the blend
+        alg_bytes = 2 * frames_d.numel() + faces_d.numel() + roi_px * (16 + 6)
+        t0 = time.perf_counter()
+        ncpu = 4
+        for i in range(ncpu):
+            RR.restore_img_cv2(*cases[i])
+        t_cpu = (time.perf_counter() - t0) / ncpu
+        restore = {"value": FRAMES / (ms_dev * 1e-3), "unit": "frames/s", "ms_per_16_frames": ms_dev,
+                   "e2e": {"value": FRAMES / (ms_host * 1e-3), "unit": "frames/s",
+                           "h2d_bytes_per_step": frames_h.numel() + faces_h.numel(),
+                           "d2h_bytes_per_step": fr_out_h.numel()},
+                   "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms_dev * 1e-3) / 1e9, "peak": peak_bw,
+                                "unit": "GB/s", "frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / peak_bw,
+                                "traffic": None, "algorithmic_bytes": alg_bytes, "roi_pixels": roi_px},
+                   "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "frames/s", "cores": os.cpu_count() or 1,
+                                    "kind": "reference",
+                                    "sample": f"{ncpu} frames through the reference's OpenCV call sequence "
+                                              "(oracle.restore_ref.restore_img_cv2 = affine_transform.py:85-115), "
+                                              "cv2's own thread pool"},
+                   "what": "AlignRestore.restore_img for 16 x 1080p frames, ~400 px faces, byte-exact vs OpenCV "
+                           "(tests/test_restore_gpu.py); 7 launches + 1 D2D copy per call"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -371,6 +426,7 @@ def main():
                                         "achieved": seg_flops * args.steps / (ms_total * 1e-3) / 1e12 / 1.0,
                                         "frac": seg_flops * args.steps / (ms_total * 1e-3) / 1e12 / peak_tf}},
             "from_pixels": from_pixels,
+            "restore": restore,
             "cpu_baseline": cpu,
         }))
     if world > 1:

@@ -212,6 +212,7 @@ typedef struct LsRestoreArgs {
   void* scratch;              /* 12 * F + 4 bytes: uint64 area[F] (sum of the eroded mask * 1024), int32 w_edge[F],
                                  int32 status (set to 1 when some w_edge > gmax: output then invalid) */
   int32_t F, H, W, hf, wf;
+  int32_t mh, mw;             /* size of the all-ones mask (AlignRestore.face_size = 280 x 210); 0: same as the face */
   int32_t RW, RH;             /* >= width / height of every ROI */
   int32_t gmax;
 } LsRestoreArgs;

@@ -92,6 +92,8 @@ class LsRestoreArgs(C.Structure):
         ("W", C.c_int32),
         ("hf", C.c_int32),
         ("wf", C.c_int32),
+        ("mh", C.c_int32),
+        ("mw", C.c_int32),
         ("RW", C.c_int32),
         ("RH", C.c_int32),
         ("gmax", C.c_int32),
@@ -366,7 +368,7 @@ def resize_aa_u8(x, oh, ow, out) -> None:
     _check(lib().ls_resize_aa_u8(_ptr(x), n, H, W, oh, ow, _ptr(out), _stream()), "ls_resize_aa_u8")
 
 
-def restore_faces(frames, out, faces, mats, rois, lanczos_tab, gauss_tab, work, scratch, RW, RH, gmax) -> None:
+def restore_faces(frames, out, faces, mats, rois, lanczos_tab, gauss_tab, work, scratch, RW, RH, gmax, mh=0, mw=0) -> None:
     """frames / out uint8 (F,H,W,3); faces uint8 (F,hf,wf,3); mats float64 (F,6); rois int32 (F,4); see LsRestoreArgs"""
     assert frames.dtype == torch.uint8 and out.dtype == torch.uint8 and faces.dtype == torch.uint8
     assert mats.dtype == torch.float64 and rois.dtype == torch.int32 and lanczos_tab.dtype == torch.int16
@@ -380,6 +382,7 @@ def restore_faces(frames, out, faces, mats, rois, lanczos_tab, gauss_tab, work, 
     a.work, a.scratch = _ptr(work), _ptr(scratch)
     a.F, a.H, a.W = frames.shape[0], frames.shape[1], frames.shape[2]
     a.hf, a.wf = faces.shape[1], faces.shape[2]
+    a.mh, a.mw = mh, mw
     a.RW, a.RH, a.gmax = RW, RH, gmax
     assert work.numel() >= 3 * a.F * RW * RH and scratch.numel() * scratch.element_size() >= 12 * a.F + 4
     assert gauss_tab.shape == (gmax + 1, 2 * gmax + 1) and lanczos_tab.numel() == 32 * 32 * 64

@@ -43,7 +43,7 @@ struct RestoreP {
   unsigned long long* area;  // [F] sum of e2 * 1024
   int* wedge;              // [F]
   int* status;             // [1] != 0: w_edge beyond the Gaussian table
-  int F, H, W, hf, wf, RW, RH, gmax;
+  int F, H, W, hf, wf, mh, mw, RW, RH, gmax;  // mask: ones(mh, mw) (AlignRestore.face_size), face: hf x wf
 };
 
 // cv::saturate_cast<int>(double) == cvRound: round half to even
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) restore_mask_kernel(const RestoreP p) {
 #pragma unroll
       for (int dx = -1; dx <= 0; ++dx) {
         const int xx = x + dx, yy = y + dy;
-        if (xx >= 0 && yy >= 0) e = fminf(e, mask_at(M, xx, yy, p.wf, p.hf));
+        if (xx >= 0 && yy >= 0) e = fminf(e, mask_at(M, xx, yy, p.mw, p.mh));
       }
     p.e2[((size_t)f * p.RH + ry) * p.RW + rx] = e;
     fix = (unsigned int)(e * 1024.0f);  // multiples of 1 / 1024: exact
@@ -270,6 +270,8 @@ static int restore_impl(const LsRestoreArgs* a, cudaStream_t stream) {
   p.W = a->W;
   p.hf = a->hf;
   p.wf = a->wf;
+  p.mh = a->mh > 0 ? a->mh : a->hf;
+  p.mw = a->mw > 0 ? a->mw : a->wf;
   p.RW = a->RW;
   p.RH = a->RH;
   p.gmax = a->gmax;

@@ -484,22 +484,29 @@ class LipsyncPipeline:
                        f"awk '{{print $1-{padding_duration}}}') {video_out_path}")
         subprocess.run(command, shell=True)
 
-    def _restore_video(self, faces, video_frames, boxes, affine_matrices):
-        """lipsync_pipeline.py:343-358: resize -> uint8 on the GPU (faces_to_uint8), then the reference's own cv2 inverse
-        affine paste per frame (AlignRestore.restore_img, untouched)"""
+    def _restore_video(self, faces, video_frames, boxes, affine_matrices, frames_per_call: int = 32):
+        """lipsync_pipeline.py:343-358 on the GPU: anti-aliased resize -> uint8 (faces_to_uint8, ls_resize_aa_u8), then
+        the inverse-affine paste-back of AlignRestore.restore_img (affine_transform.py:85-115) for `frames_per_call`
+        frames per launch (restore.FaceRestorer, ls_restore_faces: the same bytes as the reference's per-frame cv2
+        path).  Returns the restored frames as one uint8 array (n, H, W, 3) like restore_video."""
         import numpy as np
 
-        video_frames = video_frames[: len(faces)]
-        out_frames = []
-        # resize + uint8 conversion on the GPU, batched over the frames that share a box size (usually all of them)
-        sizes = [(int(b[3] - b[1]), int(b[2] - b[0])) for b in boxes[: len(faces)]]
-        u8 = [None] * len(faces)
-        for hw in sorted(set(sizes)):
+        from .restore import FaceRestorer
+
+        n = len(faces)
+        video_frames = np.asarray(video_frames[:n])
+        if getattr(self, "_face_restorer", None) is None:
+            self._face_restorer = FaceRestorer(self.device)
+        restorer = self._face_restorer
+        sizes = [(int(b[3] - b[1]), int(b[2] - b[0])) for b in boxes[:n]]
+        out = np.empty_like(video_frames)
+        for hw in sorted(set(sizes)):  # frames that share a box size go together (usually all of them)
             idx = [i for i, s in enumerate(sizes) if s == hw]
-            batch = self.faces_to_uint8(torch.stack([faces[i] for i in idx]), hw[0], hw[1]).cpu().numpy()
-            for k, i in enumerate(idx):
-                u8[i] = batch[k]
-        for index in range(len(faces)):
-            out_frames.append(self.image_processor.restorer.restore_img(video_frames[index], u8[index],
-                                                                        affine_matrices[index]))
-        return np.stack(out_frames, axis=0)
+            for c0 in range(0, len(idx), frames_per_call):
+                chunk = idx[c0:c0 + frames_per_call]
+                u8 = self.faces_to_uint8(torch.stack([faces[i] for i in chunk]), hw[0], hw[1])
+                mats = [affine_matrices[i] for i in chunk]
+                res = restorer.restore_imgs(video_frames[chunk], u8, mats)
+                restorer.check_status()
+                out[chunk] = res.cpu().numpy()
+        return out

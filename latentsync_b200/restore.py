@@ -17,6 +17,7 @@ import torch
 
 from . import _lib as L
 
+FACE_SIZE = (210, 280)  # AlignRestore.face_size (w, h) = (int(75 * 2.8), int(100 * 2.8)), affine_transform.py:40-43
 GMAX = 128  # largest w_edge with a precomputed Gaussian kernel (w_edge = sqrt(face area in the frame) // 20)
 
 
@@ -135,7 +136,7 @@ class FaceRestorer:
             a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
             inv = invert_affine(np.asarray(a, np.float64).reshape(2, 3))  # affine_transform.py:89 (upscale_factor == 1)
             mats[i] = invert_affine(inv).reshape(6)                        # cv::warpAffine's own inversion
-            rois[i] = face_roi(inv, wf, hf, W, H)
+            rois[i] = face_roi(inv, max(wf, FACE_SIZE[0]), max(hf, FACE_SIZE[1]), W, H)
         rw = int(max(1, (rois[:, 2] - rois[:, 0]).max()))
         rh = int(max(1, (rois[:, 3] - rois[:, 1]).max()))
         return mats, rois, rw, rh
@@ -162,7 +163,8 @@ class FaceRestorer:
         scratch = torch.empty(3 * F + 1, dtype=torch.int32, device=self.device)
         if out is None:
             out = torch.empty_like(fr)
-        L.restore_faces(fr, out, fc, mats_d, rois_d, self.lanczos, self.gauss, work, scratch, rw, rh, GMAX)
+        L.restore_faces(fr, out, fc, mats_d, rois_d, self.lanczos, self.gauss, work, scratch, rw, rh, GMAX,
+                        mh=FACE_SIZE[1], mw=FACE_SIZE[0])  # the mask is ones(face_size) whatever the face (:97)
         self._last_scratch = scratch
         return out
 

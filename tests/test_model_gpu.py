@@ -307,6 +307,31 @@ def test_pixel_pre_and_post_processing_vs_oracle():
         assert got.shape == (4, h, w, 3) and diff.max().item() <= 1 and frac < 2e-3
 
 
+def test_restore_video_stage_vs_opencv():
+    """SURVEY.md §8f rank 3 through the pipeline: LipsyncPipeline.restore_video (lipsync_pipeline.py:343-358) = resize
+    + uint8 (rank 2 kernel) + AlignRestore.restore_img per frame; the GPU stage must give the bytes OpenCV gives for
+    the same uint8 faces, for frames with two different box sizes and more frames than one launch takes"""
+    import numpy as np
+    pytest.importorskip("cv2")
+    from oracle import restore_ref as RR
+
+    pipe, _ = get_pipe("tiny")
+    g = torch.Generator().manual_seed(77)
+    n = 7
+    dec = torch.rand(n, 3, 256, 256, generator=g) * 2.2 - 1.1
+    cases = [RR.synthetic_case(400 + i, 360, 640, (0.9, 1.5), (40.0, 200.0)) for i in range(n)]
+    frames = np.stack([c[0] for c in cases])
+    boxes = [[0, 0, 210, 280]] * 5 + [[0, 0, 200, 260]] * 2
+    mats = [c[2] for c in cases]
+    out = pipe._restore_video(dec, frames, boxes, mats, frames_per_call=3)
+    assert out.shape == frames.shape and out.dtype == np.uint8
+    for i in range(n):
+        h, w = boxes[i][3], boxes[i][2]
+        face = pipe.faces_to_uint8(dec[i:i + 1], h, w).cpu().numpy()[0]
+        ref = RR.restore_img_cv2(frames[i], face, mats[i])  # off-size boxes: the mask stays ones(280, 210) (:97)
+        assert np.array_equal(out[i], ref), f"frame {i}: {(out[i] != ref).sum()} bytes differ"
+
+
 def _need(path):
     if not os.path.exists(path):
         pytest.skip(f"{os.path.basename(path)} not generated yet (python -m oracle.make_golden stage2)")
