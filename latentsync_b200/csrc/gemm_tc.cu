@@ -104,6 +104,7 @@ struct GemmKParams {
   int ldo;
   int flags;
   int tma_store;
+  int epi_alt;           // 1: the two epilogue groups take alternate tiles (launches with >= 3 tiles per CTA)
   int splits;            // split-K factor: `splits` CTAs share one output tile, each reducing `kb_per` k-blocks
   int kb_per;
   float* ws;             // split-K partials, fp32 [splits][M][N] (library-owned scratch)
@@ -407,7 +408,9 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8 * CTAS);  // one arrival per epilogue warp of every CTA of the pair
+      // one arrival per epilogue warp that reads the accumulator: all 8 (split-K, legacy path) or the 4 of the group
+      // that owns the tile (epi_alt: the two groups take alternate tiles)
+      mbar_init(&tmem_empty[a], (p.epi_alt ? 4 : 8) * CTAS);
     }
     fence_barrier_init();
   }
@@ -554,7 +557,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       // wait for the PREVIOUS store per slab.  (With one store per 128-row slab issued behind a 128-thread barrier
       // and a wait on the preceding store, each slab cost ~1500 clocks of latency: a K = 64 GEMM took as long as K = 320.)
       uint8_t* my_stage = staging + warp * 2 * WSLAB_BYTES;  // 32 rows x 128 bytes
-      constexpr int NSLAB_MAX = 4;  // slabs per group at BN = 256
+      constexpr int NSLAB_MAX = 4;  // split-K parking: slabs per group at BN = 256
       const int nslab = geglu ? BN / 64 : BN / 32;
       const int n_out_total = geglu ? p.N / 2 : p.N;
       const int gtid = (warp - 4 * group) * 32 + lane;  // 0..127 inside the group
@@ -581,7 +584,14 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           bias_next[k] = (c < BN && nt * BN + c < p.N) ? __ldg(brow + c) : 0.f;
         }
       };
-      fetch_bias(unit);
+      // With >= 3 tiles per CTA (host: epi_alt) the two groups take ALTERNATE tiles (group g owns accumulator g): the
+      // per-tile serial part (decode, bias row, residual prefetch, barriers: ~1700 clocks) of one group overlaps the slab
+      // work of the other (level-0 short-K linear 18.0 -> 16.5 us).  With one or two tiles per CTA both groups share
+      // every tile (contiguous halves of its slabs), which finishes a lone tile sooner.
+      const bool alt = (p.epi_alt != 0);
+      const int w_first = unit + (alt ? group * nunits : 0);
+      const int w_step = alt ? 2 * nunits : nunits;
+      fetch_bias(w_first);
 #ifdef LS_GEMM_PROBE
       long long ep[5][12];
       for (int i = 0; i < 5; ++i)
@@ -591,7 +601,8 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
 #else
 #define EP_STAMP(k) do {} while (0)
 #endif
-      for (int w = unit; w < total_work; w += nunits, ++lt) {
+      lt = alt ? group : 0;
+      for (int w = w_first; w < total_work; w += w_step, lt += (alt ? 2 : 1)) {
         const int tile = (int)fdiv((uint32_t)w, p.fd_splits);
         const int sp = w - tile * p.splits;
         const int acc = lt & 1;
@@ -607,11 +618,12 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         const bool tile_ok = m0 < p.M;
         EP_STAMP(8);
         const int g0 = (group + lt) & 1;  // split-K parking: slab parity of this group alternates per tile
-        // normal path: contiguous slab range; with an odd slab count the larger half alternates (5 = 3 + 2, then 2 + 3)
+        // normal path: the group's slabs [j_lo, j_hi) are stored in pairs from j_lo on, an odd count leaves a single
+        // shared tile: with an odd slab count the larger half alternates between the groups (5 = 3 + 2, then 2 + 3)
         const int n_first = ((lt & 1) == 0) ? (nslab + 1) / 2 : nslab / 2;
-        const int j_lo = group == 0 ? 0 : n_first;
-        const int j_hi = group == 0 ? n_first : nslab;
-        const int n_mine = j_hi - j_lo;  // slabs are stored in pairs from j_lo on, an odd count leaves a single
+        const int j_lo = alt ? 0 : (group == 0 ? 0 : n_first);
+        const int j_hi = alt ? nslab : (group == 0 ? n_first : nslab);
+        const int n_mine = j_hi - j_lo;
         // (1) this tile's bias row (host guarantees one row per tile: bias_div % 128 == 0) -> the group's smem row.  Its
         //     previous contents were last read before the final slab barrier of the previous tile.
         float* my_bias = bias_sm + group * 256;
@@ -635,7 +647,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         fetch_res(0, res[0]);
         fetch_res(1, res[1]);
         EP_STAMP(10);
-        fetch_bias(w + nunits);  // (3) next work item's bias row -> registers
+        fetch_bias(w + w_step);  // (3) this group's next work item's bias row -> registers
         EP_STAMP(0);
         named_bar_sync(1 + group, 128);  // bias row visible to the group
         EP_STAMP(1);
@@ -754,8 +766,11 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         // only the epilogue counts): a store costs its issuer ~450 clocks whatever the box, so 32-column boxes
         // (64-byte rows) made the TMA unit the bound of every short-K launch at ~16 B/clk/SM; coalesced st.global
         // from the staging buffer was slower still (15.0 vs 11.5 us at M = 32768, N = 320).
+#pragma unroll 1
+        for (int pi = 0; 2 * pi < n_mine; ++pi) {
 #pragma unroll
-        for (int s = 0; s < NSLAB_MAX; ++s) {
+        for (int hs = 0; hs < 2; ++hs) {
+          const int s = 2 * pi + hs;
           const int j = j_lo + s;
           if (j >= j_hi) break;
           const int ncol0 = geglu ? nt * (BN / 2) + j * 32 : nt * BN + j * 32;  // first output column of the slab
@@ -801,7 +816,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             if (ncol0 + 32 <= n_out_total) {
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4) {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&res[s & 1][e4]);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&res[hs][e4]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 t = __half22float2(h2[e]);
@@ -815,7 +830,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
               for (int e = 0; e < 32; ++e)
                 if (ncol0 + e < n_out_total) f[e] += __half2float(rr[e]);
             }
-            if (s + 2 < NSLAB_MAX) fetch_res(s + 2, res[s & 1]);  // refill the buffer just consumed
+            fetch_res(s + 2, res[hs]);  // refill the buffer just consumed (zeros beyond the last slab)
           }
           if (p.flags & LS_EPI_SILU) {
 #pragma unroll
@@ -823,7 +838,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           }
           // stage.  Pair: row `lane` of the warp's buffer is 128 bytes, 16-byte chunk c sits at c ^ (lane & 7)
           // (SWIZZLE_128B).  Trailing single slab: 64-byte rows, chunk c at c ^ ((lane >> 1) & 3) (SWIZZLE_64B).
-          const int half_sel = s & 1;
+          const int half_sel = hs;
           const bool single = (half_sel == 0) && (s == n_mine - 1);
           if (half_sel == 0) {  // the previous store has finished reading the buffer
             if (lane == 0) bulk_wait_group_read<0>();
@@ -839,7 +854,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
                                   : my_stage + lane * 128 + (((half_sel * 4 + c) ^ (lane & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = u;
           }
-          EP_STAMP(3 + s);
+          EP_STAMP(3 + (s & 3));
           if (half_sel == 1 || single || ncol0 + 32 >= n_out_total) {
             // staged: one TMA store of the warp's 32 rows x 64 (32) columns; columns >= N and rows >= M are clipped
             // by the TMA unit.  128-byte rows: half as many row requests per byte as a 32-column box.
@@ -850,6 +865,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
               bulk_commit_group();
             }
           }
+        }
         }
         EP_STAMP(7);
         named_bar_sync(1 + group, 128);  // every warp of the group has read the bias row: the next tile may overwrite it
@@ -1244,6 +1260,12 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
   const long total = (long)m_units * p.n_tiles * p.splits;
   const int units = sms / CTAS;
+  static int env_alt = -1;
+  if (env_alt < 0) {
+    const char* e = getenv("LS_GEMM_EPI_ALT");  // 0 / 1 forces the epilogue mode (A/B measurements)
+    env_alt = e ? atoi(e) : 2;
+  }
+  p.epi_alt = (p.tma_store && p.splits == 1 && (env_alt == 1 || (env_alt == 2 && total >= 3L * units))) ? 1 : 0;
   const int grid = (int)(total < units ? total : units) * CTAS;
   static bool attr_set = false;
   if (!attr_set) {
