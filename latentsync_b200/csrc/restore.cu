@@ -24,6 +24,7 @@
 #include "../../include/latentsync_b200.h"
 
 #include <atomic>
+#include <limits.h>
 
 namespace ls {
 
@@ -80,33 +81,47 @@ __device__ __forceinline__ float mask_at(const double* M, int x, int y, int wf, 
   return s;
 }
 
-// (1) e2 = erode(mask, 2 x 2) (anchor (1, 1): window {y - 1, y} x {x - 1, x}) and the exact sum of e2 per frame
+// (1) e2 = erode(mask, 2 x 2) (anchor (1, 1): window {y - 1, y} x {x - 1, x}) and the exact sum of e2 per frame.  The
+// warped mask is evaluated once per pixel of the block's 33 x 9 footprint (left / upper halo) into shared memory.
 __global__ void __launch_bounds__(256) restore_mask_kernel(const RestoreP p) {
   pdl_prologue();
+  __shared__ float mk[9][33];
   const int f = blockIdx.z;
   const int* roi = p.rois + 4 * f;
+  const int bx = roi[0] + blockIdx.x * 32, by = roi[1] + blockIdx.y * 8;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  double M[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) M[i] = p.mats[6 * f + i];
+  for (int i = tid; i < 9 * 33; i += 256) {
+    const int ly = i / 33, lx = i - ly * 33;
+    const int xx = bx - 1 + lx, yy = by - 1 + ly;
+    // outside the frame: ignored by the erosion (+inf); right / lower overhang of the block is never read
+    mk[ly][lx] = (xx < 0 || yy < 0) ? INFINITY : ((xx < p.W && yy < p.H) ? mask_at(M, xx, yy, p.mw, p.mh) : 0.f);
+  }
+  __syncthreads();
   const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
   const int x = roi[0] + rx, y = roi[1] + ry;
   unsigned int fix = 0;
   if (x < roi[2] && y < roi[3]) {
-    double M[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) M[i] = p.mats[6 * f + i];
-    float e = INFINITY;
-#pragma unroll
-    for (int dy = -1; dy <= 0; ++dy)
-#pragma unroll
-      for (int dx = -1; dx <= 0; ++dx) {
-        const int xx = x + dx, yy = y + dy;
-        if (xx >= 0 && yy >= 0) e = fminf(e, mask_at(M, xx, yy, p.mw, p.mh));
-      }
+    const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
+    const float e = fminf(fminf(mk[ly - 1][lx - 1], mk[ly - 1][lx]), fminf(mk[ly][lx - 1], mk[ly][lx]));
     p.e2[((size_t)f * p.RH + ry) * p.RW + rx] = e;
     fix = (unsigned int)(e * 1024.0f);  // multiples of 1 / 1024: exact
   }
-  // block sum -> one atomic per warp
+  // block sum -> ONE atomic per block (one per warp put 8 k same-address atomics on each frame's counter: 68 of the
+  // kernel's 74 us)
+  __shared__ unsigned int wsum[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) fix += __shfl_xor_sync(0xffffffffu, fix, o);
-  if (threadIdx.x == 0 && fix != 0) atomicAdd(p.area + f, (unsigned long long)fix);
+  if (threadIdx.x == 0) wsum[threadIdx.y] = fix;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += wsum[i];
+    if (tot != 0) atomicAdd(p.area + f, (unsigned long long)tot);
+  }
 }
 
 // (2) w_edge = int(sqrt(float32 sum)) // 20 (affine_transform.py:101-102)
@@ -126,79 +141,193 @@ __device__ __forceinline__ float plane_at(const float* pl, const int* roi, int R
   return pl[(size_t)(y - roi[1]) * RW + (x - roi[0])];
 }
 
-// (3) erode with ones(2 w, 2 w) (anchor (w, w): offsets -w .. w - 1), rows then columns.  w == 0: cv2 substitutes a
-// 3 x 3 rectangle for the empty kernel (offsets -1 .. 1).
-template <bool ROWS>
-__global__ void __launch_bounds__(256) restore_erode_kernel(const RestoreP p, const float* __restrict__ src,
-                                                            float* __restrict__ dst) {
-  pdl_prologue();
-  const int f = blockIdx.z;
-  const int* roi = p.rois + 4 * f;
-  const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
-  const int x = roi[0] + rx, y = roi[1] + ry;
-  if (x >= roi[2] || y >= roi[3]) return;
-  const int w = p.wedge[f];
-  const int lo = (w == 0) ? -1 : -w, hi = (w == 0) ? 1 : w - 1;
-  const float* pl = src + (size_t)f * p.RH * p.RW;
-  float e = INFINITY;
-  for (int d = lo; d <= hi; ++d) {
-    const int xx = ROWS ? x + d : x, yy = ROWS ? y : y + d;
-    if (xx < 0 || yy < 0 || xx >= p.W || yy >= p.H) continue;  // outside the frame: ignored
-    e = fminf(e, plane_at(pl, roi, p.RW, xx, yy));
-    if (e == 0.f) break;
-  }
-  dst[((size_t)f * p.RH + ry) * p.RW + rx] = e;
-}
-
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (n == 1) return 0;
   while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
   return i;
 }
 
-// (4) GaussianBlur (2 w + 1) x (2 w + 1), sigma from the kernel size; rows: sequential FMA; columns: symmetric FMA
-template <bool ROWS>
-__global__ void __launch_bounds__(256) restore_blur_kernel(const RestoreP p, const float* __restrict__ src,
-                                                           float* __restrict__ dst) {
+// (3) + (4) the two erosions and the blur are 1-D window passes over a ROI plane.  A block stages its rows / columns
+// plus a halo of w on both sides in shared memory (border rules applied while loading), then every output walks its
+// window there: no bounds checks and no global loads inside the window loop.
+//   erode, ones(2 w, 2 w), anchor (w, w): min over offsets -w .. w - 1, pixels outside the frame ignored (+inf);
+//          w == 0: cv2 substitutes a 3 x 3 rectangle for the empty kernel (offsets -1 .. 1)
+//   blur,  (2 w + 1) taps, BORDER_REFLECT_101: rows accumulate left to right with FMA, columns accumulate
+//          k[w] p0 + sum_j k[w + j] (p[+j] + p[-j]) with FMA (OpenCV's order, see the header)
+// Row passes: 128 x 2 outputs per block; column passes: 32 x 32 outputs (four per thread).
+constexpr int WIN_HALO = 128;  // == the largest w with a Gaussian kernel (gmax <= WIN_HALO is checked on the host)
+constexpr int ROW_TX = 128, ROW_TY = 2, COL_TX = 32, COL_TY = 32;
+
+template <bool ROWS, bool BLUR>
+__global__ void __launch_bounds__(256) restore_window_kernel(const RestoreP p, const float* __restrict__ src,
+                                                             float* __restrict__ dst) {
   pdl_prologue();
+  constexpr int TX = ROWS ? ROW_TX : COL_TX, TY = ROWS ? ROW_TY : COL_TY;
+  constexpr int LEN = (ROWS ? TX : TY) + 2 * WIN_HALO;  // window axis, with halo
+  constexpr int LINES = ROWS ? TY : TX;                 // independent lines per block
+  __shared__ float tile[LINES * LEN];                   // ROWS: [line = y][t along x]; COLS: [t along y][line = x]
   const int f = blockIdx.z;
   const int* roi = p.rois + 4 * f;
-  const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
-  const int x = roi[0] + rx, y = roi[1] + ry;
-  if (x >= roi[2] || y >= roi[3]) return;
   const int w = p.wedge[f];
+  if (w > p.gmax || w > WIN_HALO) return;  // flagged by restore_wedge_kernel: the output is invalid anyway
+  const int x0 = roi[0] + blockIdx.x * TX, y0 = roi[1] + blockIdx.y * TY;
+  if (x0 >= roi[2] || y0 >= roi[3]) return;
+  const int hw = (w == 0) ? 1 : w;
+  const int n_axis = (ROWS ? TX : TY) + 2 * hw;
   const float* pl = src + (size_t)f * p.RH * p.RW;
-  const size_t o = ((size_t)f * p.RH + ry) * p.RW + rx;
-  if (w == 0 || w > p.gmax) {  // 1 x 1 kernel: identity
-    dst[o] = pl[(size_t)ry * p.RW + rx];
-    return;
-  }
-  const float* k = p.gtab + (size_t)w * (2 * p.gmax + 1);
-  float s;
-  if (ROWS) {
-    s = __fmul_rn(plane_at(pl, roi, p.RW, reflect101(x - w, p.W), y), k[0]);
-    for (int j = 1; j <= 2 * w; ++j) s = __fmaf_rn(plane_at(pl, roi, p.RW, reflect101(x - w + j, p.W), y), k[j], s);
-  } else {
-    s = __fmul_rn(plane_at(pl, roi, p.RW, x, y), k[w]);
-    for (int j = 1; j <= w; ++j) {
-      const float a = plane_at(pl, roi, p.RW, x, reflect101(y + j, p.H));
-      const float b = plane_at(pl, roi, p.RW, x, reflect101(y - j, p.H));
-      s = __fmaf_rn(__fadd_rn(a, b), k[w + j], s);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_axis * LINES; i += 256) {
+    int t, line, x, y;
+    if (ROWS) {
+      line = i / n_axis;
+      t = i - line * n_axis;
+      x = x0 - hw + t;
+      y = y0 + line;
+    } else {
+      t = i / LINES;
+      line = i - t * LINES;
+      x = x0 + line;
+      y = y0 - hw + t;
     }
+    float v;
+    if (BLUR) {
+      const int xr = ROWS ? reflect101(x, p.W) : x, yr = ROWS ? y : reflect101(y, p.H);
+      v = (xr < p.W && yr < p.H) ? plane_at(pl, roi, p.RW, xr, yr) : 0.f;
+    } else {
+      v = (x < 0 || y < 0 || x >= p.W || y >= p.H) ? INFINITY : plane_at(pl, roi, p.RW, x, y);
+    }
+    tile[ROWS ? line * LEN + t : t * LINES + line] = v;
   }
-  dst[o] = s;
+  __syncthreads();
+  const float* k = p.gtab + (size_t)w * (2 * p.gmax + 1);
+  constexpr int PER = (TX * TY) / 256;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int idx = tid + q * 256;
+    const int lx = idx % TX, ly = idx / TX;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= roi[2] || y >= roi[3]) continue;
+    const int c = (ROWS ? lx : ly) + hw;                     // centre position along the window axis
+    const float* line = ROWS ? tile + ly * LEN : tile + lx;  // element t of the line: line[t * stride]
+    constexpr int stride = ROWS ? 1 : LINES;
+    float r;
+    if (!BLUR) {
+      const int lo = (w == 0) ? -1 : -w, hi = (w == 0) ? 1 : w - 1;
+      r = INFINITY;
+      for (int d = lo; d <= hi; ++d) r = fminf(r, line[(c + d) * stride]);
+    } else if (w == 0) {
+      r = line[c * stride];  // 1 x 1 kernel
+    } else if (ROWS) {
+      r = __fmul_rn(line[(c - w) * stride], k[0]);
+      for (int j = 1; j <= 2 * w; ++j) r = __fmaf_rn(line[(c - w + j) * stride], k[j], r);
+    } else {
+      r = __fmul_rn(line[c * stride], k[w]);
+      for (int j = 1; j <= w; ++j) r = __fmaf_rn(__fadd_rn(line[(c + j) * stride], line[(c - j) * stride]), k[w + j], r);
+    }
+    dst[((size_t)f * p.RH + (y - roi[1])) * p.RW + (x - roi[0])] = r;
+  }
 }
 
-// (5) Lanczos-4 warp of the face + blend, ROI pixels only
+// 8 x 8 Lanczos taps of one pixel from `base` (shared-memory tile or the face in global memory; inlined per call site
+// so that the tile reads compile to LDS): row pointer = base + (yy - oy) * pitch, texel xx - ox.  Taps outside the face
+// contribute 0; pixels whose 8 x 8 window lies inside the face skip the per-tap checks.
+__device__ __forceinline__ void lanczos_acc(const uint8_t* base, int pitch, int ox, int oy, int sx, int sy, int wf, int hf,
+                                            const uint4* wq, int (&acc)[3]) {
+  const bool interior = sx >= 3 && sy >= 3 && sx + 4 < wf && sy + 4 < hf;
+  if (interior) {
+#pragma unroll 2
+    for (int ky = 0; ky < 8; ++ky) {
+      const uint4 w8 = __ldg(wq + ky);
+      const int16_t* wv = reinterpret_cast<const int16_t*>(&w8);
+      const uint8_t* px = base + (sy - 3 + ky - oy) * pitch + (sx - 3 - ox) * 3;
+#pragma unroll
+      for (int kx = 0; kx < 8; ++kx) {
+        const int w = wv[kx];
+        acc[0] += w * px[kx * 3];
+        acc[1] += w * px[kx * 3 + 1];
+        acc[2] += w * px[kx * 3 + 2];
+      }
+    }
+    return;
+  }
+  for (int ky = 0; ky < 8; ++ky) {
+    const int yy = sy - 3 + ky;
+    if (yy < 0 || yy >= hf) continue;
+    const uint4 w8 = __ldg(wq + ky);
+    const int16_t* wv = reinterpret_cast<const int16_t*>(&w8);
+    const uint8_t* row = base + (yy - oy) * pitch - ox * 3;
+#pragma unroll
+    for (int kx = 0; kx < 8; ++kx) {
+      const int xx = sx - 3 + kx;
+      if (xx < 0 || xx >= wf) continue;
+      const int w = wv[kx];
+      acc[0] += w * row[xx * 3];
+      acc[1] += w * row[xx * 3 + 1];
+      acc[2] += w * row[xx * 3 + 2];
+    }
+  }
+}
+
+// (5) Lanczos-4 warp of the face + blend, ROI pixels only.  A 32 x 8 block of frame pixels reads a small rectangle of
+// the face (the block's source bounding box + the 8-tap reach): it is staged in shared memory once (coalesced byte
+// rows) and the 192 byte reads per pixel hit shared memory instead of L1 tags; the 64 int16 weights of a pixel are
+// eight 16-byte loads.  (First version: 256 scalar global loads per pixel, 949 us for 16 x 1080p frames.)
+constexpr int BLEND_SMEM = 40 * 1024;
+
 __global__ void __launch_bounds__(256) restore_blend_kernel(const RestoreP p, const float* __restrict__ soft) {
   pdl_prologue();
+  __shared__ __align__(16) uint8_t tile[BLEND_SMEM];
+  __shared__ int box[4];  // min sx, min sy, max sx, max sy over the pixels that need the warp
   const int f = blockIdx.z;
   const int* roi = p.rois + 4 * f;
   const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
   const int x = roi[0] + rx, y = roi[1] + ry;
-  if (x >= roi[2] || y >= roi[3]) return;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const bool inside = (x < roi[2] && y < roi[3]);
+  if (tid == 0) {
+    box[0] = box[1] = INT_MAX;
+    box[2] = box[3] = INT_MIN;
+  }
+  __syncthreads();
   const size_t o = ((size_t)f * p.RH + ry) * p.RW + rx;
-  const float m = soft[o], e = p.e2[o];
+  const float m = inside ? soft[o] : 0.f, e = inside ? p.e2[o] : 0.f;
+  const bool warp_px = inside && m != 0.f && e != 0.f;  // m == 0: out = frame; e == 0: the face term is 0
+  int sx = 0, sy = 0, fx = 0, fy = 0;
+  if (warp_px) {
+    double M[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) M[i] = p.mats[6 * f + i];
+    src_coord(M, x, y, sx, sy, fx, fy);
+  }
+  {  // warp-level bounding box, then one shared-memory atomic per warp and bound
+    const int lo_x = __reduce_min_sync(0xffffffffu, warp_px ? sx : INT_MAX);
+    const int lo_y = __reduce_min_sync(0xffffffffu, warp_px ? sy : INT_MAX);
+    const int hi_x = __reduce_max_sync(0xffffffffu, warp_px ? sx : INT_MIN);
+    const int hi_y = __reduce_max_sync(0xffffffffu, warp_px ? sy : INT_MIN);
+    if (threadIdx.x == 0 && lo_x != INT_MAX) {
+      atomicMin(&box[0], lo_x);
+      atomicMin(&box[1], lo_y);
+      atomicMax(&box[2], hi_x);
+      atomicMax(&box[3], hi_y);
+    }
+  }
+  __syncthreads();
+  const uint8_t* face = p.faces + (size_t)f * p.hf * p.wf * 3;
+  // rectangle of the face the block touches, clipped to the face
+  const int bx0 = max(0, box[0] - 3), by0 = max(0, box[1] - 3);
+  const int bx1 = min(p.wf, box[2] + 5), by1 = min(p.hf, box[3] + 5);
+  const int bw = bx1 - bx0, bh = by1 - by0;
+  const bool any = box[0] != INT_MAX && bw > 0 && bh > 0;
+  const bool staged = any && (size_t)bw * 3 * bh <= BLEND_SMEM;
+  if (staged) {
+    const int rowb = bw * 3;
+    for (int i = tid; i < rowb * bh; i += 256) {
+      const int r = i / rowb, c = i - r * rowb;
+      tile[i] = face[((size_t)(by0 + r) * p.wf + bx0) * 3 + c];
+    }
+  }
+  __syncthreads();
+  if (!inside) return;
   const size_t pix = (((size_t)f * p.H + y) * p.W + x) * 3;
   if (m == 0.f) {  // 0 * (e r) + 1 * u == u
     if (p.out != p.frames) {
@@ -209,28 +338,12 @@ __global__ void __launch_bounds__(256) restore_blend_kernel(const RestoreP p, co
     return;
   }
   int acc[3] = {0, 0, 0};
-  if (e != 0.f) {
-    double M[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) M[i] = p.mats[6 * f + i];
-    int sx, sy, fx, fy;
-    src_coord(M, x, y, sx, sy, fx, fy);
-    const int16_t* wt = p.ltab + (size_t)(fy * 32 + fx) * 64;
-    const uint8_t* face = p.faces + (size_t)f * p.hf * p.wf * 3;
-    for (int ky = 0; ky < 8; ++ky) {
-      const int yy = sy - 3 + ky;
-      if (yy < 0 || yy >= p.hf) continue;
-      const uint8_t* row = face + (size_t)yy * p.wf * 3;
-#pragma unroll
-      for (int kx = 0; kx < 8; ++kx) {
-        const int xx = sx - 3 + kx;
-        if (xx < 0 || xx >= p.wf) continue;
-        const int wv = wt[ky * 8 + kx];
-        acc[0] += wv * row[xx * 3];
-        acc[1] += wv * row[xx * 3 + 1];
-        acc[2] += wv * row[xx * 3 + 2];
-      }
-    }
+  if (warp_px) {
+    const uint4* wq = reinterpret_cast<const uint4*>(p.ltab + (size_t)(fy * 32 + fx) * 64);
+    if (staged)
+      lanczos_acc(tile, bw * 3, bx0, by0, sx, sy, p.wf, p.hf, wq, acc);
+    else
+      lanczos_acc(face, p.wf * 3, 0, 0, sx, sy, p.wf, p.hf, wq, acc);
   }
   const float om = __fsub_rn(1.0f, m);
 #pragma unroll
@@ -245,7 +358,7 @@ static int restore_impl(const LsRestoreArgs* a, cudaStream_t stream) {
   LS_CHECK(a != nullptr, "ls_restore_faces: null args");
   LS_CHECK(a->F >= 1 && a->H >= 1 && a->W >= 1 && a->hf >= 8 && a->wf >= 8, "ls_restore_faces: bad geometry");
   LS_CHECK(a->H < 32768 && a->W < 32768, "ls_restore_faces: frame larger than OpenCV's short coordinates");
-  LS_CHECK(a->RW >= 1 && a->RH >= 1 && a->gmax >= 1, "ls_restore_faces: bad ROI / table size");
+  LS_CHECK(a->RW >= 1 && a->RH >= 1 && a->gmax >= 1 && a->gmax <= WIN_HALO, "ls_restore_faces: bad ROI / table size (gmax <= %d)", WIN_HALO);
   LS_CHECK(a->frames && a->out && a->faces && a->mats && a->rois && a->lanczos_tab && a->gauss_tab && a->work &&
                a->scratch,
            "ls_restore_faces: null pointer");
@@ -281,10 +394,13 @@ static int restore_impl(const LsRestoreArgs* a, cudaStream_t stream) {
   const dim3 block(32, 8), grid((a->RW + 31) / 32, (a->RH + 7) / 8, a->F);
   LS_CUDA(launch_k(restore_mask_kernel, grid, block, (size_t)0, stream, p));
   LS_CUDA(launch_k(restore_wedge_kernel, dim3((a->F + 127) / 128), dim3(128), (size_t)0, stream, p));
-  LS_CUDA(launch_k(restore_erode_kernel<true>, grid, block, (size_t)0, stream, p, (const float*)p.e2, p.t0));
-  LS_CUDA(launch_k(restore_erode_kernel<false>, grid, block, (size_t)0, stream, p, (const float*)p.t0, p.t1));
-  LS_CUDA(launch_k(restore_blur_kernel<true>, grid, block, (size_t)0, stream, p, (const float*)p.t1, p.t0));
-  LS_CUDA(launch_k(restore_blur_kernel<false>, grid, block, (size_t)0, stream, p, (const float*)p.t0, p.t1));
+  const dim3 wblock(256);
+  const dim3 grid_r((a->RW + ROW_TX - 1) / ROW_TX, (a->RH + ROW_TY - 1) / ROW_TY, a->F);
+  const dim3 grid_c((a->RW + COL_TX - 1) / COL_TX, (a->RH + COL_TY - 1) / COL_TY, a->F);
+  LS_CUDA(launch_k(restore_window_kernel<true, false>, grid_r, wblock, (size_t)0, stream, p, (const float*)p.e2, p.t0));
+  LS_CUDA(launch_k(restore_window_kernel<false, false>, grid_c, wblock, (size_t)0, stream, p, (const float*)p.t0, p.t1));
+  LS_CUDA(launch_k(restore_window_kernel<true, true>, grid_r, wblock, (size_t)0, stream, p, (const float*)p.t1, p.t0));
+  LS_CUDA(launch_k(restore_window_kernel<false, true>, grid_c, wblock, (size_t)0, stream, p, (const float*)p.t0, p.t1));
   LS_CUDA(launch_k(restore_blend_kernel, grid, block, (size_t)0, stream, p, (const float*)p.t1));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(7, std::memory_order_relaxed);
