@@ -33,7 +33,7 @@ WORKLOAD = "configs[1]: one 16-frame 256x256 segment per step: 20x(UNet3D fwd, C
 # DRAM traffic of the dominant kernel (gemm_tc_kernel): sum of dram__bytes_read.sum + dram__bytes_write.sum over the 341
 # GEMM launches of ONE CFG-batched UNet forward, from the ncu capture profiles/r1b_launches_unet.csv (joined table:
 # profiles/r1_launch_table.txt).  Same unit of work as `achieved` (FLOPs of those 341 launches / their summed duration).
-GEMM_DRAM_BYTES_PER_UNET_FORWARD = 9.4709e9
+GEMM_DRAM_BYTES_PER_UNET_FORWARD = 9.4858e9
 
 
 def make_config(world: int, steps: int, spb: int = 1) -> dict:
@@ -151,7 +151,7 @@ def run_reference(args):
     fps = FRAMES / (DDIM_STEPS * t)
     sample = (f"each step = 1 CFG-batched UNet forward (fp32, oracle port) of the {DDIM_STEPS} per segment; "
               f"frames/s = 16 / (20 * t_fwd), VAE decode excluded; {len(times)} timed + {warm_done} warm-up samples")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": warm_done, "ms_per_step": DDIM_STEPS * t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -161,7 +161,28 @@ def run_reference(args):
     }))
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." to stdout at
+    communicator creation: a 4-GPU run's first stdout line was that, not JSON), so fd 1 is pointed at stderr for the
+    whole run and the result line goes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -398,7 +419,7 @@ def main():
                          f"{t:.1f} s; frames/s = 16 / (20 * t), VAE decode excluded"}
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -410,7 +431,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": gemm_tf / peak_tf, "traffic": GEMM_DRAM_BYTES_PER_UNET_FORWARD,
-                         "traffic_unit": "bytes per UNet forward (341 launches, ncu profiles/r1b_launches_unet.csv)",
+                         "traffic_unit": "bytes per UNet forward (341 launches, ncu profiles/r1c_launches_unet.csv)",
                          "algorithmic_bytes_per_unet_forward": uplan.bytes("gemm"),
                          "peak_source": peak_src,
                          "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
