@@ -48,6 +48,10 @@ void ls_reset_launch_count(void);
 #define LS_EPI_GEGLU 1   /* W rows are packed [value | gate] per N tile; out[m, j] = v * gelu_erf(g) (diffusers GEGLU) */
 #define LS_EPI_OUT_F32 2 /* store fp32 instead of fp16 */
 #define LS_EPI_SILU 4    /* out = silu(out) */
+/* timing probes only (tools/gemm_ablate.py): the main loop skips the A loads / B loads / MMA issue; the OUTPUT IS GARBAGE */
+#define LS_DBG_NO_A 256
+#define LS_DBG_NO_B 512
+#define LS_DBG_NO_MMA 1024
 
 typedef struct LsGemmArgs {
   /* A operand: up to 3 K-segments, each an fp16 channels-last tensor [nimg, H, W, ld] using the first `ch`

@@ -470,6 +470,26 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
           const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
           const uint32_t sa = smem_base + stage * stage_bytes;
+          if (CTAS == 1 && (p.flags & (LS_DBG_NO_A | LS_DBG_NO_B))) {
+            // main-loop ablation (timing probes, tools/gemm_ablate.py; the result is garbage): drop one operand's load.
+            // Same shape as produce_kblock (probe of the next stage first) so that only the TMA issue count differs.
+            const uint32_t bytes = ((p.flags & LS_DBG_NO_A) ? 0u : (uint32_t)A_STAGE_BYTES) +
+                                   ((p.flags & LS_DBG_NO_B) ? 0u : (uint32_t)(b_rows * 128));
+            const uint32_t fb = full0 + stage * 8;
+            uint32_t rdy;
+            asm volatile(
+                "{\n.reg .pred P;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, P;\n}"
+                : "=r"(rdy) : "r"(empty0 + nstage * 8), "r"(nphase ^ 1u) : "memory");
+            if (bytes) mbar_expect_tx(&full_bar[stage], bytes); else mbar_arrive(&full_bar[stage]);
+            if (!(p.flags & LS_DBG_NO_A))
+              tma_load_4d(smem + stage * stage_bytes, &p.mapA[s], &full_bar[stage], cb * BK, x0 + dx, y0 + dy, i0);
+            if (!(p.flags & LS_DBG_NO_B))
+              tma_load_3d(smem + stage * stage_bytes + A_STAGE_BYTES, &p.mapB, &full_bar[stage], kcol, brow, bz);
+            (void)fb;
+            ready = rdy;
+          } else
           ready = produce_kblock<CTAS>(sa, sa + A_STAGE_BYTES, &p.mapA[s], &p.mapB, full0 + stage * 8, tx, cb * BK,
                                        x0 + dx, y0 + dy, i0, kcol, brow, bz, empty0 + nstage * 8, nphase ^ 1u);
           kcol += BK;
@@ -531,6 +551,16 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
           const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
           const uint32_t sa = smem_base + stage * stage_bytes;
+          if (CTAS == 1 && (p.flags & LS_DBG_NO_MMA)) {  // ablation: consume the stage without issuing MMAs
+            uint32_t rdy;
+            asm volatile(
+                "{\n.reg .pred P;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+                "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%3];\n"
+                "selp.u32 %0, 1, 0, P;\n}"
+                : "=r"(rdy) : "r"(full0 + nstage * 8), "r"(nphase), "r"(empty0 + stage * 8) : "memory");
+            ready = rdy;
+          } else
           ready = mma_kblock<CTAS>(d_tmem, umma_desc_sw128(sa), umma_desc_sw128(sa + A_STAGE_BYTES), idesc,
                                    kb != kb0 ? 1u : 0u, empty0 + stage * 8, full0 + nstage * 8, nphase);
           stage = nstage;
