@@ -48,7 +48,8 @@ void ls_reset_launch_count(void);
 #define LS_EPI_GEGLU 1   /* W rows are packed [value | gate] per N tile; out[m, j] = v * gelu_erf(g) (diffusers GEGLU) */
 #define LS_EPI_OUT_F32 2 /* store fp32 instead of fp16 */
 #define LS_EPI_SILU 4    /* out = silu(out) */
-/* timing probes only (tools/gemm_ablate.py): the main loop skips the A loads / B loads / MMA issue; the OUTPUT IS GARBAGE */
+/* timing probes, honoured only by the -DLS_GEMM_ABLATE build (make gemm_ablate; tools/gemm_ablate.py): the main loop
+ * skips the A loads / B loads / MMA issue and the OUTPUT IS GARBAGE; the product build ignores them */
 #define LS_DBG_NO_A 256
 #define LS_DBG_NO_B 512
 #define LS_DBG_NO_MMA 1024

@@ -470,6 +470,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
           const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
           const uint32_t sa = smem_base + stage * stage_bytes;
+#ifdef LS_GEMM_ABLATE
           if (CTAS == 1 && (p.flags & (LS_DBG_NO_A | LS_DBG_NO_B))) {
             // main-loop ablation (timing probes, tools/gemm_ablate.py; the result is garbage): drop one operand's load.
             // Same shape as produce_kblock (probe of the next stage first) so that only the TMA issue count differs.
@@ -490,6 +491,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             (void)fb;
             ready = rdy;
           } else
+#endif
           ready = produce_kblock<CTAS>(sa, sa + A_STAGE_BYTES, &p.mapA[s], &p.mapB, full0 + stage * 8, tx, cb * BK,
                                        x0 + dx, y0 + dy, i0, kcol, brow, bz, empty0 + nstage * 8, nphase ^ 1u);
           kcol += BK;
@@ -551,6 +553,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
           const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
           const uint32_t sa = smem_base + stage * stage_bytes;
+#ifdef LS_GEMM_ABLATE
           if (CTAS == 1 && (p.flags & LS_DBG_NO_MMA)) {  // ablation: consume the stage without issuing MMAs
             uint32_t rdy;
             asm volatile(
@@ -561,6 +564,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
                 : "=r"(rdy) : "r"(full0 + nstage * 8), "r"(nphase), "r"(empty0 + stage * 8) : "memory");
             ready = rdy;
           } else
+#endif
           ready = mma_kblock<CTAS>(d_tmem, umma_desc_sw128(sa), umma_desc_sw128(sa + A_STAGE_BYTES), idesc,
                                    kb != kb0 ? 1u : 0u, empty0 + stage * 8, full0 + nstage * 8, nphase);
           stage = nstage;

@@ -2,6 +2,7 @@
 removed (LS_DBG_* flags; results are garbage, only time is read).  L2-resident operands (M = 2048, N = 18 tiles), two K
 values; the per-k-block figure is the time difference divided by the extra k-blocks of the two waves."""
 import sys, os, math
+os.environ.setdefault("LS_SO_NAME", "_C_ablate.so")  # make -C latentsync_b200/csrc gemm_ablate
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
