@@ -27,13 +27,24 @@ def t(M, N, K, bn, flags, pair=1):
 clk_mhz = float(os.environ.get("SM_MHZ", "1935"))
 M = 2048
 print(f"clocks per k-block (tile 128 x BN x 64; tensor work = 2 BN clk), assuming {clk_mhz:.0f} MHz")
-for bn in (64, 128, 160, 256):
+for bn in ((160,) if os.environ.get('QUICK') else (64, 128, 160, 256)):
     N = bn * 18
     row = []
     for name, fl in (("full", 0), ("no A", NO_A), ("no B", NO_B), ("no A,B", NO_A | NO_B), ("no MMA", NO_MMA), ("TMA A only", NO_B | NO_MMA), ("TMA B only", NO_A | NO_MMA), ("nothing", NO_A | NO_B | NO_MMA)):
         t1, t2 = t(M, N, 3200, bn, fl), t(M, N, 6400, bn, fl)
         kb = 2 * 50  # two waves x 50 extra k-blocks
         row.append(f"{name} {(t2 - t1) * clk_mhz / kb:5.0f}")
+    print(f"BN={bn:3d}: " + " | ".join(row), flush=True)
+# hand-shake only ("nothing") with the issuer's tcgen05.commit replaced by a plain mbarrier.arrive (2048: the commit still
+# executes, on a dummy barrier ... so this shows whether WAITING for the commit's arrival is the cost), plus one extra arrive (4096)
+for bn in (64, 160):
+    N = bn * 18
+    row = []
+    for name, fl in (("nothing", NO_A | NO_B | NO_MMA), ("nothing, stage freed by plain arrive", NO_A | NO_B | NO_MMA | 2048), ("+ one more arrive", NO_A | NO_B | NO_MMA | 2048 | 4096),
+                     ("no commit at all", NO_A | NO_B | NO_MMA | 8192), ("no commit, no fence", NO_A | NO_B | NO_MMA | 8192 | 16384),
+                     ("full, no fence", 16384), ("nothing, polling waits", NO_A | NO_B | NO_MMA | 32768), ("full, polling waits", 32768)):
+        t1, t2 = t(M, N, 3200, bn, fl), t(M, N, 6400, bn, fl)
+        row.append(f"{name} {(t2 - t1) * clk_mhz / 100:5.0f}")
     print(f"BN={bn:3d}: " + " | ".join(row), flush=True)
 if os.environ.get("PAIR", "1") == "1":
     for bn in (128, 256):
