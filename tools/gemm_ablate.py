@@ -35,17 +35,6 @@ for bn in ((160,) if os.environ.get('QUICK') else (64, 128, 160, 256)):
         kb = 2 * 50  # two waves x 50 extra k-blocks
         row.append(f"{name} {(t2 - t1) * clk_mhz / kb:5.0f}")
     print(f"BN={bn:3d}: " + " | ".join(row), flush=True)
-# hand-shake only ("nothing") with the issuer's tcgen05.commit replaced by a plain mbarrier.arrive (2048: the commit still
-# executes, on a dummy barrier ... so this shows whether WAITING for the commit's arrival is the cost), plus one extra arrive (4096)
-for bn in (64, 160):
-    N = bn * 18
-    row = []
-    for name, fl in (("nothing", NO_A | NO_B | NO_MMA), ("nothing, stage freed by plain arrive", NO_A | NO_B | NO_MMA | 2048), ("+ one more arrive", NO_A | NO_B | NO_MMA | 2048 | 4096),
-                     ("no commit at all", NO_A | NO_B | NO_MMA | 8192), ("no commit, no fence", NO_A | NO_B | NO_MMA | 8192 | 16384),
-                     ("full, no fence", 16384), ("nothing, polling waits", NO_A | NO_B | NO_MMA | 32768), ("full, polling waits", 32768)):
-        t1, t2 = t(M, N, 3200, bn, fl), t(M, N, 6400, bn, fl)
-        row.append(f"{name} {(t2 - t1) * clk_mhz / 100:5.0f}")
-    print(f"BN={bn:3d}: " + " | ".join(row), flush=True)
 if os.environ.get("PAIR", "1") == "1":
     for bn in (128, 256):
         N = bn * 18
