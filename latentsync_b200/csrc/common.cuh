@@ -205,6 +205,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
+// true in exactly one lane of the (converged) warp.  Control warps run their loops with all lanes and guard the issue
+// instructions with this predicate: under `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT +
+// BRA.U.ANY loop and moves each operand to a uniform register with R2UR.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t e;
+  asm volatile(
+      "{\n.reg .pred E;\n"
+      "elect.sync _|E, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, E;\n}"
+      : "=r"(e));
+  return e != 0;
+}
+
 // Programmatic dependent launch (PDL): every kernel is launched with programmaticStreamSerialization so that its CTAs
 // are scheduled while the previous kernel of the stream drains; `pdl_prologue()` (griddepcontrol.wait) must run before
 // the first access to memory written by earlier kernels, and EVERY kernel must execute it (completion is transitive
