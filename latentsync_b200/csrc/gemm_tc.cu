@@ -1061,7 +1061,9 @@ static double tile_cost(int ctas, int bn, int splits, int m_tiles, int N, int nu
   const double t_main = kb_per * t_kb;
   const double t_tile = (t_main > t_epi ? t_main : t_epi);
   // split-K: every CTA parks an fp32 partial, meets its peers and finishes 1/splits of the tile
-  const double t_split = splits > 1 ? 6000.0 + 300.0 * splits : 0.0;
+  // measured (tools/l3_probe.py, cold weights): the level-3 conv (K = 11520) takes 35 / 30 / 57 us at 2 / 4 / 8 splits -
+  // beyond 4 the fp32 partials (splits x M x N x 4 B written and read back) cost more than the shorter K loop saves
+  const double t_split = splits > 1 ? 6000.0 + 300.0 * splits + (splits > 4 ? 12000.0 : 0.0) : 0.0;
   return waves * t_tile + t_epi + t_split + 2000.0;
 }
 
