@@ -400,3 +400,20 @@ def test_no_product_code_imports_the_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_bench_prints_exactly_one_stdout_line():
+    """bench.py's contract is ONE JSON line on stdout; libraries (NCCL) print there too, so bench routes fd 1 to stderr
+    for the run and writes the result to the saved descriptor (bench.claim_stdout / bench.emit)"""
+    import json
+    import subprocess
+    import sys
+
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "print('library noise on stdout'); os.write(1, b'raw fd 1 noise\\n'); bench.emit({'metric': 'x', 'value': 1.5})"
+            % ROOT)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.splitlines()
+    assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "x", "value": 1.5}, res.stdout
+    assert "library noise on stdout" in res.stderr and "raw fd 1 noise" in res.stderr
