@@ -453,18 +453,25 @@ class UNetEngine:
             self.w.put(name + ".b", self.w.raw(r + ".conv2.bias") + self.w.raw(r + ".conv_shortcut.bias"))
         return self.w.t[name + ".w"], self.w.t[name + ".b"]
 
-    def plan(self, B: int, F: int, H: int, W: int, S: int) -> "UNetPlan":
-        key = (B, F, H, W, S)
+    def plan(self, B: int, F: int, H: int, W: int, S: int, uncond_zero: bool = False) -> "UNetPlan":
+        """`uncond_zero`: the caller guarantees that the FIRST half of the batch carries all-zero audio embeddings (the
+        pipeline builds the classifier-free-guidance batch that way, lipsync_pipeline.py:503-507).  With bias-free
+        to_k / to_v (attention.py:231-232) its keys and values are exactly 0, softmax is uniform over zeros, the
+        attention output is exactly 0 and `to_out` adds exactly its bias: those rows skip LayerNorm, to_q, attention and
+        to_out and get `hidden + bias` instead - the same bits, fewer launches' worth of rows (B == 2 only)."""
+        uncond_zero = bool(uncond_zero) and B == 2 and S > 0
+        key = (B, F, H, W, S, uncond_zero)
         if key not in self.plans:
-            self.plans[key] = UNetPlan(self, B, F, H, W, S)
+            self.plans[key] = UNetPlan(self, B, F, H, W, S, uncond_zero)
         return self.plans[key]
 
 
 class UNetPlan(Plan):
-    def __init__(self, eng: UNetEngine, B: int, F: int, H: int, W: int, S: int):
+    def __init__(self, eng: UNetEngine, B: int, F: int, H: int, W: int, S: int, uncond_zero: bool = False):
         super().__init__(eng.device)
         self.eng = eng
         self.B, self.F, self.H, self.W, self.S = B, F, H, W, S
+        self.uncond_zero = uncond_zero
         self.taps: Dict[str, Tuple[Buf, int]] = {}  # name -> (buffer, level); filled only when LS_DEBUG_TAPS=1
         self.debug = os.environ.get("LS_DEBUG_TAPS", "0") == "1"
         c = eng.cfg
@@ -574,7 +581,34 @@ class UNetPlan(Plan):
         hs2 = self._linear(o, t + ".attn1.to_out.0", cc, residual=hs)
         del o, n, hs
         hs = hs2
-        if c["add_audio_layer"] and self.audio_kv is not None:
+        if c["add_audio_layer"] and self.audio_kv is not None and self.uncond_zero:
+            # cross-attention with a null-audio first half (see UNetEngine.plan): only the conditional rows go through
+            # LayerNorm -> to_q -> attention -> to_out; the unconditional rows become hidden + to_out.bias
+            half = rows // 2
+            off = half * cc * 2  # bytes to the conditional half of an fp16 [rows][cc] buffer
+            nh = self.buf(half, cc)
+            self.layernorm(hs.ptr + off, half, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), nh.ptr)
+            qh = self.buf(half, cc)
+            self.gemm([(nh.ptr, cc, cc, 1)], 1, 1, half, w.lin(t + ".attn2.to_q.weight"), cc, qh.ptr, cc)
+            koff, voff = eng.kv_off[a]
+            ldkv = eng.kv_total
+            kv_rows = self.F * self.S * ldkv * 2  # bytes to the conditional half of audio_kv
+            self.attention(qh.ptr, self.audio_kv.ptr + kv_rows + 2 * koff, self.audio_kv.ptr + kv_rows + 2 * voff,
+                           nh.ptr, cc, ldkv, ldkv, cc, self.F, heads, d, hw, self.S)
+            del qh
+            hs2 = self.buf(rows, cc)
+            ob = w.f32(t + ".attn2.to_out.0.bias").data_ptr()
+            self.gemm([(nh.ptr, cc, cc, 1)], 1, 1, half, w.lin(t + ".attn2.to_out.0.weight"), cc, hs2.ptr + off, cc,
+                      bias_ptr=ob, residual_ptr=hs.ptr + off, ldr=cc)
+            # unconditional rows: a K = 64 GEMM over zero operands is `bias + residual` in the GEMM's own epilogue
+            if getattr(self, "_zero_a", None) is None:
+                self._zero_a = torch.zeros(self._rows(0) // 2, KPAD, dtype=torch.float16, device=eng.device)
+                self._zero_w = torch.zeros(max(c["block_out_channels"]), KPAD, dtype=torch.float16, device=eng.device)
+            self.gemm([(self._zero_a.data_ptr(), KPAD, KPAD, 1)], 1, 1, half, self._zero_w[:cc], cc, hs2.ptr, cc,
+                      bias_ptr=ob, residual_ptr=hs.ptr, ldr=cc)
+            del nh, hs
+            hs = hs2
+        elif c["add_audio_layer"] and self.audio_kv is not None:
             # cross-attention: frame f attends to its own S audio tokens (attention.py:183-194)
             n = self.buf(rows, cc)
             self.layernorm(hs.ptr, rows, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), n.ptr)

@@ -27,6 +27,8 @@ def shard_segments(num_segments: int, rank: int, world_size: int) -> range:
 
 
 class LipsyncPipeline:
+    cfg_null_audio_shortcut = True  # see UNetEngine.plan(uncond_zero=...); False keeps the full-batch cross-attention
+
     def __init__(self, vae, audio_encoder, denoising_unet, scheduler):
         self.vae = vae
         self.audio_encoder = audio_encoder
@@ -163,7 +165,8 @@ class LipsyncPipeline:
         if unet.add_audio_layer:
             assert audio_embeds is not None
             S = audio_embeds.shape[-2]
-        plan = unet.plan(nb, F, h, w, S)
+        # the unconditional half of the CFG batch is built right here as zeros: the plan may use that (engine.plan)
+        plan = unet.plan(nb, F, h, w, S, uncond_zero=(do_cfg and S > 0 and self.cfg_null_audio_shortcut))
         if S:
             a = audio_embeds.to(dev, torch.float16).reshape(F * S, -1)
             buf = plan.audio_in.tensor()

@@ -307,6 +307,43 @@ def test_pixel_pre_and_post_processing_vs_oracle():
         assert got.shape == (4, h, w, 3) and diff.max().item() <= 1 and frac < 2e-3
 
 
+@pytest.mark.parametrize("name,hw", [("tiny", 16), ("stage2", 32)])
+def test_null_audio_shortcut_is_bitwise_identical(name, hw):
+    """engine.UNetEngine.plan(uncond_zero=True): with all-zero audio in the first half of the CFG batch (what the pipeline
+    builds, lipsync_pipeline.py:503-507) the cross-attention of those rows is exactly `to_out.bias`; the shortcut plan
+    must give the SAME BITS as the full plan, and fewer attention rows"""
+    unet, _, _ = get_unet(name)
+    full = unet.plan(2, 16, hw, hw, 50)
+    short = unet.plan(2, 16, hw, hw, 50, uncond_zero=True)
+    assert short is not full and short.uncond_zero and not full.uncond_zero
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(full.x_in.tensor().shape, generator=g, device="cuda").half()
+    a = torch.randn(full.audio_in.tensor().shape, generator=g, device="cuda").half()
+    a[: a.shape[0] // 2] = 0  # null audio for the unconditional half
+    outs = []
+    for plan in (full, short):
+        plan.x_in.tensor().copy_(x)
+        plan.audio_in.tensor().copy_(a)
+        plan.t_in.tensor().fill_(501.0)
+        plan.replay()
+        torch.cuda.synchronize()
+        outs.append(plan.eps_out.tensor().clone())
+    assert torch.isfinite(outs[0]).all() and outs[0].abs().max() > 0
+    assert torch.equal(outs[0], outs[1])
+    assert short.flops("attention") < full.flops("attention")
+    # and the pipeline uses it: same latents from both settings of the switch
+    pipe, _ = get_pipe(name)
+    from latentsync_b200 import synthetic as syn
+    seg = {k: v.cuda() for k, v in syn.segment_inputs(3, 0, 16, hw * 8, hw * 8).items()}
+    lat = {}
+    for flag in (True, False):
+        pipe.cfg_null_audio_shortcut = flag
+        lat[flag] = pipe.denoise_segment(seg["latents"], seg["audio_embeds"], seg["mask_latents"],
+                                         seg["masked_image_latents"], seg["ref_latents"], 2, 1.5).clone()
+    pipe.cfg_null_audio_shortcut = True
+    assert torch.equal(lat[True], lat[False])
+
+
 def test_restore_video_stage_vs_opencv():
     """SURVEY.md §8f rank 3 through the pipeline: LipsyncPipeline.restore_video (lipsync_pipeline.py:343-358) = resize
     + uint8 (rank 2 kernel) + AlignRestore.restore_img per frame; the GPU stage must give the bytes OpenCV gives for
