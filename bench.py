@@ -364,9 +364,9 @@ def main():
     if rank == 0 and world == 1:
         import numpy as np
         from latentsync_b200.restore import FaceRestorer
-        from oracle import restore_ref as RR
+        from oracle import restore_ref as RR  # cpu_baseline of this leg only (the reference's OpenCV call sequence)
 
-        cases = [RR.synthetic_case(500 + i, 1080, 1920, (0.45, 0.6), (500.0, 700.0)) for i in range(FRAMES)]
+        cases = [syn.restore_case(500 + i, 1080, 1920, (0.45, 0.6), (500.0, 700.0)) for i in range(FRAMES)]
         frames_h = torch.from_numpy(np.stack([c[0] for c in cases])).pin_memory()
         faces_h = torch.from_numpy(np.stack([c[1] for c in cases])).pin_memory()
         mats = [c[2] for c in cases]
@@ -388,7 +388,7 @@ def main():
 
         ms_dev = timed_ms(lambda: restorer.restore_imgs(frames_d, faces_d, mats, out=out_d))
         ms_host = timed_ms(lambda: fr_out_h.copy_(restorer.restore_imgs(frames_h, faces_h, mats), non_blocking=True))
-        _, rois, _, _ = restorer.plan(mats, RR.FACE_W, RR.FACE_H, 1920, 1080)
+        _, rois, _, _ = restorer.plan(mats, 210, 280, 1920, 1080)
         roi_px = int(((rois[:, 2] - rois[:, 0]) * (rois[:, 3] - rois[:, 1])).sum())
         # algorithmic bytes: frame read + write (u8 x 3), the face once, per ROI pixel the e2 / soft-mask planes once each
         # way (2 x 2 x 4 B) and the ROI frame bytes once more each way for the blend

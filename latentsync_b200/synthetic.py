@@ -114,3 +114,18 @@ def segment_inputs(seed: int, segment: int = 0, num_frames: int = 16, height: in
     ref_px = uniform(seed, tag + ".refpx", (num_frames, 3, height, width), -1.0, 1.0)
     return dict(latents=lat, audio_embeds=audio, mask_latents=mask_lat, masked_image_latents=masked_lat,
                 ref_latents=ref_lat, ref_pixel_values=ref_px, masks=masks)
+
+
+def restore_case(seed: int, H: int, W: int, scale=(1.2, 1.6), origin=(-20.0, 60.0)):
+    """deterministic frame / face / affine matrix (numpy PCG64: identical on every host).  The matrix maps frame ->
+    face coordinates like AlignRestore.align_warp_face's: `scale` > 1 makes the face smaller than 210 x 280 in the
+    frame, `origin` is the range of the frame position (x and y) of the face's top-left corner."""
+    rng = np.random.default_rng(seed)
+    frame = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    face = rng.integers(0, 256, (280, 210, 3), dtype=np.uint8)
+    ang = rng.uniform(-0.3, 0.3)
+    sc = rng.uniform(*scale)
+    R = np.array([[sc * math.cos(ang), -sc * math.sin(ang)], [sc * math.sin(ang), sc * math.cos(ang)]])
+    o = np.array([rng.uniform(*origin), rng.uniform(*origin)])
+    A = np.concatenate([R, (-R @ o)[:, None]], axis=1)
+    return frame, face, A
