@@ -229,7 +229,7 @@ def main():
     h, w = HEIGHT // 8, WIDTH // 8
     # the plan the pipeline runs (null-audio shortcut of the CFG batch, engine.UNetEngine.plan); FLOP counts stay those of
     # the full plan (algorithmic work)
-    uplan = unet.plan(2, FRAMES, h, w, 50, uncond_zero=pipe.cfg_null_audio_shortcut)
+    uplan = unet.plan(2, FRAMES, h, w, 50, uncond_zero=pipe.cfg_null_audio_shortcut, same_sample=pipe.cfg_null_audio_shortcut and pipe.cfg_shared_prefix)
     uplan_full = unet.plan(2, FRAMES, h, w, 50, capture=False)
     vplan = vae.plan(FRAMES, h, w)
 

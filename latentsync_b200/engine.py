@@ -453,25 +453,33 @@ class UNetEngine:
             self.w.put(name + ".b", self.w.raw(r + ".conv2.bias") + self.w.raw(r + ".conv_shortcut.bias"))
         return self.w.t[name + ".w"], self.w.t[name + ".b"]
 
-    def plan(self, B: int, F: int, H: int, W: int, S: int, uncond_zero: bool = False) -> "UNetPlan":
+    def plan(self, B: int, F: int, H: int, W: int, S: int, uncond_zero: bool = False,
+             same_sample: bool = False) -> "UNetPlan":
         """`uncond_zero`: the caller guarantees that the FIRST half of the batch carries all-zero audio embeddings (the
         pipeline builds the classifier-free-guidance batch that way, lipsync_pipeline.py:503-507).  With bias-free
         to_k / to_v (attention.py:231-232) its keys and values are exactly 0, softmax is uniform over zeros, the
         attention output is exactly 0 and `to_out` adds exactly its bias: those rows skip LayerNorm, to_q, attention and
         to_out and get `hidden + bias` instead - the same bits, fewer launches' worth of rows (B == 2 only)."""
         uncond_zero = bool(uncond_zero) and B == 2 and S > 0
-        key = (B, F, H, W, S, uncond_zero)
+        # `same_sample` (only together with uncond_zero): both halves of the batch also carry the SAME sample and timestep
+        # (lipsync_pipeline.py:542-549 duplicates the latents).  Until the first audio cross-attention the two halves
+        # are then the same tensor: the first ResnetBlock3D and the self-attention part of the first transformer run
+        # once, on half the rows.
+        same_sample = bool(same_sample) and uncond_zero
+        key = (B, F, H, W, S, uncond_zero, same_sample)
         if key not in self.plans:
-            self.plans[key] = UNetPlan(self, B, F, H, W, S, uncond_zero)
+            self.plans[key] = UNetPlan(self, B, F, H, W, S, uncond_zero, same_sample)
         return self.plans[key]
 
 
 class UNetPlan(Plan):
-    def __init__(self, eng: UNetEngine, B: int, F: int, H: int, W: int, S: int, uncond_zero: bool = False):
+    def __init__(self, eng: UNetEngine, B: int, F: int, H: int, W: int, S: int, uncond_zero: bool = False,
+                 same_sample: bool = False):
         super().__init__(eng.device)
         self.eng = eng
         self.B, self.F, self.H, self.W, self.S = B, F, H, W, S
         self.uncond_zero = uncond_zero
+        self.same_sample = same_sample
         self.taps: Dict[str, Tuple[Buf, int]] = {}  # name -> (buffer, level); filled only when LS_DEBUG_TAPS=1
         self.debug = os.environ.get("LS_DEBUG_TAPS", "0") == "1"
         c = eng.cfg
@@ -556,10 +564,16 @@ class UNetPlan(Plan):
         del n
         return self._linear(gg, ff + ".net.2", cc, residual=hs)
 
-    def _transformer(self, a: str, x: Buf, cc: int, lvl: int) -> Buf:
-        """Transformer3DModel.forward (attention.py:82-124) + BasicTransformerBlock.forward (:174-199)"""
+    def _transformer(self, a: str, x: Buf, cc: int, lvl: int, shared: bool = False) -> Buf:
+        """Transformer3DModel.forward (attention.py:82-124) + BasicTransformerBlock.forward (:174-199).
+        `shared` (same_sample plans, first transformer only): `x` holds ONE batch element that stands for both; the part
+        before the audio cross-attention runs on it once."""
         eng, w, c = self.eng, self.eng.w, self.eng.cfg
         h, wd = self._geo(lvl)
+        full_B = self.B
+        if shared:
+            assert self.uncond_zero and full_B == 2 and x.rows * 2 == self._rows(lvl)
+            self.B = 1  # geometry of the shared part: one batch element
         rows, hw = self._rows(lvl), h * wd
         heads = c["attention_head_dim"]
         d = cc // heads
@@ -581,13 +595,17 @@ class UNetPlan(Plan):
         hs2 = self._linear(o, t + ".attn1.to_out.0", cc, residual=hs)
         del o, n, hs
         hs = hs2
+        if shared:
+            self.B = full_B
+            rows = self._rows(lvl)
         if c["add_audio_layer"] and self.audio_kv is not None and self.uncond_zero:
             # cross-attention with a null-audio first half (see UNetEngine.plan): only the conditional rows go through
             # LayerNorm -> to_q -> attention -> to_out; the unconditional rows become hidden + to_out.bias
             half = rows // 2
             off = half * cc * 2  # bytes to the conditional half of an fp16 [rows][cc] buffer
+            hoff = 0 if hs.rows == half else off  # a shared (one-element) hidden state serves both halves
             nh = self.buf(half, cc)
-            self.layernorm(hs.ptr + off, half, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), nh.ptr)
+            self.layernorm(hs.ptr + hoff, half, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), nh.ptr)
             qh = self.buf(half, cc)
             self.gemm([(nh.ptr, cc, cc, 1)], 1, 1, half, w.lin(t + ".attn2.to_q.weight"), cc, qh.ptr, cc)
             koff, voff = eng.kv_off[a]
@@ -599,7 +617,7 @@ class UNetPlan(Plan):
             hs2 = self.buf(rows, cc)
             ob = w.f32(t + ".attn2.to_out.0.bias").data_ptr()
             self.gemm([(nh.ptr, cc, cc, 1)], 1, 1, half, w.lin(t + ".attn2.to_out.0.weight"), cc, hs2.ptr + off, cc,
-                      bias_ptr=ob, residual_ptr=hs.ptr + off, ldr=cc)
+                      bias_ptr=ob, residual_ptr=hs.ptr + hoff, ldr=cc)
             # unconditional rows: a K = 64 GEMM over zero operands is `bias + residual` in the GEMM's own epilogue
             if getattr(self, "_zero_a", None) is None:
                 self._zero_a = torch.zeros(self._rows(0) // 2, KPAD, dtype=torch.float16, device=eng.device)
@@ -622,6 +640,16 @@ class UNetPlan(Plan):
             del n, hs
             hs = hs2
         hs = self._ff(t + ".norm3", t + ".ff", hs)
+        if shared:
+            # residual = the shared input for both halves: proj_out as two half-batch GEMMs
+            key = a + ".proj_out"
+            out = self.buf(rows, cc)
+            half = rows // 2
+            for e in range(2):
+                o8 = e * half * cc * 2
+                self.gemm([(hs.ptr + o8, cc, cc, 1)], 1, 1, half, w.lin(key + ".weight"), cc, out.ptr + o8, cc,
+                          bias_ptr=w.f32(key + ".bias").data_ptr(), residual_ptr=x.ptr, ldr=cc)
+            return out
         return self._linear(hs, a + ".proj_out", cc, residual=x)
 
     def _motion(self, m: str, x: Buf, cc: int, lvl: int) -> Buf:
@@ -732,10 +760,19 @@ class UNetPlan(Plan):
             p = f"down_blocks.{i}"
             cout = boc[i]
             for j in range(c["layers_per_block"]):
-                x = self._resnet(f"{p}.resnets.{j}", [(x, ch)], cout, i)
+                shared = (self.same_sample and i == 0 and j == 0 and typ == "CrossAttnDownBlock3D" and
+                          c["add_audio_layer"] and self.audio_kv is not None)
+                if shared:
+                    # both batch elements are the same tensor up to the first audio cross-attention: one element's worth
+                    # of rows (the first half of conv_in's output) through the resnet and the self-attention part
+                    self.B = 1
+                    x = self._resnet(f"{p}.resnets.{j}", [(x, ch)], cout, i)  # reads the first half of its input
+                    self.B = B
+                else:
+                    x = self._resnet(f"{p}.resnets.{j}", [(x, ch)], cout, i)
                 ch = cout
                 if typ == "CrossAttnDownBlock3D":
-                    x = self._transformer(f"{p}.attentions.{j}", x, ch, i)
+                    x = self._transformer(f"{p}.attentions.{j}", x, ch, i, shared=shared)
                 if w.has(f"{p}.motion_modules.{j}.temporal_transformer.norm.weight"):
                     x = self._motion(f"{p}.motion_modules.{j}", x, ch, i)
                 self._tap(f"{p}.{j}", x, i)

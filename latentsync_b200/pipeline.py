@@ -28,6 +28,8 @@ def shard_segments(num_segments: int, rank: int, world_size: int) -> range:
 
 class LipsyncPipeline:
     cfg_null_audio_shortcut = True  # see UNetEngine.plan(uncond_zero=...); False keeps the full-batch cross-attention
+    cfg_shared_prefix = True        # see UNetEngine.plan(same_sample=...): needs the shortcut above; not bitwise (GroupNorm
+                                    # partial sums are chunked differently), same tolerance against the reference
 
     def __init__(self, vae, audio_encoder, denoising_unet, scheduler):
         self.vae = vae
@@ -166,7 +168,9 @@ class LipsyncPipeline:
             assert audio_embeds is not None
             S = audio_embeds.shape[-2]
         # the unconditional half of the CFG batch is built right here as zeros: the plan may use that (engine.plan)
-        plan = unet.plan(nb, F, h, w, S, uncond_zero=(do_cfg and S > 0 and self.cfg_null_audio_shortcut))
+        # ... and both halves get the same latents / mask / reference channels and timestep from ls_concat13 below
+        short = do_cfg and S > 0 and self.cfg_null_audio_shortcut
+        plan = unet.plan(nb, F, h, w, S, uncond_zero=short, same_sample=short and self.cfg_shared_prefix)
         if S:
             a = audio_embeds.to(dev, torch.float16).reshape(F * S, -1)
             buf = plan.audio_in.tensor()

@@ -137,8 +137,9 @@ class UNet3DConditionModel(nn.Module):
             self._engine = UNetEngine({k: v for k, v in self.state_dict().items()}, self._cfg, dev)
         return self._engine
 
-    def plan(self, B: int, F: int, H: int, W: int, S: int, capture: bool = True, uncond_zero: bool = False):
-        p = self.engine().plan(B, F, H, W, S, uncond_zero)
+    def plan(self, B: int, F: int, H: int, W: int, S: int, capture: bool = True, uncond_zero: bool = False,
+             same_sample: bool = False):
+        p = self.engine().plan(B, F, H, W, S, uncond_zero, same_sample)
         if capture and p.graph is None:
             p.capture()
         return p

@@ -336,12 +336,46 @@ def test_null_audio_shortcut_is_bitwise_identical(name, hw):
     from latentsync_b200 import synthetic as syn
     seg = {k: v.cuda() for k, v in syn.segment_inputs(3, 0, 16, hw * 8, hw * 8).items()}
     lat = {}
-    for flag in (True, False):
-        pipe.cfg_null_audio_shortcut = flag
-        lat[flag] = pipe.denoise_segment(seg["latents"], seg["audio_embeds"], seg["mask_latents"],
-                                         seg["masked_image_latents"], seg["ref_latents"], 2, 1.5).clone()
-    pipe.cfg_null_audio_shortcut = True
-    assert torch.equal(lat[True], lat[False])
+    try:
+        for key, (shortcut, prefix) in {"full": (False, False), "null": (True, False), "prefix": (True, True)}.items():
+            pipe.cfg_null_audio_shortcut, pipe.cfg_shared_prefix = shortcut, prefix
+            lat[key] = pipe.denoise_segment(seg["latents"], seg["audio_embeds"], seg["mask_latents"],
+                                            seg["masked_image_latents"], seg["ref_latents"], 2, 1.5).clone()
+    finally:
+        pipe.cfg_null_audio_shortcut, pipe.cfg_shared_prefix = True, True
+    assert torch.equal(lat["null"], lat["full"])
+    rel = ((lat["prefix"] - lat["full"]).norm() / lat["full"].norm()).item()
+    print(f"pipeline, shared prefix vs full plan: latents rel-L2 {rel:.2e}")
+    assert rel < 2e-3, rel  # shared prefix: GroupNorm chunking differs, fp16 rounding noise only
+
+
+@pytest.mark.parametrize("name,hw", [("tiny", 16), ("stage2", 32)])
+def test_shared_prefix_plan_matches_full_plan(name, hw):
+    """engine.UNetEngine.plan(uncond_zero=True, same_sample=True): when both halves of the CFG batch carry the same sample
+    and timestep (lipsync_pipeline.py:542-549) everything before the first audio cross-attention is computed once.  Same
+    arithmetic per element; only the GroupNorm partial-sum chunking differs (fp32 summation order), so the outputs agree
+    to fp16 rounding noise"""
+    unet, _, _ = get_unet(name)
+    full = unet.plan(2, 16, hw, hw, 50)
+    short = unet.plan(2, 16, hw, hw, 50, uncond_zero=True, same_sample=True)
+    assert short is not full and short.same_sample and short.launches != full.launches
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(full.x_in.tensor().shape, generator=g, device="cuda").half()
+    x[x.shape[0] // 2:] = x[: x.shape[0] // 2]  # the duplicated sample
+    a = torch.randn(full.audio_in.tensor().shape, generator=g, device="cuda").half()
+    a[: a.shape[0] // 2] = 0
+    outs = []
+    for plan in (full, short):
+        plan.x_in.tensor().copy_(x)
+        plan.audio_in.tensor().copy_(a)
+        plan.t_in.tensor().fill_(301.0)
+        plan.replay()
+        torch.cuda.synchronize()
+        outs.append(plan.eps_out.tensor().clone())
+    rel = ((outs[0] - outs[1]).norm() / outs[0].norm()).item()
+    print(f"{name}: shared-prefix plan vs full plan rel-L2 {rel:.2e}, launches {short.launches} vs {full.launches}")
+    assert torch.isfinite(outs[1]).all() and rel < 2e-3  # two fp16 evaluations of the same network differ by rounding noise
+    assert short.flops() < full.flops()
 
 
 def test_restore_video_stage_vs_opencv():
