@@ -8,6 +8,11 @@ scaling) and the decoded frames are gathered to rank 0 with NCCL inside the time
 
     python bench.py [--gpus N] [--steps K] [--warmup W]         # this framework (CUDA kernels behind the C-ABI)
     python bench.py --impl reference ...                         # CPU reference arm: oracle port on the host cores
+    python bench.py --clip-segments 8                            # BASELINE configs[2]: ONE 8-segment clip sharded over
+    python bench.py --clip-segments 94 --ddim-steps 50 --guidance 2.0   # configs[3]   the ranks (strong scaling)
+
+Clip mode goes through the product's sharded entry LipsyncPipeline.run_clip (shard_segments -> run_segments ->
+gather_frames): the clip's total work is fixed, a step is one pass over the whole clip.
 """
 from __future__ import annotations
 
@@ -30,15 +35,17 @@ WORKLOAD = "configs[1]: one 16-frame 256x256 segment per step: 20x(UNet3D fwd, C
            "Whisper embeds 16x50x384) + DDIM + VAE decode + paste-back, random-init stage2 weights"
 
 
-# DRAM traffic of the dominant kernel (gemm_tc_kernel): sum of dram__bytes_read.sum + dram__bytes_write.sum over the 341
-# GEMM launches of ONE CFG-batched UNet forward, from the ncu capture profiles/r1b_launches_unet.csv (joined table:
-# profiles/r1_launch_table.txt).  Same unit of work as `achieved` (FLOPs of those 341 launches / their summed duration).
-GEMM_DRAM_BYTES_PER_UNET_FORWARD = 9.4858e9
-
-
-def make_config(world: int, steps: int, spb: int = 1) -> dict:
-    return {"workload": WORKLOAD, "segments_per_gpu": steps, "segments_per_batch": spb, "frames_per_segment": FRAMES, "ddim_steps": DDIM_STEPS,
-            "guidance_scale": GUIDANCE, "parallelism": f"segments x{world}",
+def make_config(world: int, steps: int, spb: int = 1, clip: int = 0, ddim: int = DDIM_STEPS, g: float = GUIDANCE) -> dict:
+    wl = WORKLOAD
+    if clip:
+        which = {(8, 20): "configs[2]: 5 s clip (125 frames -> 8 segments), 20 steps",
+                 (94, 50): "configs[3]: 60 s clip (1500 frames -> 94 segments), 50 DDIM steps, CFG 2.0"}.get(
+                     (clip, ddim), f"clip of {clip} segments, {ddim} DDIM steps")
+        wl = (f"{which}: the clip's {clip} 16-frame 256x256 segments sharded over the ranks "
+              "(LipsyncPipeline.run_clip), decoded frames gathered on rank 0 as fp16 over NCCL")
+    return {"workload": wl, "segments_per_gpu": steps if not clip else None, "clip_segments": clip or None,
+            "segments_per_batch": spb, "frames_per_segment": FRAMES, "ddim_steps": ddim,
+            "guidance_scale": g, "parallelism": f"segments x{world}",
             "operands": "fp16 tensor-core operands, fp32 accumulate (bf16 cannot meet rel-L2 1e-2, DESIGN.md)",
             "l2": "no explicit flush: 2.5 GB of fp16 weights stream through the 126 MB L2 every UNet forward"}
 
@@ -47,9 +54,10 @@ def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)"
+        return (p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)",
+                p["bf16_tflops"])
     except Exception:
-        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)", 1590.0
 
 
 class ClockSampler:
@@ -101,64 +109,143 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_forward_sample(threads: int):
-    """the oracle port (oracle/unet_ref.py, fp32) on the host cores: ONE CFG-batched UNet forward of the 20 a segment
-    needs; frames/s extrapolated as 16 / (20 * t) (VAE decode, 5.8 % of the FLOPs, left out => flatters the CPU)"""
-    from latentsync_b200 import synthetic as syn
-    from latentsync_b200.spec import STAGE2_UNET_CONFIG
-    from oracle.unet_ref import unet_forward
-
-    torch.set_num_threads(threads)
-    sd = syn.unet_state_dict(STAGE2_UNET_CONFIG, seed=0)
-    seg = syn.segment_inputs(11, 0, FRAMES, HEIGHT, WIDTH)
+def _cfg_batch(seg):
     x = torch.cat([seg["latents"]] * 2)
     x = torch.cat([x, torch.cat([seg["mask_latents"]] * 2), torch.cat([seg["masked_image_latents"]] * 2),
                    torch.cat([seg["ref_latents"]] * 2)], dim=1)
     a = seg["audio_embeds"][None]
-    a = torch.cat([torch.zeros_like(a), a])
+    return x, torch.cat([torch.zeros_like(a), a])
 
-    def one():
-        t0 = time.perf_counter()
-        unet_forward(sd, STAGE2_UNET_CONFIG, x, 951, a)
-        return time.perf_counter() - t0
 
-    return one
+def cpu_sample(threads: int, ddim: int = DDIM_STEPS):
+    """bounded CPU sample for the `cpu_baseline` object of the default run: ONE CFG-batched fp32 UNet forward of the
+    oracle port (oracle/unet_ref.py) and the oracle VAE decode of 2 of the 16 frames; the segment time is assembled as
+    ddim * t_fwd + 8 * t_vae2 (the --impl reference arm times a WHOLE segment instead)"""
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.spec import STAGE2_UNET_CONFIG
+    from oracle import pipeline_ref as P
+    from oracle.unet_ref import unet_forward
+
+    torch.set_num_threads(threads)
+    sd = syn.unet_state_dict(STAGE2_UNET_CONFIG, seed=0)
+    vsd = syn.vae_decoder_state_dict(seed=0)
+    seg = syn.segment_inputs(11, 0, FRAMES, HEIGHT, WIDTH)
+    x, a = _cfg_batch(seg)
+    t0 = time.perf_counter()
+    unet_forward(sd, STAGE2_UNET_CONFIG, x, 951, a)
+    t_fwd = time.perf_counter() - t0
+    z = (seg["latents"] / 0.18215)[0].permute(1, 0, 2, 3)[:2].contiguous()
+    t0 = time.perf_counter()
+    P.vae_decode(vsd, z)
+    t_vae2 = time.perf_counter() - t0
+    t_seg = ddim * t_fwd + (FRAMES / 2) * t_vae2
+    return {"value": FRAMES / t_seg, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"1 CFG-batched fp32 UNet forward of the oracle port ({t_fwd:.1f} s) + oracle VAE decode of 2 of "
+                      f"the 16 frames ({t_vae2:.1f} s); segment = {ddim} x forward + 8 x that decode = {t_seg:.0f} s"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path for the same workload.  The reference is Python and cannot travel to
     the GPU box (no diffusers / decord there, and /root/reference is absent), so this times the oracle port, which
-    oracle/make_golden.py pins to the reference's own modules at rel-L2 2e-6."""
+    oracle/make_golden.py pins to the reference's own modules at rel-L2 2e-6, on ALL host cores.  One step = ONE WHOLE
+    segment, measured: 20 x (CFG concat, fp32 UNet forward, CFG combine, DDIM update) + VAE decode + paste-back
+    (oracle/pipeline_ref.py, the restatement of lipsync_pipeline.py:500-575).  A segment is ~2-3 minutes of CPU work,
+    so exactly one is timed whatever --steps asks for, after one untimed warm-up forward; `steps` / `warmup` in the
+    line are what was actually run.  If one forward is so slow that a segment would not end within ~5 minutes, the loop
+    is cut after `max_steps` forwards and the remainder is scaled (the line says so)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.spec import STAGE2_UNET_CONFIG
+    from oracle import pipeline_ref as P
+    from oracle.unet_ref import unet_forward
+
     threads = os.cpu_count() or 1
-    one = cpu_forward_sample(threads)
-    budget = 400.0
-    t_first = one()
-    warm_done = 1
-    times = []
-    for _ in range(max(args.warmup - 1, 0)):
-        if t_first * (warm_done + 1 + args.steps) > budget:
-            break
-        one()
-        warm_done += 1
-    for _ in range(args.steps):
-        times.append(one())
-        if sum(times) + t_first * warm_done > budget and len(times) >= 1:
-            break
-    t = sum(times) / len(times)
-    fps = FRAMES / (DDIM_STEPS * t)
-    sample = (f"each step = 1 CFG-batched UNet forward (fp32, oracle port) of the {DDIM_STEPS} per segment; "
-              f"frames/s = 16 / (20 * t_fwd), VAE decode excluded; {len(times)} timed + {warm_done} warm-up samples")
+    torch.set_num_threads(threads)
+    ddim, g = args.ddim_steps, args.guidance
+    sd = syn.unet_state_dict(STAGE2_UNET_CONFIG, seed=0)
+    vsd = syn.vae_decoder_state_dict(seed=0)
+    seg = syn.segment_inputs(100, 0, FRAMES, HEIGHT, WIDTH)
+    x, a = _cfg_batch(seg)
+    t0 = time.perf_counter()
+    unet_forward(sd, STAGE2_UNET_CONFIG, x, 951, a)  # warm-up (thread pool, oneDNN primitives, page faults)
+    t_warm = time.perf_counter() - t0
+    budget = float(os.environ.get("LS_BENCH_REF_BUDGET_S", "280"))  # seconds allowed for the timed loop
+    max_steps = None
+    if t_warm * ddim > budget:
+        max_steps = max(1, int(budget / t_warm))
+    t0 = time.perf_counter()
+    lat = P.denoise_segment(lambda s_, t_, a_: unet_forward(sd, STAGE2_UNET_CONFIG, s_, t_, a_), seg, steps=ddim,
+                            guidance=g, max_steps=max_steps)
+    t_loop = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    frames = P.decode_and_paste(vsd, lat, seg)
+    t_dec = time.perf_counter() - t1
+    assert frames.shape == (FRAMES, 3, HEIGHT, WIDTH)
+    done = ddim if max_steps is None else max_steps
+    t_seg = t_loop * (ddim / done) + t_dec
+    fps = FRAMES / t_seg
+    sample = (f"ONE whole segment on {threads} host threads, fp32 oracle port: {done} of {ddim} CFG-batched UNet forwards "
+              f"timed ({t_loop:.1f} s{'' if max_steps is None else ', scaled to ' + str(ddim)}) + VAE decode + paste-back "
+              f"({t_dec:.1f} s); 1 untimed warm-up forward ({t_warm:.1f} s)")
     emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": warm_done, "ms_per_step": DDIM_STEPS * t * 1e3, "higher_is_better": True,
+        "steps": 1, "warmup": 1, "ms_per_step": t_seg * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": make_config(args.gpus, len(times)), "unet_step_ms": t * 1e3,
+        "config": make_config(args.gpus, 1, ddim=ddim, g=g), "unet_step_ms": t_loop / done * 1e3,
+        "vae_decode_paste_ms": t_dec * 1e3,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def gpu_eager_baseline(dev, ddim: int = DDIM_STEPS, g: float = GUIDANCE):
+    """BASELINE.md §1/§3's GPU bar: the reference's network as stock PyTorch eager on THIS B200, fp16 (the reference's
+    own GPU dtype, scripts/inference.py), cuDNN convolutions, cuBLAS linears, F.scaled_dot_product_attention - the
+    oracle port of the reference modules moved to the GPU with `.half()`, none of this repo's kernels.  Informational:
+    one forward (median of 3 after a warm-up) and one whole segment (20-step CFG loop + VAE decode + paste)."""
+    from latentsync_b200 import synthetic as syn
+    from latentsync_b200.spec import STAGE2_UNET_CONFIG
+    from oracle import pipeline_ref as P
+    from oracle import unet_ref as U
+
+    sd = {k: v.to(dev, torch.float16) for k, v in syn.unet_state_dict(STAGE2_UNET_CONFIG, seed=0).items()}
+    vsd = {k: v.to(dev, torch.float16) for k, v in syn.vae_decoder_state_dict(seed=0).items()}
+    seg = {k: v.to(dev, torch.float16) for k, v in syn.segment_inputs(100, 0, FRAMES, HEIGHT, WIDTH).items()}
+    x, a = _cfg_batch(seg)
+    old = U.USE_SDPA
+    U.USE_SDPA = True
+    try:
+        fn = lambda s_, t_, a_: U.unet_forward(sd, STAGE2_UNET_CONFIG, s_, t_, a_)  # noqa: E731
+        fn(x, 951, a)
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(x, 951, a)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        fwd_ms = sorted(ts)[1]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lat = P.denoise_segment(fn, seg, steps=ddim, guidance=g)
+        frames = P.decode_and_paste(vsd, lat, seg)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        seg_ms = e0.elapsed_time(e1)
+        ok = bool(torch.isfinite(frames.float()).all().item())
+    finally:
+        U.USE_SDPA = old
+    del sd, vsd
+    torch.cuda.empty_cache()
+    return {"value": FRAMES / (seg_ms * 1e-3), "unit": "frames/s", "unet_step_ms": fwd_ms, "ms_per_step": seg_ms,
+            "finite": ok, "dtype": "f16",
+            "what": "oracle port of the reference modules as PyTorch eager on this GPU (.half().cuda(): cuDNN conv, "
+                    "cuBLAS linear, F.scaled_dot_product_attention); one segment = 20-step CFG loop + VAE decode + paste; "
+                    "device-resident inputs, CUDA events"}
 
 
 _RESULT_FD = None
@@ -181,27 +268,54 @@ def emit(obj) -> None:
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
 
 
+def _traffic_record(n_gemm: int):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the GEMM launches of ONE UNet forward, from the ncu
+    launch list of the SAME plan that is timed here (tools/profile_unet.py -> tools/join_launches.py write
+    profiles/unet_gemm_traffic.json).  Returned only when that capture has the timed plan's GEMM launch count."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "unet_gemm_traffic.json")) as f:
+            rec = json.load(f)
+        if int(rec["gemm_launches"]) == int(n_gemm):
+            return float(rec["dram_bytes"]), rec.get("source", "profiles/unet_gemm_traffic.json")
+    except Exception:
+        pass
+    return None, "no ncu capture of this plan (launch count differs or file absent)"
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the informational legs (from_pixels, restore, gpu_eager_baseline, cpu_baseline)")
     ap.add_argument("--segments-per-batch", type=int, default=1,
                     help="advance this many segments of the clip together as one UNet batch (throughput mode; the "
                          "default 1 is BASELINE.json configs[1], one segment at a time like the reference's loop)")
+    ap.add_argument("--clip-segments", type=int, default=0,
+                    help="strong-scaling mode: ONE clip of this many segments sharded over the ranks through "
+                         "LipsyncPipeline.run_clip (8 = BASELINE configs[2], 94 with --ddim-steps 50 --guidance 2.0 = "
+                         "configs[3]); a step is one pass over the whole clip")
+    ap.add_argument("--ddim-steps", type=int, default=DDIM_STEPS)
+    ap.add_argument("--guidance", type=float, default=GUIDANCE)
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-kind time table to stderr")
     args = ap.parse_args()
+    clip = max(0, args.clip_segments)
+    if args.steps is None:
+        args.steps = 1 if clip else 5
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    ddim, guidance = args.ddim_steps, args.guidance
 
     import torch.distributed as dist
 
+    from latentsync_b200 import _lib
     from latentsync_b200 import synthetic as syn
-    from latentsync_b200.pipeline import LipsyncPipeline
+    from latentsync_b200.pipeline import LipsyncPipeline, shard_segments
     from latentsync_b200.scheduler import DDIMScheduler
     from latentsync_b200.spec import STAGE2_UNET_CONFIG
     from latentsync_b200.unet import UNet3DConditionModel
@@ -227,57 +341,123 @@ def main():
     vae = AutoencoderKLDecoder({**syn.vae_decoder_state_dict(seed=0), **syn.vae_encoder_state_dict(seed=0)}, device=dev)
     pipe = LipsyncPipeline(vae, None, unet, DDIMScheduler()).to(dev)
     h, w = HEIGHT // 8, WIDTH // 8
+    do_cfg = guidance > 1.0
+    short = do_cfg and pipe.cfg_null_audio_shortcut
     # the plan the pipeline runs (null-audio shortcut of the CFG batch, engine.UNetEngine.plan); FLOP counts stay those of
     # the full plan (algorithmic work)
-    uplan = unet.plan(2, FRAMES, h, w, 50, uncond_zero=pipe.cfg_null_audio_shortcut, same_sample=pipe.cfg_null_audio_shortcut and pipe.cfg_shared_prefix)
-    uplan_full = unet.plan(2, FRAMES, h, w, 50, capture=False)
+    nb = 2 if do_cfg else 1
+    uplan = unet.plan(nb, FRAMES, h, w, 50, uncond_zero=short, same_sample=short and pipe.cfg_shared_prefix)
+    uplan_full = unet.plan(nb, FRAMES, h, w, 50, capture=False)
     vplan = vae.plan(FRAMES, h, w)
-
-    # ---- synthetic segments: device-resident copies for `value`, pinned host copies for `e2e`
-    nseg = args.steps + args.warmup
-    host = [{k: v.pin_memory() for k, v in syn.segment_inputs(100 + rank, s, FRAMES, HEIGHT, WIDTH).items()}
-            for s in range(min(nseg, 4))]
-    resident = [{k: v.to(dev) for k, v in s.items()} for s in host]
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    out_host = torch.empty(FRAMES, 3, HEIGHT, WIDTH, dtype=torch.float32).pin_memory()
-    d2h = out_host.numel() * out_host.element_size()
-    gather_list = [torch.empty(FRAMES, 3, HEIGHT, WIDTH, device=dev) for _ in range(world)] if rank == 0 else None
-
     spb = max(1, args.segments_per_batch)
+    frame_bytes16 = FRAMES * 3 * HEIGHT * WIDTH * 2  # one segment's decoded frames as fp16 (the gathered / D2H payload)
 
-    def run(seg_list, e2e: bool):
-        """`len(seg_list)` steps (= segments), advanced `spb` at a time"""
-        for frames in pipe.run_segments(seg_list, DDIM_STEPS, GUIDANCE, segments_per_batch=spb):
+    def pin(seg):
+        return {k: v.pin_memory() for k, v in seg.items()}
+
+    if clip:
+        # ---------------- strong scaling: ONE clip, `clip` segments, contiguous shards (run_clip)
+        mine = list(shard_segments(clip, rank, world))
+        nuniq = min(len(mine), 4)  # distinct synthetic segments per rank (inputs repeat beyond that: timing only)
+        host = {i: pin(syn.segment_inputs(100, i, FRAMES, HEIGHT, WIDTH)) for i in mine[:nuniq]}
+        host_of = {i: host[mine[k % nuniq]] for k, i in enumerate(mine)} if mine else {}
+        resident_u = {i: {k: v.to(dev) for k, v in s_.items()} for i, s_ in host.items()}
+        resident_of = {i: resident_u[mine[k % nuniq]] for k, i in enumerate(mine)} if mine else {}
+        h2d = sum(v.numel() * v.element_size() for v in next(iter(host.values())).values()) * clip if mine else 0
+        clip_host = torch.empty(clip * FRAMES, 3, HEIGHT, WIDTH, dtype=torch.float16).pin_memory() if rank == 0 else None
+        d2h = clip * frame_bytes16
+        warm_n = min(clip, world)  # warm-up clip: one segment per rank (plans captured, NCCL connections up)
+
+        def run_pass(e2e: bool, nseg: int):
+            """one pass over a clip of `nseg` segments (the real clip, or the `world`-segment warm-up clip whose
+            segment r is rank r's first segment)"""
+            full = nseg == clip
+
+            def src(i):
+                seg = (host_of if e2e else resident_of)[i if full else mine[0]]
+                return {k: v.to(dev, non_blocking=True) for k, v in seg.items()} if e2e else seg
+
+            out = pipe.run_clip(src, num_segments=nseg, num_inference_steps=ddim, guidance_scale=guidance,
+                                segments_per_batch=spb)
+            if e2e and rank == 0 and out is not None:
+                clip_host[: out.shape[0]].copy_(out, non_blocking=True)
+
+        def timed(e2e: bool):
+            for _ in range(args.warmup):
+                run_pass(e2e, warm_n)
+            torch.cuda.synchronize()
             if world > 1:
-                dist.gather(frames, gather_list, dst=0)
-            if e2e:
-                out_host.copy_(frames, non_blocking=True)
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                run_pass(e2e, clip)
+            b.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = torch.tensor([a.elapsed_time(b)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return ms.item()
 
-    def timed(segs, e2e: bool):
-        run([segs[i % len(segs)] for i in range(args.warmup)], e2e)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        run([segs[(args.warmup + i) % len(segs)] for i in range(args.steps)], e2e)
-        b.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+        frames_total = FRAMES * clip * args.steps
+        launches_per_step = (len(mine) * (ddim * (uplan.launches + 2) + vplan.launches + 2)) if rank == 0 else 0
+        scaling = "strong"
+    else:
+        # ---------------- configs[1] (default): K segments per rank, weak scaling
+        nseg = args.steps + args.warmup
+        host = [pin(syn.segment_inputs(100 + rank, s_, FRAMES, HEIGHT, WIDTH)) for s_ in range(min(nseg, 4))]
+        resident = [{k: v.to(dev) for k, v in s_.items()} for s_ in host]
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values()) * world
+        out_host = torch.empty(world * args.steps * FRAMES, 3, HEIGHT, WIDTH, dtype=torch.float16).pin_memory() \
+            if rank == 0 else None
+        d2h = frame_bytes16 * world
+
+        def run(seg_list, e2e: bool):
+            """`len(seg_list)` steps (= segments) on this rank, advanced `spb` at a time; the ranks' decoded frames are
+            gathered on rank 0 as fp16 (one gather of the whole block) and, end to end, copied to pinned host memory"""
+            if e2e:
+                seg_list = [{k: v.to(dev, non_blocking=True) for k, v in s_.items()} for s_ in seg_list]
+            frames = torch.cat([f.to(torch.float16)
+                                for f in pipe.run_segments(seg_list, ddim, guidance, segments_per_batch=spb)])
+            if world > 1:
+                frames = pipe.gather_frames(frames, dst=0)
+            if e2e and rank == 0:
+                out_host[: frames.shape[0]].copy_(frames, non_blocking=True)
+
+        def timed(e2e: bool):
+            segs = host if e2e else resident
+            run([segs[i % len(segs)] for i in range(args.warmup)], e2e)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            run([segs[(args.warmup + i) % len(segs)] for i in range(args.steps)], e2e)
+            b.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = torch.tensor([a.elapsed_time(b)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return ms.item()
+
+        frames_total = FRAMES * args.steps * world
+        launches_per_step = ddim * (uplan.launches + 2) + vplan.launches + 2
+        scaling = "weak"
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = timed(resident, e2e=False)
+    _lib.reset_launch_count()
+    ms_total = timed(e2e=False)
+    counted = _lib.launch_count()  # C-ABI launches issued by THIS process during warm-up + timed region (graphs: at capture)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(host, e2e=True)
-    frames_total = FRAMES * args.steps * world
+    ms_e2e = timed(e2e=True)
     value = frames_total / (ms_total * 1e-3)
     e2e_value = frames_total / (ms_e2e * 1e-3)
 
@@ -292,36 +472,74 @@ def main():
     b.record()
     torch.cuda.synchronize()
     unet_ms = a.elapsed_time(b) / DDIM_STEPS
-    uplan.run_timed()
-    table = uplan.run_timed()
-    vtable = vplan.run_timed()
-    peak_tf, peak_bw, peak_src = measured_peaks()
-    n_gemm, gemm_ms_eager = table["gemm"]
-    # dominant kernel: the 341 GEMM launches of one UNet forward replayed as their own CUDA graph (kernel time without
-    # the ~3 us host gap that the per-launch event pairs of run_timed add to each of them; that figure is kept as
-    # `achieved_eager_events`)
-    gemm_ms = uplan.time_kind_in_graph("gemm")
-    kind_ms = {k: uplan.time_kind_in_graph(k) for k in ("attention", "groupnorm", "layernorm")}
-    gemm_tf = uplan.flops("gemm") / (gemm_ms * 1e-3) / 1e12  # executed GEMM FLOPs of the plan that was timed
-    seg_flops = DDIM_STEPS * uplan_full.flops() + vplan.flops()
-    launches_per_step = DDIM_STEPS * (uplan.launches + 2) + vplan.launches + 2 + (1 if world > 1 else 0)
-    if args.profile_kernels and rank == 0:
-        tot = sum(ms for _, ms in table.values())
-        for k, (n, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
-            print(f"unet  {k:20s} {n:4d} launches {ms:8.3f} ms {100 * ms / tot:5.1f} %", file=sys.stderr)
-        tot = sum(ms for _, ms in vtable.values())
-        for k, (n, ms) in sorted(vtable.items(), key=lambda kv: -kv[1][1]):
-            print(f"vae   {k:20s} {n:4d} launches {ms:8.3f} ms {100 * ms / tot:5.1f} %", file=sys.stderr)
-        for name, pl in (("unet", uplan), ("vae", vplan)):
-            for kind in ("gemm", "attention", "groupnorm", "layernorm"):
-                for d, n, ms, tf in pl.shape_table(kind):
-                    print(f"{name} {kind} x{n:3d} {ms:8.3f} ms {tf:7.1f} TF/s  {d}", file=sys.stderr)
+    peak_tf, peak_bw, peak_src, peak_burst = measured_peaks()
+    roof = None
+    if rank == 0:
+        uplan.run_timed()
+        table = uplan.run_timed()
+        vtable = vplan.run_timed()
+        n_gemm, gemm_ms_eager = table["gemm"]
+        gemm_flops = uplan.flops("gemm")  # executed GEMM FLOPs of the plan that was timed
+        # dominant kernel (gemm_tc_kernel / gemm_tc_pair_kernel): the plan's GEMM launches replayed as their own CUDA graph,
+        # timed with CUDA events on the launching stream.
+        #   sustained: that graph back to back for >= 1 s (the power state of a seconds-long step) -> / sustained cuBLAS peak
+        #   burst    : 5 replays after the idle gap of the table runs above                         -> / burst cuBLAS peak
+        gemm_ms_burst = uplan.time_kind_in_graph("gemm", reps=5)
+        gemm_ms = uplan.time_kind_in_graph("gemm", reps=max(20, int(1000.0 / max(gemm_ms_burst, 1e-3))))
+        kind_ms = {k: uplan.time_kind_in_graph(k, reps=20) for k in ("attention", "groupnorm", "layernorm")}
+        # in-step estimate: the whole captured forward minus the same forward without its GEMM launches
+        nongemm_ms = uplan.time_kind_in_graph(None, reps=20, exclude="gemm")
+        gemm_ms_instep = max(unet_ms - nongemm_ms, 1e-6)
+        gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        seg_flops = ddim * uplan_full.flops() + vplan.flops()
+        traffic, traffic_src = _traffic_record(n_gemm)
+        if args.profile_kernels:
+            tot = sum(ms for _, ms in table.values())
+            for k, (n, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+                print(f"unet  {k:20s} {n:4d} launches {ms:8.3f} ms {100 * ms / tot:5.1f} %", file=sys.stderr)
+            tot = sum(ms for _, ms in vtable.values())
+            for k, (n, ms) in sorted(vtable.items(), key=lambda kv: -kv[1][1]):
+                print(f"vae   {k:20s} {n:4d} launches {ms:8.3f} ms {100 * ms / tot:5.1f} %", file=sys.stderr)
+            for name, pl in (("unet", uplan), ("vae", vplan)):
+                for kind in ("gemm", "attention", "groupnorm", "layernorm"):
+                    for d, n, ms, tf in pl.shape_table(kind):
+                        print(f"{name} {kind} x{n:3d} {ms:8.3f} ms {tf:7.1f} TF/s  {d}", file=sys.stderr)
+        roof = {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": gemm_tf / peak_tf, "traffic": traffic,
+                "traffic_unit": "DRAM bytes of the GEMM launches of one UNet forward (ncu dram__bytes_read+write.sum)",
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_unet_forward": uplan.bytes("gemm"),
+                "peak_source": peak_src,
+                "kernel": "gemm_tc_kernel / gemm_tc_pair_kernel (tcgen05 GEMM / implicit-GEMM conv, cta_group::1 / ::2)",
+                "launches_per_unet_forward": n_gemm,
+                "flops_per_unet_forward": gemm_flops,
+                "avg_launch_us": 1e3 * gemm_ms / n_gemm,
+                "how": "CUDA events around a CUDA graph holding only the plan's GEMM launches, in plan order, replayed "
+                       "back to back for >= 1 s (sustained power state); peak = sustained cuBLAS bf16",
+                "share_of_unet_forward": gemm_ms / unet_ms,
+                "isolated_burst": {"achieved": gemm_flops / (gemm_ms_burst * 1e-3) / 1e12, "peak": peak_burst,
+                                   "frac": gemm_flops / (gemm_ms_burst * 1e-3) / 1e12 / peak_burst,
+                                   "how": "the same graph, 5 replays after an idle gap; peak = burst cuBLAS bf16"},
+                "in_step_estimate": {"achieved": gemm_flops / (gemm_ms_instep * 1e-3) / 1e12, "peak": peak_tf,
+                                     "frac": gemm_flops / (gemm_ms_instep * 1e-3) / 1e12 / peak_tf,
+                                     "gemm_ms": gemm_ms_instep, "non_gemm_graph_ms": nongemm_ms,
+                                     "how": "captured UNet forward (graph replay) minus the same forward captured "
+                                            "without its GEMM launches; launch gaps land on the GEMM side"},
+                "achieved_eager_events": gemm_flops / (gemm_ms_eager * 1e-3) / 1e12,
+                "share_of_unet_forward_eager_events": gemm_ms_eager / sum(ms for _, ms in table.values()),
+                "other_kinds_ms_in_graph": kind_ms,
+                "whole_step": {"flops_per_segment": seg_flops,
+                               "achieved": seg_flops * (frames_total / FRAMES) / (ms_total * 1e-3) / 1e12 / world,
+                               "frac": seg_flops * (frames_total / FRAMES) / (ms_total * 1e-3) / 1e12 / world / peak_tf,
+                               "unit": "TFLOP/s per GPU (algorithmic FLOPs of the full plan)"}}
 
     # ---- informational: one segment from PIXELS: pinned host frames -> H2D -> VAE encode of the
     # masked and reference frames (2 x 16 images) + nearest mask resize -> 20-step loop -> decode + paste -> D2H
+    extras = rank == 0 and world == 1 and not clip and not args.no_extras
     from_pixels = None
-    if rank == 0 and world == 1:
+    if extras:
         seg0 = host[0]
+        px_out_host = torch.empty(FRAMES, 3, HEIGHT, WIDTH, dtype=torch.float32).pin_memory()
         px_host = {"ref": seg0["ref_pixel_values"], "masks": seg0["masks"]}
         gen = torch.Generator(device=dev).manual_seed(1234)
 
@@ -335,7 +553,7 @@ def main():
             seg = {"latents": resident[0]["latents"], "audio_embeds": resident[0]["audio_embeds"],
                    "mask_latents": mask_lat, "masked_image_latents": masked_lat, "ref_latents": ref_lat,
                    "ref_pixel_values": ref_px, "masks": masks}
-            out_host.copy_(pipe.run_segments([seg], DDIM_STEPS, GUIDANCE)[0], non_blocking=True)
+            px_out_host.copy_(pipe.run_segments([seg], DDIM_STEPS, GUIDANCE)[0], non_blocking=True)
 
         for _ in range(2):
             pixels_step()
@@ -361,7 +579,7 @@ def main():
     # ---- informational: inverse-affine paste-back of 16 faces into 1080p frames, device-resident
     # and from / to pinned host memory; the reference's per-frame OpenCV path timed on the host cores beside it
     restore = None
-    if rank == 0 and world == 1:
+    if extras:
         import numpy as np
         from latentsync_b200.restore import FaceRestorer
         from oracle import restore_ref as RR  # cpu_baseline of this leg only (the reference's OpenCV call sequence)
@@ -413,44 +631,40 @@ def main():
                    "what": "AlignRestore.restore_img for 16 x 1080p frames, ~400 px faces, byte-exact vs OpenCV "
                            "(tests/test_restore_gpu.py); 7 launches + 1 D2D copy per call"}
 
+    # ---- informational: the reference network as stock PyTorch eager on this GPU (BASELINE.md's GPU bar)
+    eager = None
+    if extras:
+        try:
+            eager = gpu_eager_baseline(dev)
+        except Exception as e:  # an informational leg must never take the headline down
+            eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        t = cpu_forward_sample(threads)()
-        cpu = {"value": FRAMES / (DDIM_STEPS * t), "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "1 CFG-batched fp32 UNet forward (oracle port of the reference modules) of the 20 per segment, "
-                         f"{t:.1f} s; frames/s = 16 / (20 * t), VAE decode excluded"}
+    if rank == 0 and world == 1 and not clip and not args.no_cpu_baseline and not args.no_extras:
+        cpu = cpu_sample(os.cpu_count() or 1)
 
     if rank == 0:
         emit(({
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC if (ddim, guidance) == (DDIM_STEPS, GUIDANCE) else
+            f"lip-synced frames/s (256x256, {ddim} DDIM steps, CFG {guidance})",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": make_config(world, args.steps, spb),
+            "config": make_config(world, args.steps, spb, clip, ddim, guidance),
             "unet_step_ms": unet_ms,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "what": "pinned-host segment inputs -> H2D -> run_segments / run_clip -> fp16 frames gathered on "
+                            "rank 0 -> D2H into pinned host memory, all inside the timed region"},
             "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_note": "kernels launched on rank 0 inside the timed region: per segment ddim x (UNet plan "
+                                 "launches replayed from its CUDA graph + concat13 + cfg_ddim) + VAE plan + 2",
+            "c_abi_calls_counted": counted,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": gemm_tf / peak_tf, "traffic": GEMM_DRAM_BYTES_PER_UNET_FORWARD,
-                         "traffic_unit": "bytes per UNet forward (the 341 GEMM launches of the full plan, ncu profiles/r1c_launches_unet.csv)",
-                         "algorithmic_bytes_per_unet_forward": uplan.bytes("gemm"),
-                         "peak_source": peak_src,
-                         "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
-                         "launches_per_unet_forward": n_gemm,
-                         "flops_per_unet_forward": uplan.flops("gemm"),
-                         "avg_launch_us": 1e3 * gemm_ms / n_gemm,
-                         "how": "CUDA events around a CUDA graph holding only these launches, in plan order",
-                         "share_of_unet_forward": gemm_ms / unet_ms,
-                         "achieved_eager_events": uplan.flops("gemm") / (gemm_ms_eager * 1e-3) / 1e12,
-                         "share_of_unet_forward_eager_events": gemm_ms_eager / sum(ms for _, ms in table.values()),
-                         "other_kinds_ms_in_graph": kind_ms,
-                         "whole_step": {"flops_per_segment": seg_flops,
-                                        "achieved": seg_flops * args.steps / (ms_total * 1e-3) / 1e12 / 1.0,
-                                        "frac": seg_flops * args.steps / (ms_total * 1e-3) / 1e12 / peak_tf}},
+            "roofline": roof,
             "from_pixels": from_pixels,
             "restore": restore,
+            "gpu_eager_baseline": eager,
             "cpu_baseline": cpu,
         }))
     if world > 1:

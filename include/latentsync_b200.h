@@ -8,11 +8,19 @@
  * reference's module/pipeline signatures and calls these through ctypes.
  *
  * Conventions
- *  - All pointers are DEVICE pointers owned by the caller (PyTorch); nothing here allocates or frees.
+ *  - All pointers passed in are DEVICE pointers owned by the caller (PyTorch); the library never frees or keeps them.
+ *    The library itself owns three small per-device scratch areas, allocated with cudaMalloc on FIRST use and kept for
+ *    the life of the process: split-K fp32 partials + per-tile tickets (ls_gemm, 64 MB + 32 KB) and GroupNorm partial
+ *    sums + tickets (ls_groupnorm*, 4 MB + 128 KB).  They can only grow OUTSIDE stream capture (a call that would
+ *    need to grow during capture fails with an error: run the launch sequence once eagerly first, as
+ *    engine.Plan.capture does), that growth synchronises the device once, and a superseded block is never freed
+ *    because CUDA graphs captured earlier still point at it.  Kernels whose CTAs wait for one another (the
+ *    single-launch GroupNorm, split-K GEMMs) are launched cooperatively, so co-residency is enforced by the driver.
  *  - Activations are channels-last fp16: a (b f) x H x W x C video tensor is a row-major [rows, C] matrix with
  *    rows = (b f) * H * W ("tokens").  Weights are packed fp16 [N][K] (K contiguous).
  *  - Every function takes the CUDA stream to launch on (as void*) and returns 0 on success; on failure a
- *    message is available from ls_last_error().  No function synchronises the device.
+ *    message is available from ls_last_error().  No function synchronises the device (except the one-time scratch
+ *    growth above).
  *  - Not re-entrant per stream; one host thread per GPU (the reference's server is single-consumer,
  *    scripts/api.py:24-27,95).
  */

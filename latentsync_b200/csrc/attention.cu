@@ -352,7 +352,8 @@ static int launch_attn(const AttnKParams& p, cudaStream_t stream) {
   constexpr int DS = DP + 8;
   if (p.sq <= 16 && p.skv <= 16) {
     const size_t smem = (size_t)4 * 3 * 16 * DS * sizeof(__half);
-    static bool set_short = false;
+    static bool set_short_dev[16] = {};
+    bool& set_short = set_short_dev[dev_slot()];
     if (!set_short) {
       LS_CUDA(cudaFuncSetAttribute(attn_short_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       set_short = true;
@@ -361,7 +362,8 @@ static int launch_attn(const AttnKParams& p, cudaStream_t stream) {
     LS_CUDA(launch_k(attn_short_kernel<D>, dim3((unsigned)((probs + 3) / 4)), dim3(128), (size_t)(smem), (cudaStream_t)(stream), p));
   } else {
     const size_t smem = (size_t)5 * 64 * DS * sizeof(__half);
-    static bool set_gen = false;
+    static bool set_gen_dev[16] = {};
+    bool& set_gen = set_gen_dev[dev_slot()];
     if (!set_gen) {
       LS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       set_gen = true;

@@ -722,7 +722,8 @@ static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
     g_atc_probe = probe_buf;
   }
 #endif
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {};
+  bool& attr_set = attr_set_dev[dev_slot()];
   if (!attr_set) {
     LS_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     if (D == 80)

@@ -47,6 +47,56 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Cooperative launch: the driver only starts the grid when ALL its CTAs can be resident at once (and fails the launch
+// if they never can).  Used by the kernels whose CTAs wait for one another inside the kernel - the single-launch
+// GroupNorm (global ticket rendezvous) and split-K GEMMs - so that their co-residency does not rest on "nothing else is
+// running": a concurrent kernel on another stream (NCCL) or an early-launched dependent (PDL) can no longer starve it.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_coop_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// index of the current device, clamped into [0, 16): key of the per-device caches (function attributes such as
+// cudaFuncAttributeMaxDynamicSharedMemorySize are per device; a process-wide `static bool` is wrong for cuda:1)
+inline int dev_slot() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d > 15) ? 15 : d;
+}
+
+// Library-owned device scratch (split-K partials, GroupNorm partial sums, tickets): allocated on first use, grown
+// OUTSIDE stream capture only, and a superseded block is never freed - CUDA graphs captured earlier still point at it.
+struct ScratchBlock {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+// returns 0 on success; `zero`: cudaMemset the new block (tickets)
+inline int scratch_reserve(ScratchBlock& b, size_t need, size_t minimum, bool zero, cudaStream_t stream, const char* who) {
+  if (need <= b.bytes) return 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cs);
+  LS_CHECK(cs == cudaStreamCaptureStatusNone, "%s: scratch must be sized by an eager warm-up run", who);
+  LS_CUDA(cudaDeviceSynchronize());
+  const size_t bytes = need > minimum ? need : minimum;
+  void* p = nullptr;
+  LS_CUDA(cudaMalloc(&p, bytes));
+  if (zero) LS_CUDA(cudaMemset(p, 0, bytes));
+  b.ptr = p;  // the old block (if any) stays allocated for the life of the process: earlier graphs may reference it
+  b.bytes = bytes;
+  return 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------

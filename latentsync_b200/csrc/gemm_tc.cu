@@ -37,6 +37,17 @@ namespace ls {
 
 extern std::atomic<int64_t> g_launch_count;
 
+// Which lane runs the two control loops (TMA producer, MMA issuer).  Under `if (lane == 0)` ptxas cannot tell that a
+// single lane is active: it keeps the operands in vector registers, moves them to uniform registers (R2UR) every
+// k-block and wraps each UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY waterfall loop (~75 / ~95 dependent
+// instructions per k-block).  With the WHOLE loop under one `elect.sync` predicate it knows, and emits the uniform
+// instructions back to back (~45 per k-block).  -DLS_GEMM_LANE0 keeps the old form for A/B runs.
+#ifdef LS_GEMM_LANE0
+#define LS_ONE_LANE() (lane == 0)
+#else
+#define LS_ONE_LANE() elect_one()
+#endif
+
 constexpr int BM = 128;
 constexpr int BK = 64;  // fp16 elements: one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
@@ -423,7 +434,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
 
   if (warp == PRODUCER_WARP) {
     // ------------------------------------------------------------------ TMA producer (one lane, every CTA)
-    if (lane == 0) {
+    if (LS_ONE_LANE()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t ready = 0;  // probe result for the current stage's `empty` barrier
@@ -514,7 +525,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer (one lane, pair leader only)
-    if (leader && lane == 0) {
+    if (leader && LS_ONE_LANE()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t ready = 0;  // probe result for the current stage's `full` barrier
@@ -1034,29 +1045,39 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 }
 
 static int num_sms() {
-  static int n = 0;
+  static int n_dev[16] = {};  // per device: a process may drive several GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return 148;
+  int& n = n_dev[dev];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
   return n;
 }
 
-// Estimated cycles of one launch: waves x max(main loop, epilogue) + tail.  Per 64-wide k-block the main loop is bound
-// by the SM's shared-memory port, which TMA writes and tcgen05 operand reads share: measured with the clock64 probes
-// (profiles/r1_gemm_issue_loop.txt) ~ 330 + BN cycles for a single CTA (128 x BN tile) and ~ 560 + 0.15 BN for a CTA pair
-// (256 x BN tile), against 2 BN cycles of tensor work - so pairs only tie, and wide tiles win unless they waste columns.
-static double tile_cost(int ctas, int bn, int splits, int m_tiles, int N, int num_kb, int sms) {
+// Estimated cycles of one launch: waves x max(main loop, epilogue) + tail, from MEASURED clocks per 64-wide k-block
+// (profiles/r2_gemm_ablate_elect.txt, tools/gemm_ablate.py on B200, both control loops under elect.sync):
+//   single CTA, 128 x BN tile : 434 / 465 / 583 / 998 clk at BN = 64 / 128 / 160 / 256 (tensor work: 2 BN clk)
+//   CTA pair,   256 x BN tile : 392 / 397 / 502 / 637 / 885 clk at BN = 64 / 128 / 160 / 192 / 256 PER PAIR - i.e. half that
+//                               per 128 rows: each CTA stages only half of the B tile (cta_group::2)
+// and checked against the sweep of the UNet's own shapes (profiles/r2_gemm_shapes_elect.txt, tools/gemm_shapes.py): the
+// model's choice is within 2 % of the best measured configuration summed over those shapes.  Pairs win wherever the
+// main loop dominates (3x3 convolutions, K >= 2048 linears: 256 x 160 tiles, +9-14 %); they lose on short-K launches
+// (epilogue-bound, and a pair launch costs ~2 us more: cluster scheduling + two cluster barriers).
+static double tile_cost(int ctas, int bn, int splits, int m_tiles, int N, int num_kb, int sms, bool geglu, bool res) {
+  static const double T1[9] = {0, 420, 434, 450, 465, 583, 700, 850, 998};
+  static const double T2[9] = {0, 392, 400, 420, 440, 502, 637, 760, 885};
   const int n_tiles = (N + bn - 1) / bn;
   const int m_units = (m_tiles + ctas - 1) / ctas;
   const long work = (long)m_units * n_tiles * splits;
   const int units = sms / ctas;
   const long waves = (work + units - 1) / units;
-  const double port = (ctas == 1) ? 330.0 + bn : 1.05 * (560.0 + 0.15 * bn);
-  const double t_kb = (2.0 * bn > port) ? 2.0 * bn : port;
-  const double t_epi = 400.0 + 300.0 * ((bn / 32 + 1) / 2);
+  const double t_kb = (ctas == 1 ? T1 : T2)[bn / 32];
+  const int nslab = geglu ? bn / 64 : bn / 32;
+  double t_epi = 1200.0 + nslab * (geglu ? 1500.0 : (res ? 1000.0 : 800.0));
+  if (ctas == 2) t_epi *= 1.05;
   const int kb_per = (num_kb + splits - 1) / splits;
   const double t_main = kb_per * t_kb;
   const double t_tile = (t_main > t_epi ? t_main : t_epi);
@@ -1064,15 +1085,12 @@ static double tile_cost(int ctas, int bn, int splits, int m_tiles, int N, int nu
   // measured (tools/l3_probe.py, cold weights): the level-3 conv (K = 11520) takes 35 / 30 / 57 us at 2 / 4 / 8 splits -
   // beyond 4 the fp32 partials (splits x M x N x 4 B written and read back) cost more than the shorter K loop saves
   const double t_split = splits > 1 ? 6000.0 + 300.0 * splits + (splits > 4 ? 12000.0 : 0.0) : 0.0;
-  return waves * t_tile + t_epi + t_split + 2000.0;
+  return waves * t_tile + t_epi + t_split + 3000.0 + (ctas == 2 ? 4000.0 : 0.0);
 }
 
 // split-K scratch (fp32 partials + per-tile tickets), owned by the library, grown outside graph capture
 struct SplitScratch {
-  float* ws = nullptr;
-  size_t ws_floats = 0;
-  unsigned int* tickets = nullptr;
-  size_t ntickets = 0;
+  ScratchBlock ws_b, tickets_b;
 };
 static SplitScratch g_split[16];
 
@@ -1184,7 +1202,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
           const long tiles = (long)p.m_tiles * ((a->N + bn - 1) / bn);
           if (tiles * sp > sms) break;  // the rendezvous needs every CTA of the launch resident: a single wave
         }
-        const double c = tile_cost(ctas, bn, sp, p.m_tiles, a->N, p.num_kb, sms);
+        const double c = tile_cost(ctas, bn, sp, p.m_tiles, a->N, p.num_kb, sms, geglu, a->residual != nullptr);
         if (best_cost < 0 || c < best_cost) {
           best_cost = c;
           best_bn = bn;
@@ -1207,25 +1225,14 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     SplitScratch& sc = g_split[dev];
     const size_t need = (size_t)best_split * M * a->N;
     const size_t ntick = (size_t)p.m_tiles * p.n_tiles * 2 + 2;
-    if (need > sc.ws_floats || ntick > sc.ntickets) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(stream, &cs);
-      LS_CHECK(cs == cudaStreamCaptureStatusNone, "ls_gemm: split-K scratch must be sized by an eager warm-up run");
-      LS_CUDA(cudaDeviceSynchronize());
-      if (need > sc.ws_floats) {
-        if (sc.ws) cudaFree(sc.ws);
-        sc.ws_floats = need > (size_t)(16u << 20) ? need : (size_t)(16u << 20);  // 64 MB covers every UNet/VAE shape
-        LS_CUDA(cudaMalloc(&sc.ws, sc.ws_floats * sizeof(float)));
-      }
-      if (ntick > sc.ntickets) {
-        if (sc.tickets) cudaFree(sc.tickets);
-        sc.ntickets = ntick > 8192 ? ntick : 8192;
-        LS_CUDA(cudaMalloc(&sc.tickets, sc.ntickets * sizeof(unsigned int)));
-        LS_CUDA(cudaMemset(sc.tickets, 0, sc.ntickets * sizeof(unsigned int)));
-      }
-    }
-    p.ws = sc.ws;
-    p.tickets = sc.tickets;
+    // 64 MB of fp32 partials / 8 K tickets cover every UNet / VAE shape; a superseded block is never freed
+    int rc = scratch_reserve(sc.ws_b, need * sizeof(float), (size_t)64 << 20, false, stream, "ls_gemm");
+    if (rc != 0) return rc;
+    rc = scratch_reserve(sc.tickets_b, ntick * sizeof(unsigned int), (size_t)8192 * sizeof(unsigned int), true, stream,
+                         "ls_gemm");
+    if (rc != 0) return rc;
+    p.ws = reinterpret_cast<float*>(sc.ws_b.ptr);
+    p.tickets = reinterpret_cast<unsigned int*>(sc.tickets_b.ptr);
   }
 
   // tensor maps
@@ -1303,7 +1310,11 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   }
   p.epi_alt = (p.tma_store && p.splits == 1 && (env_alt == 1 || (env_alt == 2 && total >= 3L * units))) ? 1 : 0;
   const int grid = (int)(total < units ? total : units) * CTAS;
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {};  // function attributes are per device
+  int dev_attr = 0;
+  LS_CUDA(cudaGetDevice(&dev_attr));
+  LS_CHECK(dev_attr >= 0 && dev_attr < 16, "ls_gemm: device index %d out of range", dev_attr);
+  bool& attr_set = attr_set_dev[dev_attr];
   if (!attr_set) {
     LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
@@ -1311,7 +1322,12 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     LS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     attr_set = true;
   }
-  if (CTAS == 1)
+  if (CTAS == 1 && p.splits > 1)
+    // split-K CTAs meet at a per-tile ticket inside the kernel: cooperative launch = the driver guarantees that the
+    // whole (single-wave) grid is resident, whatever else runs on the GPU
+    LS_CUDA(launch_coop_k(gemm_tc_kernel<false>, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), (cudaStream_t)(stream),
+                          p));
+  else if (CTAS == 1)
     LS_CUDA(launch_k(geglu ? gemm_tc_kernel<true> : gemm_tc_kernel<false>, dim3(grid), dim3(GEMM_THREADS),
                      (size_t)(smem), (cudaStream_t)(stream), p));
   else

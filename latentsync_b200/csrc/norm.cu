@@ -840,12 +840,18 @@ using namespace ls;
 // scratch for the partial sums + tickets, owned by the library (one per device, grown on demand; single stream use)
 namespace ls {
 struct GnScratch {
-  float* partial = nullptr;
-  size_t partial_floats = 0;
-  unsigned int* tickets = nullptr;
-  size_t ntickets = 0;
+  ScratchBlock partial_b, tickets_b;
+  float* partial() const { return reinterpret_cast<float*>(partial_b.ptr); }
+  unsigned int* tickets() const { return reinterpret_cast<unsigned int*>(tickets_b.ptr); }
 };
 static GnScratch g_gn[16];
+// 4 MB of partial sums / 32 K tickets cover every UNet / VAE shape of this package; larger requests grow (never free)
+static int gn_reserve(GnScratch& sc, size_t partial_floats, size_t ntickets, cudaStream_t stream, const char* who) {
+  int rc = scratch_reserve(sc.partial_b, partial_floats * sizeof(float), (size_t)4 << 20, false, stream, who);
+  if (rc != 0) return rc;
+  return scratch_reserve(sc.tickets_b, ntickets * sizeof(unsigned int), (size_t)32768 * sizeof(unsigned int), true, stream,
+                         who);
+}
 }  // namespace ls
 
 extern "C" int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows,
@@ -862,23 +868,9 @@ extern "C" int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, in
   LS_CHECK(dev >= 0 && dev < 16, "ls_groupnorm_stats: device index %d out of range", dev);
   GnScratch& sc = g_gn[dev];
   const size_t need = (size_t)ninst * chunks * groups * 2;
-  if (need > sc.partial_floats || (size_t)ninst > sc.ntickets) {
-    // growing is not stream-ordered: only legal outside graph capture (plans warm up eagerly before capturing)
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing((cudaStream_t)stream, &cs);
-    LS_CHECK(cs == cudaStreamCaptureStatusNone, "ls_groupnorm_stats: scratch must be sized by an eager warm-up run");
-    LS_CUDA(cudaDeviceSynchronize());
-    if (need > sc.partial_floats) {
-      if (sc.partial) cudaFree(sc.partial);
-      sc.partial_floats = need > (1u << 20) ? need : (1u << 20);
-      LS_CUDA(cudaMalloc(&sc.partial, sc.partial_floats * sizeof(float)));
-    }
-    if ((size_t)ninst > sc.ntickets) {
-      if (sc.tickets) cudaFree(sc.tickets);
-      sc.ntickets = ninst > 4096 ? ninst : 4096;
-      LS_CUDA(cudaMalloc(&sc.tickets, sc.ntickets * sizeof(unsigned int)));
-      LS_CUDA(cudaMemset(sc.tickets, 0, sc.ntickets * sizeof(unsigned int)));
-    }
+  {
+    const int rc = gn_reserve(sc, need, (size_t)ninst, (cudaStream_t)stream, "ls_groupnorm_stats");
+    if (rc != 0) return rc;
   }
   const int threads = 256;
   const int nvec = C / 8;
@@ -886,7 +878,7 @@ extern "C" int ls_groupnorm_stats(const void* x1, int32_t c1, const void* x2, in
   const size_t smem = (size_t)2 * RL * C * sizeof(float);
   LS_CHECK(smem <= 48 * 1024, "ls_groupnorm_stats: C=%d needs %zu bytes of smem", C, smem);
   LS_CUDA(launch_k(gn_stats_kernel, dim3(dim3(chunks, ninst)), dim3(threads), (size_t)(smem), (cudaStream_t)((cudaStream_t)stream), 
-      (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial, stats, sc.tickets));
+      (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial(), stats, sc.tickets()));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -945,7 +937,11 @@ static int groupnorm_cluster_try(const void* x1, int c1, const void* x2, int c2,
   if (ninst * cl < 128 && ninst * cl < 64) return -1;
   const int rows_per_cta = rows_per_inst / cl;
   const size_t smem = (size_t)rows_per_cta * C * 2 + red_bytes;
-  static bool attr_set = false;
+  int dev_i = 0;
+  cudaGetDevice(&dev_i);
+  if (dev_i < 0 || dev_i >= 16) return -1;
+  static bool attr_set_dev[16] = {};  // function attributes are per device
+  bool& attr_set = attr_set_dev[dev_i];
   static bool broken[5] = {false, false, false, false, false};  // per log2(cl): a launch failed once -> never retry
   int lg = 0;
   while ((1 << lg) < cl) ++lg;
@@ -1039,25 +1035,14 @@ extern "C" int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t 
   GnScratch& sc = g_gn[dev];
   const size_t need = (size_t)ninst * chunks * groups * 2;
   const size_t ntick = (size_t)2 * ninst + 2;
-  if (need > sc.partial_floats || ntick > sc.ntickets) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing((cudaStream_t)stream, &cs);
-    LS_CHECK(cs == cudaStreamCaptureStatusNone, "ls_groupnorm: scratch must be sized by an eager warm-up run");
-    LS_CUDA(cudaDeviceSynchronize());
-    if (need > sc.partial_floats) {
-      if (sc.partial) cudaFree(sc.partial);
-      sc.partial_floats = need > (1u << 20) ? need : (1u << 20);
-      LS_CUDA(cudaMalloc(&sc.partial, sc.partial_floats * sizeof(float)));
-    }
-    if (ntick > sc.ntickets) {
-      if (sc.tickets) cudaFree(sc.tickets);
-      sc.ntickets = ntick > 8192 ? ntick : 8192;
-      LS_CUDA(cudaMalloc(&sc.tickets, sc.ntickets * sizeof(unsigned int)));
-      LS_CUDA(cudaMemset(sc.tickets, 0, sc.ntickets * sizeof(unsigned int)));
-    }
+  {
+    const int rc = gn_reserve(sc, need, ntick, (cudaStream_t)stream, "ls_groupnorm");
+    if (rc != 0) return rc;
   }
-  LS_CUDA(launch_k(gn_fused_kernel, dim3(chunks, ninst), dim3(threads), smem, (cudaStream_t)stream,
-                   (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial, sc.tickets,
+  // cooperative launch: the ticket rendezvous inside gn_fused_kernel needs the whole grid resident (chunks * ninst <=
+  // capacity is checked above against the occupancy query; the driver now enforces it against whatever else runs)
+  LS_CUDA(launch_coop_k(gn_fused_kernel, dim3(chunks, ninst), dim3(threads), smem, (cudaStream_t)stream,
+                   (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial(), sc.tickets(),
                    gamma, beta, eps, silu, (__half*)y));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from .spec import SD_VAE_FT_MSE_CONFIG, unet_config
+from .spec import SD_VAE_FT_MSE_CONFIG, unet_config, validate_unet_config
 
 GEGLU_TILE = 256
 KPAD = 64  # GEMM K granularity (one 128-byte swizzle row of fp16)
@@ -155,12 +155,12 @@ class Plan:
             self.run()
         self.graph = g
 
-    def time_kind_in_graph(self, kind: str, reps: int = 5) -> float:
+    def time_kind_in_graph(self, kind: Optional[str], reps: int = 5, exclude: Optional[str] = None) -> float:
         """ms per pass of ONLY the launches of one kind (e.g. "gemm"), captured in plan order into their own CUDA graph
         and timed with CUDA events: kernel time without the host launch gap that the per-launch event pairs of
         `run_timed` include (~3 us x launches).  Buffers keep whatever the last full run left in them (timing of these
-        kernels does not depend on the values)."""
-        fns = [fn for fn, k in zip(self.ops, self.kinds) if k == kind]
+        kernels does not depend on the values).  `kind=None, exclude="gemm"`: every launch EXCEPT that kind."""
+        fns = [fn for fn, k in zip(self.ops, self.kinds) if (kind is None or k == kind) and k != exclude]
         if not fns:
             return 0.0
         s = torch.cuda.Stream(device=self.device)
@@ -360,9 +360,14 @@ class UNetEngine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: dict, device="cuda"):
         self.cfg = unet_config(cfg)
+        validate_unet_config(self.cfg)
         c = self.cfg
         self.device = torch.device(device)
         self.w = _Weights(state_dict, self.device)
+        # the plan assumes bias-free q / k / v projections (attention.py:230-232); the null-audio shortcut depends on it
+        biased = [k for k in state_dict if k.endswith((".to_q.bias", ".to_k.bias", ".to_v.bias"))]
+        if biased:
+            raise NotImplementedError(f"attention projections with bias are not implemented: {biased[:3]}")
         self.plans: Dict[Tuple[int, int, int, int, int], "UNetPlan"] = {}
         self._pack()
 

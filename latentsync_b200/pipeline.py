@@ -68,7 +68,9 @@ class LipsyncPipeline:
     def prepare_latents(self, batch_size, num_frames, num_channels_latents, height, width, dtype, device, generator):
         """lipsync_pipeline.py:182-196: ONE (b,4,1,h,w) draw repeated over all frames of the clip"""
         shape = (batch_size, num_channels_latents, 1, height // self.vae_scale_factor, width // self.vae_scale_factor)
-        latents = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+        device = torch.device(device)
+        rand_device = "cpu" if device.type == "mps" else device
+        latents = torch.randn(shape, generator=generator, device=rand_device, dtype=dtype).to(device)
         latents = latents.repeat(1, 1, num_frames, 1, 1)
         return latents * self.scheduler.init_noise_sigma
 
@@ -222,6 +224,9 @@ class LipsyncPipeline:
             return out
         z = latents / sf + sh
         z = z.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+        vdt = getattr(self.vae, "dtype", None)
+        if isinstance(vdt, torch.dtype) and not hasattr(self.vae, "plan"):
+            z = z.to(vdt)
         return self.vae.decode(z).sample
 
     @torch.no_grad()
@@ -229,7 +234,14 @@ class LipsyncPipeline:
         """decode_latents + paste_surrounding_pixels_back(decoded, ref, 1 - masks) (:571-574) without materialising the
         decoded frames in NCHW: out = decoded * (1 - m) + ref * m, m = `masks` (1 = keep the original pixel)."""
         sf = self.vae.config.scaling_factor
+        sh = float(getattr(self.vae.config, "shift_factor", 0.0) or 0.0)
         _, c, f, h, w = latents.shape
+        if not hasattr(self.vae, "plan") or sh != 0.0:
+            # a foreign VAE (e.g. diffusers' AutoencoderKL, as scripts/inference.py builds it) or a non-zero shift:
+            # the reference's two calls, lipsync_pipeline.py:571-574
+            decoded = self.decode_latents(latents)
+            return self.paste_surrounding_pixels_back(decoded, ref_pixel_values, 1 - masks, latents.device,
+                                                      torch.float32)
         plan = self.vae.plan(f, h, w)
         st = torch.cuda.current_stream().cuda_stream
         lib = L.lib()
@@ -323,36 +335,72 @@ class LipsyncPipeline:
                 frames.append(self.decode_and_paste(lat, seg["ref_pixel_values"], seg["masks"]))
         return frames
 
+    @torch.no_grad()
+    def run_clip(self, segments, num_segments: Optional[int] = None, num_inference_steps: int = 20,
+                 guidance_scale: float = 1.5, segments_per_batch: int = 1, out_dtype: torch.dtype = torch.float16,
+                 gather: bool = True, dst: int = 0) -> Optional[torch.Tensor]:
+        """The segment loop of ONE clip (lipsync_pipeline.py:500-575), sharded over the ranks of the default process
+        group: rank r denoises + decodes the contiguous block `shard_segments(n, r, world)` of the
+        clip's segments - they are independent, every rank holds a full weight replica, there is no data-path
+        collective - and the decoded frames are gathered on `dst` (NCCL point-to-point over NVLink) in `out_dtype`
+        (the reference keeps decoded frames in weight_dtype = fp16, :571-574; 6.3 MB per segment).
+
+        `segments`: the clip's prepared segment inputs (sequence indexed by segment), or a callable `i -> segment` so
+        that a rank only materialises its own shard (`num_segments` is then required).  Without an initialised process
+        group this is the single-GPU loop.  Returns (n_frames, 3, H, W) on `dst`, None on the other ranks
+        (`gather=False`: the local shard's frames on every rank)."""
+        import torch.distributed as dist
+
+        world, rank = 1, 0
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+        n = num_segments if num_segments is not None else len(segments)
+        mine = shard_segments(n, rank, world)
+        get = segments if callable(segments) else segments.__getitem__
+        local = [get(i) for i in mine]
+        frames = self.run_segments(local, num_inference_steps, guidance_scale, segments_per_batch)
+        if frames:
+            out = torch.cat([f.to(out_dtype) for f in frames])
+        else:  # more ranks than segments: an empty shard still takes part in the gather
+            out = torch.empty((0, 3, 0, 0), dtype=out_dtype, device=self.device)
+        if not gather or world == 1:
+            return out
+        return self.gather_frames(out, dst=dst)
+
     @staticmethod
-    def gather_frames(frames: torch.Tensor, seg_counts: Sequence[int], dst: int = 0) -> Optional[torch.Tensor]:
-        """NCCL gather of the per-rank decoded frames to `dst` (ranks hold contiguous blocks of `seg_counts[r]`
-        segments).  frames: (n_local_frames, 3, H, W).  Returns the whole clip on `dst`, None elsewhere."""
+    def gather_frames(frames: torch.Tensor, seg_counts: Optional[Sequence[int]] = None,
+                      dst: int = 0) -> Optional[torch.Tensor]:
+        """Gather of the per-rank decoded frames to `dst` over the default process group (NCCL on the GPUs: point-to-
+        point sends over NVLink; gloo in the CPU tests).  Ranks hold contiguous blocks of the clip in rank order;
+        frames: (n_local_frames, 3, H, W) in any dtype (fp16 / uint8 keep the payload at 6.3 / 3.1 MB per segment).
+        The ranks first agree on every rank's frame count and on the frame geometry (a rank may hold an empty shard, and
+        the clip's last segment may be shorter), so `seg_counts` is only kept for callers of the first version.
+        Returns the whole clip on `dst`, None elsewhere."""
         import torch.distributed as dist
 
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
             return frames
         world, rank = dist.get_world_size(), dist.get_rank()
-        per_seg = frames.shape[0] // max(seg_counts[rank], 1) if seg_counts[rank] else 0
-        per_seg = torch.tensor([per_seg], device=frames.device)
-        dist.all_reduce(per_seg, op=dist.ReduceOp.MAX)
-        f = int(per_seg.item())
-        shape = tuple(frames.shape[1:])
-        outs = None
+        n_local = int(frames.shape[0])
+        meta = torch.tensor([n_local] + (list(frames.shape[1:]) if n_local else [0, 0, 0]), dtype=torch.int64,
+                            device=frames.device)
+        metas = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        counts = [int(m[0].item()) for m in metas]
+        shape = tuple(int(v) for v in torch.stack(metas)[:, 1:].max(dim=0).values.tolist())
         if rank == dst:
-            outs = [torch.empty((seg_counts[r] * f,) + shape, dtype=frames.dtype, device=frames.device)
-                    for r in range(world)]
-        # ragged gather as point-to-point sends: the payload is ~6 MB per segment, NVLink-trivial
-        if rank == dst:
+            outs = [torch.empty((counts[r],) + shape, dtype=frames.dtype, device=frames.device) for r in range(world)]
             reqs = []
             for r in range(world):
                 if r == dst:
-                    outs[r].copy_(frames)
-                elif seg_counts[r] > 0:
+                    if counts[r]:
+                        outs[r].copy_(frames)
+                elif counts[r] > 0:
                     reqs.append(dist.irecv(outs[r], src=r))
             for q in reqs:
                 q.wait()
             return torch.cat(outs, dim=0)
-        if seg_counts[rank] > 0:
+        if n_local > 0:
             dist.send(frames.contiguous(), dst=dst)
         return None
 
@@ -448,14 +496,27 @@ class LipsyncPipeline:
             original_video_frames = truncate_to_length(original_video_frames, n)
             affine_matrices = truncate_to_length(affine_matrices, n)
 
+        # the reference draws the shared initial noise in weight_dtype (fp16) - :489-498 - and so do we: the loop then
+        # carries it in fp32, but it starts from exactly the reference's (fp16-rounded) values
         all_latents = self.prepare_latents(1, len(whisper_chunks), self.vae.config.latent_channels, height, width,
-                                           torch.float32, device, generator)
+                                           weight_dtype, device, generator).float()
         # `segments_per_batch` (extra keyword, swallowed by the reference's **kwargs): advance that many consecutive
         # segments of the clip as ONE UNet batch (denoise_segments: same arithmetic per segment, +8-13 % frames/s at 2-4).
         # The per-segment preparation - and with it the order of the generator's draws - stays the reference's.
         spb = max(1, int(kwargs.get("segments_per_batch", 1)))
         if callback is not None:
             spb = 1  # the callback contract is per step of ONE segment
+        # Multi-GPU: when a torch.distributed process group is up, every rank calls __call__ with the
+        # same arguments; the segments of the clip are sharded in contiguous blocks (shard_segments), frames are
+        # gathered on rank 0, which alone restores / writes the video.  Ranks skip the segments they do not own but
+        # still make the generator draws those segments would have made, so the clip is the single-GPU clip.
+        import torch.distributed as dist
+
+        world, rank = 1, 0
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+        num_inferences = math.ceil(len(whisper_chunks) / num_frames)
+        mine = shard_segments(num_inferences, rank, world)
         synced = []
         pending = []  # prepared segments waiting for their batch
 
@@ -473,11 +534,19 @@ class LipsyncPipeline:
                 synced.append(self.decode_and_paste(lat, g["ref_px"], g["masks"]).to(weight_dtype))
             pending.clear()
 
-        for i in range(math.ceil(len(whisper_chunks) / num_frames)):
+        lat_hw = (height // self.vae_scale_factor, width // self.vae_scale_factor)
+        for i in range(num_inferences):
+            inference_faces = faces[i * num_frames:(i + 1) * num_frames]
+            if i not in mine:
+                # the two encode draws of a segment this rank does not own (prepare_mask_latents, prepare_image_latents)
+                if generator is not None:
+                    shape = (len(inference_faces), self.vae.config.latent_channels) + lat_hw
+                    for _ in range(2):
+                        torch.randn(shape, generator=generator, device=generator.device, dtype=weight_dtype)
+                continue
             audio_embeds = None
             if self.denoising_unet.add_audio_layer:
                 audio_embeds = torch.stack(whisper_chunks[i * num_frames:(i + 1) * num_frames]).to(device)
-            inference_faces = faces[i * num_frames:(i + 1) * num_frames]
             latents = all_latents[:, :, i * num_frames:(i + 1) * num_frames]
             if mask == "fix_mask" and tuple(inference_faces.shape[-2:]) == (height, width):
                 ref_px, masked_px, masks = self.prepare_masks_and_masked_images(inference_faces, mask_image)
@@ -497,6 +566,15 @@ class LipsyncPipeline:
             if len(pending) >= spb:
                 flush()
         flush()
+        if world > 1:
+            local = (torch.cat(synced) if synced else
+                     torch.empty((0, 3, height, width), dtype=weight_dtype, device=device))
+            gathered = self.gather_frames(local, dst=0)
+            if rank != 0:  # rank 0 alone restores the frames and writes the video
+                if is_train:
+                    self.denoising_unet.train()
+                return None
+            synced = [gathered]
         self.image_processor_restore = self.image_processor.restorer
         frames = self._restore_video(torch.cat(synced), original_video_frames, boxes, affine_matrices)
         remain = int(frames.shape[0] / video_fps * audio_sample_rate)

@@ -195,6 +195,48 @@ def unet_config(cfg: dict) -> dict:
     return out
 
 
+# Constructor options that the kernel plan does not implement: they must sit at the value below (all of them do in
+# configs/unet/stage2.yaml and stage1.yaml); anything else raises instead of silently computing something different.
+_SUPPORTED_ONLY = dict(
+    only_cross_attention=False,      # unet_blocks.py passes it to Transformer3DModel: attn1 would become cross-attention
+    dual_cross_attention=False,
+    upcast_attention=False,          # attention runs with fp32 scores / softmax anyway, but to_q / to_k stay fp16
+    use_linear_projection=False,
+    use_inflated_groupnorm=False,    # True = per-frame GroupNorm statistics in the resnets (resnet.py:21-30)
+    mid_block_scale_factor=1,        # output_scale_factor of the mid-block resnets (unet_blocks.py:176)
+    act_fn="silu",
+    downsample_padding=1,
+    resnet_time_scale_shift="default",
+    class_embed_type=None,
+    num_class_embeds=None,
+    mid_block_type="UNetMidBlock3DCrossAttn",
+)
+
+
+def validate_unet_config(cfg: dict) -> None:
+    """raise NotImplementedError for every constructor option the engine would otherwise ignore"""
+    c = unet_config(cfg)
+    for k, want in _SUPPORTED_ONLY.items():
+        if c[k] != want:
+            raise NotImplementedError(f"UNet3DConditionModel({k}={c[k]!r}) is not implemented by latentsync_b200 "
+                                      f"(only {k}={want!r}: the LatentSync stage1/stage2 configs)")
+    if c["use_motion_module"] and c["motion_module_type"] not in ("Vanilla", None):
+        raise NotImplementedError(f"motion_module_type={c['motion_module_type']!r} (only 'Vanilla')")
+    kw = c["motion_module_kwargs"] or {}
+    if c["use_motion_module"]:
+        types = tuple(kw.get("attention_block_types", ("Temporal_Self", "Temporal_Self")))
+        if any(t != "Temporal_Self" for t in types):
+            raise NotImplementedError(f"attention_block_types={types!r} (only 'Temporal_Self')")
+        if kw.get("temporal_attention_dim_div", 1) != 1:
+            raise NotImplementedError("temporal_attention_dim_div != 1")
+    for t in c["down_block_types"]:
+        if t not in ("CrossAttnDownBlock3D", "DownBlock3D"):
+            raise NotImplementedError(f"down block type {t!r}")
+    for t in c["up_block_types"]:
+        if t not in ("CrossAttnUpBlock3D", "UpBlock3D"):
+            raise NotImplementedError(f"up block type {t!r}")
+
+
 def unet_param_spec(cfg: dict) -> "OrderedDict[str, Shape]":
     """state_dict keys and shapes of UNet3DConditionModel(**cfg), in the reference's registration order."""
     c = unet_config(cfg)

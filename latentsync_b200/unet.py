@@ -9,6 +9,8 @@ PyTorch fallback - on a machine without the CUDA extension or a GPU, forward rai
 """
 from __future__ import annotations
 
+import math
+import warnings
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Optional, Tuple, Union
@@ -18,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from .engine import UNetEngine
-from .spec import UNET_CTOR_DEFAULTS, unet_config, unet_param_spec
+from .spec import UNET_CTOR_DEFAULTS, unet_config, unet_param_spec, validate_unet_config
 
 
 @dataclass
@@ -52,6 +54,17 @@ def _set_nested(root: nn.Module, name: str, value, buffer: bool) -> None:
         mod.register_parameter(parts[-1], nn.Parameter(value, requires_grad=False))
 
 
+def _sinusoid_table(shape) -> torch.Tensor:
+    """PositionalEncoding buffer (motion_module.py:221-230): pe[0, p, 2i] = sin(p w_i), pe[0, p, 2i+1] = cos(p w_i)"""
+    _, max_len, d_model = shape
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(1, max_len, d_model)
+    pe[0, :, 0::2] = torch.sin(position * div_term)
+    pe[0, :, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
 class UNet3DConditionModel(nn.Module):
     _supports_gradient_checkpointing = False
 
@@ -61,6 +74,7 @@ class UNet3DConditionModel(nn.Module):
         if unknown:
             raise TypeError(f"UNet3DConditionModel got unexpected arguments {sorted(unknown)}")
         cfg = unet_config(kwargs)
+        validate_unet_config(cfg)
         self._cfg = cfg
         self.config = _Config(cfg)
         self.sample_size = cfg["sample_size"]
@@ -69,7 +83,10 @@ class UNet3DConditionModel(nn.Module):
         # parameter skeleton with the reference's key names; values stay zero-initialised until load_state_dict
         # (the reference default-initialises; inference always loads a checkpoint, scripts/inference.py:60-64)
         for name, shape in unet_param_spec(cfg).items():
-            _set_nested(self, name, torch.zeros(shape), buffer=name.endswith(".pe"))
+            is_pe = name.endswith(".pe")
+            # the sinusoid table is computed, not learned: the reference builds it in PositionalEncoding.__init__
+            # (motion_module.py:221-230), so a checkpoint without `pe` entries must still work
+            _set_nested(self, name, _sinusoid_table(shape) if is_pe else torch.zeros(shape), buffer=is_pe)
         self._engine: Optional[UNetEngine] = None
         self._engine_key = None
         self._out_dtype = torch.float32
@@ -89,7 +106,19 @@ class UNet3DConditionModel(nn.Module):
         if ckpt_path != "":
             ckpt = torch.load(ckpt_path, map_location=device, weights_only=True)
             resume_global_step = ckpt.get("global_step", 0)
-            unet.load_state_dict(ckpt["state_dict"], strict=False)
+            res = unet.load_state_dict(ckpt["state_dict"], strict=False)
+            # every parameter of this skeleton starts at ZERO (the reference default-initialises): a key the checkpoint
+            # does not carry would silently run as zeros.  `pe` buffers are computed in the constructor and the
+            # shape-mismatched conv_in / conv_out / attn2 entries are dropped on purpose (unet.py:473-492).
+            missing = [k for k in res.missing_keys if not k.endswith(".pe")]
+            dropped = set(getattr(unet, "_dropped_keys", ()))
+            hard = [k for k in missing if k not in dropped]
+            if hard:
+                raise KeyError(f"checkpoint {ckpt_path!r} lacks {len(hard)} UNet tensors (they would run as zeros), "
+                               f"e.g. {hard[:4]}")
+            if dropped:
+                warnings.warn(f"{len(dropped)} checkpoint tensors were dropped for shape mismatch and stay "
+                              f"zero-initialised (unet.py:473-492): {sorted(dropped)[:4]} ...")
             del ckpt
         return unet, resume_global_step
 
@@ -97,15 +126,17 @@ class UNet3DConditionModel(nn.Module):
         """drops conv_in / conv_out / attn2.to_k / attn2.to_v entries whose shapes disagree with the config
         (unet.py:473-492) before the normal load"""
         state_dict = dict(state_dict)
+        dropped = []
         if "conv_in.weight" in state_dict and state_dict["conv_in.weight"].shape[1] != self.config.in_channels:
-            state_dict.pop("conv_in.weight")
-            state_dict.pop("conv_in.bias", None)
+            dropped += ["conv_in.weight", "conv_in.bias"]
         if "conv_out.weight" in state_dict and state_dict["conv_out.weight"].shape[0] != self.config.out_channels:
-            state_dict.pop("conv_out.weight")
-            state_dict.pop("conv_out.bias", None)
+            dropped += ["conv_out.weight", "conv_out.bias"]
         for key in [k for k in state_dict if "attn2.to_k." in k or "attn2.to_v." in k]:
             if state_dict[key].shape[1] != self.config.cross_attention_dim:
-                state_dict.pop(key)
+                dropped.append(key)
+        for key in dropped:
+            state_dict.pop(key, None)
+        self._dropped_keys = dropped
         res = super().load_state_dict(state_dict, strict=strict, assign=assign)
         self._engine = None  # repack on next forward
         return res

@@ -102,6 +102,12 @@ class AutoencoderKLDecoder:
             self._enc_engine = VAEEncoderEngine({k: state_dict[k] for k in espec}, cfg, self.device)
 
     def to(self, *a, **k):
+        """The kernel plans live on the device given at construction; a wrapped `encoder=` module (e.g. a diffusers
+        AutoencoderKL that only serves encode) follows the pipeline's `.to(device)` like the reference's VAE does."""
+        if self._encoder is not None and hasattr(self._encoder, "to"):
+            moved = self._encoder.to(*a, **k)
+            if moved is not None:
+                self._encoder = moved
         return self
 
     def eval(self):

@@ -19,6 +19,11 @@ from latentsync_b200.spec import unet_config
 
 SD = Dict[str, torch.Tensor]
 
+# The reference calls F.scaled_dot_product_attention (attention.py:271, motion_module.py:300).  The CPU oracle spells the
+# same arithmetic out (softmax(q k^T d^-0.5) v) so that it does not depend on a fused kernel's rounding; bench.py's
+# PyTorch-eager-on-GPU baseline leg sets this flag to run the reference's actual call (flash / cuDNN SDPA in fp16).
+USE_SDPA = False
+
 
 def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, freq_shift: float = 0.0):
     """diffusers get_timestep_embedding as used at unet.py:95,376 (320 ch, flip_sin_to_cos, shift 0, fp32)"""
@@ -65,7 +70,10 @@ def attention(sd: SD, p: str, x, ctx, heads: int):
     def split(t):
         return t.reshape(b, t.shape[1], heads, d).permute(0, 2, 1, 3)
 
-    a = torch.softmax(split(q) @ split(k).transpose(-1, -2) * d ** -0.5, dim=-1) @ split(v)
+    if USE_SDPA:
+        a = F.scaled_dot_product_attention(split(q), split(k), split(v))
+    else:
+        a = torch.softmax(split(q) @ split(k).transpose(-1, -2) * d ** -0.5, dim=-1) @ split(v)
     a = a.permute(0, 2, 1, 3).reshape(b, s, c)
     return _lin(sd, p + ".to_out.0", a)
 
@@ -149,9 +157,11 @@ def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, audio: torch
     boc = c["block_out_channels"]
     nlev = len(boc)
     if not torch.is_tensor(timestep):
-        timestep = torch.tensor([timestep], dtype=torch.float32)
+        timestep = torch.tensor([timestep], dtype=torch.float32, device=sample.device)
     t = timestep.reshape(-1).float().expand(sample.shape[0])
-    emb = timestep_embedding(t, boc[0], c["flip_sin_to_cos"], c["freq_shift"])
+    # fp32 sinusoid, then the model's dtype (unet.py:376-381: `t_emb = t_emb.to(dtype=self.dtype)`); a no-op for the fp32
+    # CPU oracle, needed when bench.py runs this port in fp16 on the GPU as the PyTorch-eager baseline
+    emb = timestep_embedding(t, boc[0], c["flip_sin_to_cos"], c["freq_shift"]).to(sample.dtype)
     emb = _lin(sd, "time_embedding.linear_2", F.silu(_lin(sd, "time_embedding.linear_1", emb)))
 
     def tap(name, v):

@@ -36,11 +36,42 @@ def _worker(rank, world, port, nseg, out):
     dist.destroy_process_group()
 
 
-def _run(nseg, world=2):
+def _clip_worker(rank, world, port, nseg, out):
+    """run_clip (the sharded clip entry, lipsync_pipeline.py:500-575 over ranks) with a CPU stand-in for run_segments:
+    a callable segment source (only the rank's own shard is materialised), a shorter last segment, fp16 payload"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from latentsync_b200.pipeline import LipsyncPipeline, shard_segments
+
+    pipe = LipsyncPipeline.__new__(LipsyncPipeline)
+    pipe.device = torch.device("cpu")
+    built = []
+
+    def make(i):
+        built.append(i)
+        return {"i": i, "f": 4 if i < nseg - 1 else 2}
+
+    def fake_run_segments(segs, steps, guidance, segments_per_batch=1):
+        return [torch.full((s["f"], 3, 8, 8), float(s["i"])) + torch.arange(s["f"]).view(-1, 1, 1, 1) / 16
+                for s in segs]
+
+    pipe.run_segments = fake_run_segments
+    clip = pipe.run_clip(make, num_segments=nseg, num_inference_steps=2, guidance_scale=1.5, out_dtype=torch.float16)
+    assert built == list(shard_segments(nseg, rank, world))
+    if rank == 0:
+        want = torch.cat(fake_run_segments([{"i": i, "f": 4 if i < nseg - 1 else 2} for i in range(nseg)], 2, 1.5))
+        out.put(bool(clip.dtype == torch.float16 and clip.shape == want.shape and torch.equal(clip, want.half())))
+    else:
+        assert clip is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(nseg, world=2, target=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nseg, q)) for r in range(world)]
+    procs = [ctx.Process(target=target or _worker, args=(r, world, port, nseg, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -59,3 +90,11 @@ def test_gloo_shard_and_gather_ragged():
 
 def test_gloo_shard_and_gather_fewer_segments_than_ranks():
     _run(1)  # rank 1 holds nothing
+
+
+def test_gloo_run_clip_sharded_entry():
+    _run(5, target=_clip_worker)
+
+
+def test_gloo_run_clip_more_ranks_than_segments():
+    _run(1, target=_clip_worker)

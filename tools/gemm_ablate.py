@@ -36,7 +36,7 @@ for bn in ((160,) if os.environ.get('QUICK') else (64, 128, 160, 256)):
         row.append(f"{name} {(t2 - t1) * clk_mhz / kb:5.0f}")
     print(f"BN={bn:3d}: " + " | ".join(row), flush=True)
 if os.environ.get("PAIR", "1") == "1":
-    for bn in (128, 256):
+    for bn in (128, 160, 192, 256):
         N = bn * 18
         t1, t2 = t(M, N, 3200, bn, 0, pair=2), t(M, N, 6400, bn, 0, pair=2)
         print(f"pair BN={bn}: full {(t2 - t1) * clk_mhz / 100:5.0f} clk per k-block per CTA pair (256 x BN x 64; tensor work 2 BN clk per CTA)", flush=True)
