@@ -14,9 +14,15 @@
 //   The exponentials (MUFU, 16 per clock per SM) bound this kernel, not the tensor pipe: 128 x 64 exp per tile = 512
 //   clocks against 192 clocks of MMA (head_dim 40), so several CTAs are resident per SM to keep the MUFU pipe busy.
 //
-// Replaces F.scaled_dot_product_attention at latentsync/models/attention.py:271 for sq >= 128 (the short sequences -
-// 16 frames of temporal attention, 50 audio tokens, the 8x8 / 4x4 levels - stay on the warp-level kernels of
-// attention.cu, they are launch/latency bound).
+// Replaces F.scaled_dot_product_attention at latentsync/models/attention.py:271 and motion_module.py:300:
+//   * spatial self-attention and the audio cross-attention (50 keys: one key tile whose columns >= skv are masked) at
+//     every level - a query tile with fewer than 128 valid rows (8x8 / 4x4 levels) simply leaves TMEM lanes unused;
+//   * PACK = true: the temporal attention over F = 16 frames.  A 128-row tile holds 128 / F PIXELS x F frames, gathered by
+//     ONE 5-D TMA box over the [(b f) (h w)] x C token matrix (frame stride = h*w rows, pixel stride = 1 row: the
+//     "(b f) s c -> (b s) f c" rearrange of motion_module.py:264 is never materialised), rows ordered pixel-major so that
+//     S = Q K^T is block diagonal with F x F blocks; the other blocks are masked before the softmax.  8 sequences share
+//     one pair of tensor-core GEMMs instead of one warp-level mma.sync problem each.
+// The warp-level kernels of attention.cu remain only as the fallback for shapes this path does not take.
 #include "common.cuh"
 #include "../../include/latentsync_b200.h"
 
@@ -36,8 +42,16 @@ struct AttnTcParams {
   int64_t o_batch_stride;  // rows
   int64_t o_seq_stride;    // rows
   float scale_log2;
+  int pack_flog;   // PACK: log2(frames per sequence)
+  int pack_hw;     // PACK: pixels per batch element (extent of the pixel dimension)
   long long* probe;  // LS_ATC_PROBE builds only: clock64 stamps [cta][tile][8]
 };
+
+// masked score in PACK mode.  Finite on purpose: a row whose block lies in the SECOND key tile sees a fully masked first
+// tile; with -inf its running maximum would stay -inf and exp2(-inf - -inf) = NaN.  With a finite value the first tile
+// yields P = 1 garbage that the rescale of the next tile multiplies by exp2((-3e4 - m) * scale) = 0.  Small enough that
+// the rounding error of NEG * scale_log2 stays far below 1 (so exp2(~0) = 1, not inf).
+constexpr float ATC_PACK_NEG = -30000.0f;
 
 #ifdef LS_ATC_PROBE
 #define ATC_STAMP(slot) \
@@ -113,7 +127,7 @@ struct AtcCfg {
   static constexpr int CTAS_PER_SM = (D <= 40) ? 3 : (D <= 80 ? 2 : 1);
 };
 
-template <int D>
+template <int D, bool PACK>
 __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   using Cfg = AtcCfg<D>;
   constexpr int DP = Cfg::DP, KS = Cfg::KS, KSTEPS = Cfg::KSTEPS;
@@ -138,7 +152,10 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = (p.skv + ATC_BKV - 1) / ATC_BKV;
+  // PACK: the tile's 128 keys are its own 128 rows (pixel-major): two key tiles of 64 = 64 / F pixels each
+  const int n_tiles = PACK ? ATC_BQ / ATC_BKV : (p.skv + ATC_BKV - 1) / ATC_BKV;
+  const int ppt = PACK ? (ATC_BQ >> p.pack_flog) : 0;      // pixels per query tile
+  const int ppk = PACK ? (ATC_BKV >> p.pack_flog) : 0;     // pixels per key tile
 
   if (tid == 0) {
     mbar_init(q_full, 1);
@@ -174,16 +191,26 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
       auto load_k = [&](int j, int st) {
         mbar_expect_tx(k_full + st, Cfg::KV_BYTES);
 #pragma unroll
-        for (int s = 0; s < KS; ++s)
-          tma_load_4d(sm + (sK - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapK, k_full + st, s * 64, h,
-                      j * ATC_BKV, b);
+        for (int s = 0; s < KS; ++s) {
+          if constexpr (PACK)
+            tma_load_5d(sm + (sK - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapK, k_full + st, s * 64, h, 0,
+                        qt * ppt + j * ppk, b);
+          else
+            tma_load_4d(sm + (sK - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapK, k_full + st, s * 64, h,
+                        j * ATC_BKV, b);
+        }
       };
       auto load_v = [&](int j, int st) {
         mbar_expect_tx(v_full + st, Cfg::KV_BYTES);
 #pragma unroll
-        for (int s = 0; s < KS; ++s)
-          tma_load_4d(sm + (sV - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapV, v_full + st, s * 64, h,
-                      j * ATC_BKV, b);
+        for (int s = 0; s < KS; ++s) {
+          if constexpr (PACK)
+            tma_load_5d(sm + (sV - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapV, v_full + st, s * 64, h, 0,
+                        qt * ppt + j * ppk, b);
+          else
+            tma_load_4d(sm + (sV - base) + st * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.mapV, v_full + st, s * 64, h,
+                        j * ATC_BKV, b);
+        }
       };
       auto issue_s = [&](int st) {
         // S = Q K^T: KSTEPS steps of K = 16; step ks lies in slab ks / 4 at byte offset (ks % 4) * 32
@@ -209,8 +236,12 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
 
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
-      for (int s = 0; s < KS; ++s)
-        tma_load_4d(sm + (sQ - base) + s * (ATC_BQ * 128), &p.mapQ, q_full, s * 64, h, qt * ATC_BQ, b);
+      for (int s = 0; s < KS; ++s) {
+        if constexpr (PACK)
+          tma_load_5d(sm + (sQ - base) + s * (ATC_BQ * 128), &p.mapQ, q_full, s * 64, h, 0, qt * ppt, b);
+        else
+          tma_load_4d(sm + (sQ - base) + s * (ATC_BQ * 128), &p.mapQ, q_full, s * 64, h, qt * ATC_BQ, b);
+      }
       load_k(0, 0);
       load_v(0, 0);
       if (n_tiles > 1) load_k(1, 1);
@@ -271,7 +302,13 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
       if (tid == 0) ATC_STAMP(5);
       float* s = reinterpret_cast<float*>(&sv[0][0]);
       const int kbase = j * ATC_BKV;
-      if (kbase + ATC_BKV > p.skv) {
+      if constexpr (PACK) {
+        // block-diagonal mask: row r = pixel (r >> flog) attends to the keys of the same pixel only
+        const int my_blk = r >> p.pack_flog;
+#pragma unroll
+        for (int c = 0; c < ATC_BKV; ++c)
+          if (((kbase + c) >> p.pack_flog) != my_blk) s[c] = ATC_PACK_NEG;
+      } else if (kbase + ATC_BKV > p.skv) {
 #pragma unroll
         for (int c = 0; c < ATC_BKV; ++c)
           if (kbase + c >= p.skv) s[c] = -INFINITY;
@@ -335,8 +372,18 @@ __global__ void __launch_bounds__(ATC_THREADS, AtcCfg<D>::CTAS_PER_SM) attn_tc_k
     mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
     tc_fence_after();
     const float inv = 1.f / l;
-    const int qrow = qt * ATC_BQ + r;
-    __half* dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)qrow * p.o_seq_stride) * p.ldo + h * D;
+    int qrow = qt * ATC_BQ + r;
+    __half* dst;
+    if constexpr (PACK) {
+      // row r = (pixel r >> flog, frame r & (F - 1)); o_batch_stride = rows per batch element, o_seq_stride = rows per
+      // frame, pixels are consecutive rows
+      const int pix = qt * ppt + (r >> p.pack_flog);
+      const int fr = r & ((1 << p.pack_flog) - 1);
+      dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)fr * p.o_seq_stride + pix) * p.ldo + h * D;
+      qrow = (pix < p.pack_hw) ? 0 : p.sq;  // the guard below: rows of pixels past the image are not stored
+    } else {
+      dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)qrow * p.o_seq_stride) * p.ldo + h * D;
+    }
 #pragma unroll
     for (int c = 0; c < DP; c += 16) {
       uint32_t ov[16];
@@ -397,6 +444,7 @@ struct Atc2Cfg {
 template <int D>
 __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
   using Cfg = Atc2Cfg<D>;
+  constexpr bool PACK = false;  // version 2 only takes the long, contiguous self-attention sequences
   constexpr int DP = Cfg::DP, KS = Cfg::KS, KSTEPS = Cfg::KSTEPS, NST = Cfg::NST;
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t atc2_smem[];
@@ -420,7 +468,10 @@ __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = (p.skv + ATC_BKV - 1) / ATC_BKV;
+  // PACK: the tile's 128 keys are its own 128 rows (pixel-major): two key tiles of 64 = 64 / F pixels each
+  const int n_tiles = PACK ? ATC_BQ / ATC_BKV : (p.skv + ATC_BKV - 1) / ATC_BKV;
+  const int ppt = PACK ? (ATC_BQ >> p.pack_flog) : 0;      // pixels per query tile
+  const int ppk = PACK ? (ATC_BKV >> p.pack_flog) : 0;     // pixels per key tile
 
   if (tid == 0) {
     mbar_init(q_full, 1);
@@ -539,7 +590,13 @@ __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2
       tmem_ld_wait();
       float* s = reinterpret_cast<float*>(&sv[0][0]);
       const int kbase = j * ATC_BKV;
-      if (kbase + ATC_BKV > p.skv) {
+      if constexpr (PACK) {
+        // block-diagonal mask: row r = pixel (r >> flog) attends to the keys of the same pixel only
+        const int my_blk = r >> p.pack_flog;
+#pragma unroll
+        for (int c = 0; c < ATC_BKV; ++c)
+          if (((kbase + c) >> p.pack_flog) != my_blk) s[c] = ATC_PACK_NEG;
+      } else if (kbase + ATC_BKV > p.skv) {
 #pragma unroll
         for (int c = 0; c < ATC_BKV; ++c)
           if (kbase + c >= p.skv) s[c] = -INFINITY;
@@ -601,8 +658,18 @@ __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2
     mbar_wait(fin, 0);
     tc_fence_after();
     const float inv = 1.f / l;
-    const int qrow = qt * ATC_BQ + r;
-    __half* dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)qrow * p.o_seq_stride) * p.ldo + h * D;
+    int qrow = qt * ATC_BQ + r;
+    __half* dst;
+    if constexpr (PACK) {
+      // row r = (pixel r >> flog, frame r & (F - 1)); o_batch_stride = rows per batch element, o_seq_stride = rows per
+      // frame, pixels are consecutive rows
+      const int pix = qt * ppt + (r >> p.pack_flog);
+      const int fr = r & ((1 << p.pack_flog) - 1);
+      dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)fr * p.o_seq_stride + pix) * p.ldo + h * D;
+      qrow = (pix < p.pack_hw) ? 0 : p.sq;  // the guard below: rows of pixels past the image are not stored
+    } else {
+      dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)qrow * p.o_seq_stride) * p.ldo + h * D;
+    }
 #pragma unroll
     for (int c = 0; c < DP; c += 16) {
       uint32_t ov[16];
@@ -688,22 +755,59 @@ static int atc_version() {
   return v;
 }
 
-template <int D>
+// PACK maps: [d][head][frame][pixel][batch element] view of the token matrix [(b f) (h w)] x ld
+static int encode_pack(PFN_tmapEncodeTiled encode, CUtensorMap* map, const void* ptr, int D, int heads, int F, int hw,
+                       int nb, int64_t ld, int64_t seq_stride, int64_t inner_stride, int64_t outer_stride, int box_pix,
+                       const char* what) {
+  cuuint64_t gdim[5] = {(cuuint64_t)D, (cuuint64_t)heads, (cuuint64_t)F, (cuuint64_t)hw, (cuuint64_t)nb};
+  cuuint64_t gstr[4] = {(cuuint64_t)D * 2, (cuuint64_t)(seq_stride * ld) * 2, (cuuint64_t)(inner_stride * ld) * 2,
+                        (cuuint64_t)(outer_stride * ld) * 2};
+  cuuint32_t box[5] = {64, 1, (cuuint32_t)F, (cuuint32_t)box_pix, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LS_CHECK(r == CUDA_SUCCESS, "ls_attention: cuTensorMapEncodeTiled(%s, packed) failed with %d", what, (int)r);
+  return 0;
+}
+
+template <int D, bool PACK>
 static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
   using Cfg = AtcCfg<D>;
   PFN_tmapEncodeTiled encode = atc_encode_fn();
   LS_CHECK(encode != nullptr, "ls_attention: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   AttnTcParams p;
   memset(&p, 0, sizeof(p));
-  if (encode_bshd(encode, &p.mapQ, a->q, D, a->heads, a->sq, a->batch, a->ldq, a->q_seq_stride, a->q_outer_stride,
-                  ATC_BQ, "Q"))
-    return 1;
-  if (encode_bshd(encode, &p.mapK, a->k, D, a->heads, a->skv, a->batch, a->ldk, a->kv_seq_stride, a->kv_outer_stride,
-                  ATC_BKV, "K"))
-    return 1;
-  if (encode_bshd(encode, &p.mapV, a->v, D, a->heads, a->skv, a->batch, a->ldv, a->kv_seq_stride, a->kv_outer_stride,
-                  ATC_BKV, "V"))
-    return 1;
+  dim3 grid;
+  if constexpr (PACK) {
+    // temporal attention: batch = nb * hw sequences of F tokens; sequence (e, pix) lives at rows e * outer + pix * inner
+    // (+ f * seq).  Tile = 128 / F pixels x F frames.
+    const int F = a->sq, hw = a->q_inner, nb = a->batch / a->q_inner;
+    int flog = 0;
+    while ((1 << flog) < F) ++flog;
+    const int ppt = ATC_BQ / F, ppk = ATC_BKV / F;
+    if (encode_pack(encode, &p.mapQ, a->q, D, a->heads, F, hw, nb, a->ldq, a->q_seq_stride, a->q_inner_stride,
+                    a->q_outer_stride, ppt, "Q") ||
+        encode_pack(encode, &p.mapK, a->k, D, a->heads, F, hw, nb, a->ldk, a->kv_seq_stride, a->kv_inner_stride,
+                    a->kv_outer_stride, ppk, "K") ||
+        encode_pack(encode, &p.mapV, a->v, D, a->heads, F, hw, nb, a->ldv, a->kv_seq_stride, a->kv_inner_stride,
+                    a->kv_outer_stride, ppk, "V"))
+      return 1;
+    p.pack_flog = flog;
+    p.pack_hw = hw;
+    grid = dim3((hw + ppt - 1) / ppt, a->heads, nb);
+  } else {
+    if (encode_bshd(encode, &p.mapQ, a->q, D, a->heads, a->sq, a->batch, a->ldq, a->q_seq_stride, a->q_outer_stride,
+                    ATC_BQ, "Q"))
+      return 1;
+    if (encode_bshd(encode, &p.mapK, a->k, D, a->heads, a->skv, a->batch, a->ldk, a->kv_seq_stride,
+                    a->kv_outer_stride, ATC_BKV, "K"))
+      return 1;
+    if (encode_bshd(encode, &p.mapV, a->v, D, a->heads, a->skv, a->batch, a->ldv, a->kv_seq_stride,
+                    a->kv_outer_stride, ATC_BKV, "V"))
+      return 1;
+    grid = dim3((a->sq + ATC_BQ - 1) / ATC_BQ, a->heads, a->batch);
+  }
   p.o = reinterpret_cast<__half*>(a->out);
   p.ldo = a->ldo;
   p.sq = a->sq;
@@ -725,12 +829,11 @@ static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
   static bool attr_set_dev[16] = {};
   bool& attr_set = attr_set_dev[dev_slot()];
   if (!attr_set) {
-    LS_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    if (D == 80)
+    LS_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    if (D == 80 && !PACK)
       LS_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Atc2Cfg<D>::SMEM));
     attr_set = true;
   }
-  dim3 grid((a->sq + ATC_BQ - 1) / ATC_BQ, a->heads, a->batch);
   // Measured (tools/attn_bench.py): version 2 wins at head_dim 80 (S = 1024: 540 -> 419 us, S = 256: 33.5 -> 31.0 us)
   // and ties at head_dim 40 (129.6 vs 127.8 us: with one or four waits per tile, two or three CTAs per SM, both land at
   // ~1100 clocks per key tile per SM - the softmax warps' own per-tile latency chain, not the control thread, is
@@ -739,8 +842,9 @@ static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
   // the warps' latency chain is the limit; the candidates left are shared-memory bandwidth (per key tile the MMAs
   // re-read 16 KB of Q and 16 KB of P, the warps write 16 KB of P, TMA writes 16 KB of K/V: ~80 KB against 128 B/clk)
   // and the TMEM read of S (32 KB per tile).  Next: P as the A operand from TMEM.)  head_dim 160 stays on version 1 (the
-  // 3-stage ring variant of version 2 still has an accounting bug: its control thread times out).
-  if (atc_version() == 2 && D == 80) {
+  // 3-stage ring variant of version 2 still has an accounting bug: its control thread times out).  Version 2 only takes
+  // the long self-attention sequences it was written for (>= 2 full key tiles).
+  if (!PACK && atc_version() == 2 && D == 80 && a->sq >= ATC_BQ && a->skv >= 2 * ATC_BKV) {
     static const int pad = getenv("LS_ATTN_SMEM_PAD") ? atoi(getenv("LS_ATTN_SMEM_PAD")) : 0;  // debugging: forces 1 CTA/SM
     size_t smem2 = (size_t)Atc2Cfg<D>::SMEM + (size_t)pad;
     if (smem2 > 227 * 1024) smem2 = 227 * 1024;
@@ -748,27 +852,59 @@ static int launch_attn_tc(const LsAttnArgs* a, cudaStream_t stream) {
     LS_CUDA(launch_k(attn_tc2_kernel<D>, grid, dim3(ATC_THREADS), smem2, stream, p));
   }
   else {
-    LS_CUDA(launch_k(attn_tc_kernel<D>, grid, dim3(ATC_THREADS), (size_t)Cfg::SMEM, stream, p));
+    LS_CUDA(launch_k(attn_tc_kernel<D, PACK>, grid, dim3(ATC_THREADS), (size_t)Cfg::SMEM, stream, p));
   }
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
+template <int D>
+static int launch_attn_tc_any(const LsAttnArgs* a, bool pack, cudaStream_t stream) {
+  return pack ? launch_attn_tc<D, true>(a, stream) : launch_attn_tc<D, false>(a, stream);
+}
+
 // returns -1 when the problem is not one for this path (the caller then uses the warp-level kernels)
 int attention_tc_try(const LsAttnArgs* a, cudaStream_t stream) {
   if (!atc_enabled()) return -1;
-  if (a->q_inner != 1 || a->kv_inner != 1) return -1;      // strided batches (temporal attention)
-  if (a->sq < ATC_BQ || a->skv < ATC_BKV) return -1;        // short sequences
-  if (a->batch > 65535 || a->heads > 65535) return -1;
+  // Which problems take this kernel.  Measured (profiles/r2d_attention_all_tcgen05.txt): the flash kernel is built for
+  // long key sequences - one CTA per (query tile, head) pays ~8-10 k clocks of setup and hand-shake latency - so on
+  // one- or two-tile problems it LOSES to the warp-level kernels: packed temporal 40.4 vs 23.8 us (level 0), 4x4 level
+  // 14.7 vs 8.5 us, 8x8 self 14.8 vs 12.6 us, audio cross-attention 21.2 vs 20.8 us.  Default: >= 128 queries and >= 2
+  // full key tiles.  LS_ATTN_TC_ALL=1 routes everything it can take (tests run both).
+  static int all = -1;
+  if (all < 0) {
+    const char* e = getenv("LS_ATTN_TC_ALL");
+    all = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!all && (a->q_inner != 1 || a->kv_inner != 1 || a->sq < ATC_BQ || a->skv < 2 * ATC_BKV)) return -1;
+  bool pack = false;
+  if (a->q_inner != 1 || a->kv_inner != 1) {
+    // strided batches = temporal attention: packed mode needs self-attention geometry (same addressing for q and k/v),
+    // consecutive pixels one row apart, and a power-of-two sequence length that divides a 64-key tile
+    const int F = a->sq;
+    if (a->sq != a->skv || F < 2 || F > ATC_BKV || (F & (F - 1)) != 0) return -1;
+    if (a->q_inner != a->kv_inner || a->q_inner_stride != 1 || a->kv_inner_stride != 1) return -1;
+    if (a->q_outer_stride != a->kv_outer_stride || a->q_seq_stride != a->kv_seq_stride) return -1;
+    if (a->batch % a->q_inner != 0) return -1;
+    if (a->batch / a->q_inner > 65535) return -1;
+    pack = true;
+  } else {
+    if (a->batch > 65535) return -1;
+  }
+  if (a->heads > 65535) return -1;
   if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8)) return -1;
   if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
        reinterpret_cast<uintptr_t>(a->out)) & 15)
     return -1;
+  if (a->head_dim % 8) return -1;  // 16-byte rows per head for TMA and the vector stores
   switch (a->head_dim) {
-    case 40: return launch_attn_tc<40>(a, stream);
-    case 80: return launch_attn_tc<80>(a, stream);
-    case 160: return launch_attn_tc<160>(a, stream);
+    case 16: return launch_attn_tc_any<16>(a, pack, stream);
+    case 32: return launch_attn_tc_any<32>(a, pack, stream);
+    case 40: return launch_attn_tc_any<40>(a, pack, stream);
+    case 64: return launch_attn_tc_any<64>(a, pack, stream);
+    case 80: return launch_attn_tc_any<80>(a, pack, stream);
+    case 160: return launch_attn_tc_any<160>(a, pack, stream);
     default: return -1;
   }
 }

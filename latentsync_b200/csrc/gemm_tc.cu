@@ -674,23 +674,33 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         float* my_bias = bias_sm + group * 256;
         my_bias[gtid] = bias_next[0];
         my_bias[gtid + 128] = bias_next[1];
-        // (2) residual fragments: two slabs in flight (a rolling pair of register buffers)
-        uint4 res[2][4];
-        auto fetch_res = [&](int s, uint4 (&dst)[4]) {
-          const int j = j_lo + s;
+        // (2) residual of the NEXT pair of slabs, requested one pair ahead with COALESCED loads: instruction i of a
+        //     pair (32 rows x 128 bytes per warp) has lane l read 16-byte chunk (l & 7) of row 4 i + (l >> 3), i.e. four
+        //     whole 128-byte lines per instruction.  (A thread reading its own row's 64 bytes - the layout the
+        //     accumulator arrives in - touches 32 lines per instruction: the L1 spent ~2000 wavefronts per tile on it,
+        //     as much as the whole main loop of a K = 320 linear.)  The chunks reach their rows through the warp's
+        //     staging buffer: stored at the 128B-swizzled position the output chunk will take, read back by the row's
+        //     thread (both patterns conflict-free), then overwritten by the output.
+        uint4 res[8];
+        const bool has_res = (p.residual != nullptr);
+        auto fetch_res_pair = [&](int s0) {  // slabs j_lo + s0, j_lo + s0 + 1 (or the trailing single slab)
+          const int j = j_lo + s0;
           const int ncol0 = nt * BN + j * 32;
-          if (p.residual != nullptr && j < j_hi && row_ok && ncol0 + 32 <= n_out_total) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * (int64_t)p.ldr + ncol0);
+          const bool single = (j == j_hi - 1);
+          const int64_t mrow0 = m0 + q * 32;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dst[e] = __ldg(rp + e);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) dst[e] = make_uint4(0u, 0u, 0u, 0u);
+          for (int i = 0; i < 8; ++i) {
+            // pair: 4 rows x 8 chunks per instruction; single slab (64-byte rows): 8 rows x 4 chunks, 4 instructions
+            const int rr = single ? (i * 8 + (lane >> 2)) : (i * 4 + (lane >> 3));
+            const int cc = single ? (lane & 3) : (lane & 7);
+            const int col = ncol0 + cc * 8;
+            const bool ok = has_res && j < j_hi && (!single || i < 4) && (mrow0 + rr < p.M) && (col + 8 <= n_out_total);
+            res[i] = ok ? __ldg(reinterpret_cast<const uint4*>(p.residual + (mrow0 + rr) * (int64_t)p.ldr + col))
+                        : make_uint4(0u, 0u, 0u, 0u);
           }
         };
         EP_STAMP(9);
-        fetch_res(0, res[0]);
-        fetch_res(1, res[1]);
+        if (has_res) fetch_res_pair(0);
         EP_STAMP(10);
         fetch_bias(w + w_step);  // (3) this group's next work item's bias row -> registers
         EP_STAMP(0);
@@ -857,25 +867,44 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             if (lane == 0) mbar_arrive_leader<CTAS>(&tmem_empty[acc]);
             released = true;
           }
-          if (p.residual != nullptr) {
-            if (ncol0 + 32 <= n_out_total) {
-#pragma unroll
-              for (int e4 = 0; e4 < 4; ++e4) {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&res[hs][e4]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t = __half22float2(h2[e]);
-                  f[e4 * 8 + e * 2] += t.x;
-                  f[e4 * 8 + e * 2 + 1] += t.y;
+          // stage address of this thread's row: pair = 128-byte rows, chunk c at c ^ (lane & 7) (SWIZZLE_128B);
+          // trailing single slab = 64-byte rows, chunk c at c ^ ((lane >> 1) & 3) (SWIZZLE_64B)
+          const int half_sel = hs;
+          const bool single = (half_sel == 0) && (s == n_mine - 1);
+          if (has_res && hs == 0) {
+            // the previous store has finished reading the buffer -> park this pair's residual chunks, request the next pair's
+            const bool single_p = single;
+            if (lane == 0) bulk_wait_group_read<0>();
+            __syncwarp();
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (single_p) {
+                if (i < 4) {
+                  const int rr = i * 8 + (lane >> 2), cc = lane & 3;
+                  *reinterpret_cast<uint4*>(my_stage + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4)) = res[i];
                 }
+              } else {
+                const int rr = i * 4 + (lane >> 3), cc = lane & 7;
+                *reinterpret_cast<uint4*>(my_stage + rr * 128 + ((cc ^ (rr & 7)) << 4)) = res[i];
               }
-            } else if (row_ok) {  // ragged last slab: scalar, in-bounds columns only
-              const __half* rr = p.residual + m * (int64_t)p.ldr + ncol0;
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (ncol0 + e < n_out_total) f[e] += __half2float(rr[e]);
             }
-            fetch_res(s + 2, res[hs]);  // refill the buffer just consumed (zeros beyond the last slab)
+            __syncwarp();
+            fetch_res_pair(2 * pi + 2);
+          }
+          if (has_res) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint8_t* src = single ? my_stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)
+                                          : my_stage + lane * 128 + (((half_sel * 4 + c) ^ (lane & 7)) << 4);
+              const uint4 u = *reinterpret_cast<const uint4*>(src);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __half22float2(h2[e]);
+                f[c * 8 + e * 2] += t.x;
+                f[c * 8 + e * 2 + 1] += t.y;
+              }
+            }
           }
           if (p.flags & LS_EPI_SILU) {
 #pragma unroll
@@ -883,9 +912,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           }
           // stage.  Pair: row `lane` of the warp's buffer is 128 bytes, 16-byte chunk c sits at c ^ (lane & 7)
           // (SWIZZLE_128B).  Trailing single slab: 64-byte rows, chunk c at c ^ ((lane >> 1) & 3) (SWIZZLE_64B).
-          const int half_sel = hs;
-          const bool single = (half_sel == 0) && (s == n_mine - 1);
-          if (half_sel == 0) {  // the previous store has finished reading the buffer
+          if (half_sel == 0 && !has_res) {  // the previous store has finished reading the buffer
             if (lane == 0) bulk_wait_group_read<0>();
             __syncwarp();
           }
@@ -1067,8 +1094,10 @@ static int num_sms() {
 // main loop dominates (3x3 convolutions, K >= 2048 linears: 256 x 160 tiles, +9-14 %); they lose on short-K launches
 // (epilogue-bound, and a pair launch costs ~2 us more: cluster scheduling + two cluster barriers).
 static double tile_cost(int ctas, int bn, int splits, int m_tiles, int N, int num_kb, int sms, bool geglu, bool res) {
-  static const double T1[9] = {0, 420, 434, 450, 465, 583, 700, 850, 998};
-  static const double T2[9] = {0, 392, 400, 420, 440, 502, 637, 760, 885};
+  // (the ablation's N = 18 tiles / M = 2048 problem is the L2-contention worst case for wide tiles; the wide-tile entries
+  // below are the per-k-block clocks of the large-M VAE convolutions, profiles/r2_gemm_shapes_vae.txt)
+  static const double T1[9] = {0, 420, 434, 450, 495, 583, 680, 780, 880};
+  static const double T2[9] = {0, 392, 400, 430, 460, 505, 600, 700, 815};
   const int n_tiles = (N + bn - 1) / bn;
   const int m_units = (m_tiles + ctas - 1) / ctas;
   const long work = (long)m_units * n_tiles * splits;
@@ -1158,7 +1187,9 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   const bool rows_contig = (a->W < BM) || (a->W % BM == 0) || (a->H == 1 && a->nimg == 1);
   p.tma_store = (!(a->flags & LS_EPI_OUT_F32) && (a->ldo % 8 == 0) && rows_contig && M < (1ll << 31) &&
                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->bias_div == 0 || a->bias_div % BM == 0) &&
-                 (a->residual == nullptr || ((a->ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0)))
+                 (a->residual == nullptr ||
+                  ((a->ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 &&
+                   ((a->flags & LS_EPI_GEGLU ? a->N / 2 : a->N) % 8 == 0))))
                     ? 1
                     : 0;
 

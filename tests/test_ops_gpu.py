@@ -5,6 +5,8 @@ fp32 on both sides, so the only difference is summation order and the final fp16
 """
 import math
 
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -403,3 +405,17 @@ def test_layout_and_time_embedding():
     L.small_linear(emb, 2, 320, w, b, add, 1280, True, True, yv)
     want = F.silu(F.silu(emb) @ w.float().t() + b) + add
     assert rel_l2(yv, want) < 1e-5
+
+
+def test_attention_every_shape_on_the_tcgen05_kernel():
+    """LS_ATTN_TC_ALL=1 routes the audio cross-attention (50 keys), the 8x8 / 4x4 levels and the temporal attention
+    (packed: 128-row tiles of 128 / F pixels x F frames, block-diagonal mask) to the tcgen05 flash kernel instead of the
+    warp-level kernels.  The switch is read once per process, so the attention tests re-run in a child process."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, LS_ATTN_TC_ALL="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k",
+                          "attention and not every_shape", "--no-header", "-p", "no:cacheprovider"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]

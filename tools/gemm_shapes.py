@@ -45,6 +45,12 @@ SHAPES = [
     ("conv L2 2560->1280", 32, 8, 8, [(2560, 9)], 1280, 0, False),
     ("conv L3 1280->1280", 32, 4, 4, [(1280, 9)], 1280, 0, True),
     ("conv L3 2560->1280", 32, 4, 4, [(2560, 9)], 1280, 0, False),
+    ("vae 512 32x32", 16, 32, 32, [(512, 9)], 512, 0, True),
+    ("vae 512 64x64", 16, 64, 64, [(512, 9)], 512, 0, True),
+    ("vae 512->256 128x128", 16, 128, 128, [(512, 9)], 256, 0, False),
+    ("vae 256 128x128", 16, 128, 128, [(256, 9)], 256, 0, True),
+    ("vae 256->128 256x256", 16, 256, 256, [(256, 9)], 128, 0, False),
+    ("vae 128 256x256", 16, 256, 256, [(128, 9)], 128, 0, True),
 ]
 
 
