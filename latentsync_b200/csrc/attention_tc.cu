@@ -699,6 +699,323 @@ __global__ void __launch_bounds__(ATC_THREADS, Atc2Cfg<D>::CTAS_PER_SM) attn_tc2
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// =================================================================================================================
+// One-tile attention: every problem whose keys fit ONE key tile - the audio cross-attention (50 keys), the 8x8 / 4x4
+// levels (64 / 16 keys) and, PACK = true, the temporal attention over F <= 32 frames (a 128-row tile of 128 / F pixels x
+// F frames attends to itself through a block-diagonal mask).  No online softmax, no rescale: S = Q K^T, one softmax pass,
+// O = P V.  The flash kernel above pays ~8-10 k clocks of per-CTA setup and hand-shake latency, fine for 16 key tiles and
+// ruinous for one (packed temporal attention: 40 us against 24 us on the warp-level kernel), so this kernel is
+// PERSISTENT: a CTA walks over (query tile, head) work items, its control thread keeps the Q / K / V loads of the next
+// items in flight (ring of NST stages) and issues S_{i+1} while the four softmax warps (thread = row) are still busy
+// with item i; O is double buffered in TMEM so that the store of item i - 1 overlaps P V_i.
+//   per item:  control  wait loads_i, [S_{i-1} read] -> S_i MMAs -> (S_i done => P V_{i-1} done: refill its stage)
+//                       wait P_i, [O buffer read]   -> P V_i MMAs
+//              warps    wait S_i -> tcgen05.ld -> mask / max / exp2 / sum -> P_i (fp16, 128B-swizzled A tile) -> signal
+//                       then the epilogue of item i - 1: tcgen05.ld O, * 1 / l, fp16 rows to global
+// PACK: the row's keys are columns [32 w, 32 w + 32) of S for warp w (rows are pixel-major, F divides 32), so a thread
+// loads ONE 32-column block, masks the other pixels' columns, and writes 64 bytes of P; the rest of the P tile is zeroed
+// once per CTA and never touched again.
+// =================================================================================================================
+template <int D, bool PACK>
+struct AtoCfg {
+  static constexpr int DP = (D + 15) / 16 * 16;
+  static constexpr int KS = (DP + 63) / 64;
+  static constexpr int KSTEPS = DP / 16;
+  static constexpr int KT = PACK ? 128 : 64;             // keys per tile
+  static constexpr int Q_BYTES = KS * ATC_BQ * 128;
+  static constexpr int KV_SLAB = KT * 128;
+  static constexpr int KV_BYTES = KS * KV_SLAB;
+  static constexpr int STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;
+  static constexpr int P_BYTES = (KT / 64) * ATC_BQ * 128;
+  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int NST_RAW = (BUDGET - P_BYTES) / STAGE_BYTES;
+  static constexpr int NST = NST_RAW > 3 ? 3 : (NST_RAW < 1 ? 1 : NST_RAW);
+  static constexpr int TILE_BYTES = NST * STAGE_BYTES + P_BYTES;
+  static constexpr int SMEM = TILE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+  static constexpr int TMEM_NEED = KT + 2 * DP;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static constexpr int CTAS_PER_SM = (2 * SMEM <= 226 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
+};
+
+struct AttnOneParams {
+  CUtensorMap mapQ, mapK, mapV;
+  __half* o;
+  int ldo;
+  int sq, skv;
+  int64_t o_batch_stride;  // rows
+  int64_t o_seq_stride;    // rows
+  float scale_log2;
+  int heads, tiles_q;      // work item w -> h = w % heads, qt = (w / heads) % tiles_q, b = w / (heads * tiles_q)
+  int n_items;
+  int pack_flog, pack_hw;
+};
+
+template <int D, bool PACK>
+__global__ void __launch_bounds__(ATC_THREADS, AtoCfg<D, PACK>::CTAS_PER_SM) attn_one_kernel(const __grid_constant__ AttnOneParams p) {
+  using Cfg = AtoCfg<D, PACK>;
+  constexpr int DP = Cfg::DP, KS = Cfg::KS, KSTEPS = Cfg::KSTEPS, KT = Cfg::KT, NST = Cfg::NST;
+  pdl_prologue();
+  extern __shared__ uint8_t ato_smem_raw[];
+  const uint32_t raw = smem_u32(ato_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = ato_smem_raw + (base - raw);
+  const uint32_t sP = base + NST * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Cfg::TILE_BYTES);
+  uint64_t* full = bars + 0;      // [NST] loads of an item have landed
+  uint64_t* s_full = bars + 4;    // S_i complete (and every earlier MMA)
+  uint64_t* s_free = bars + 5;    // the 4 warps hold S_i in registers
+  uint64_t* p_full = bars + 6;    // the 4 warps have written P_i
+  uint64_t* o_full = bars + 7;    // [2] P V_i complete
+  uint64_t* o_free = bars + 9;    // [2] the 4 warps have read O buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_mine = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items w = blockIdx.x + i * gridDim.x
+  const int ppt = PACK ? (ATC_BQ >> p.pack_flog) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) mbar_init(full + s, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full + 0, 1);
+    mbar_init(o_full + 1, 1);
+    mbar_init(o_free + 0, 4);
+    mbar_init(o_free + 1, 4);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem;         // columns [0, KT): scores
+  const uint32_t tO = tmem + KT;    // columns [KT, KT + 2 DP): two output accumulators
+
+  auto decode = [&](int i, int& qt, int& h, int& b) {
+    const int w = (int)blockIdx.x + i * (int)gridDim.x;
+    h = w % p.heads;
+    const int t = w / p.heads;
+    qt = t % p.tiles_q;
+    b = t / p.tiles_q;
+  };
+
+  if (warp == 4) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ control: TMA producer + MMA issuer
+      tma_prefetch_desc(&p.mapQ);
+      tma_prefetch_desc(&p.mapK);
+      tma_prefetch_desc(&p.mapV);
+      constexpr uint32_t idesc_s = (1u << 4) | (uint32_t(KT >> 3) << 17) | (uint32_t(ATC_BQ >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 16) | (uint32_t(DP >> 3) << 17) | (uint32_t(ATC_BQ >> 4) << 24);
+      auto load_item = [&](int i) {
+        int qt, h, b;
+        decode(i, qt, h, b);
+        const int st = i % NST;
+        uint8_t* q_dst = sm + st * Cfg::STAGE_BYTES;
+        uint8_t* k_dst = q_dst + Cfg::Q_BYTES;
+        uint8_t* v_dst = k_dst + Cfg::KV_BYTES;
+        mbar_expect_tx(full + st, Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          if constexpr (PACK) {
+            tma_load_5d(q_dst + s * (ATC_BQ * 128), &p.mapQ, full + st, s * 64, h, 0, qt * ppt, b);
+            tma_load_5d(k_dst + s * Cfg::KV_SLAB, &p.mapK, full + st, s * 64, h, 0, qt * ppt, b);
+            tma_load_5d(v_dst + s * Cfg::KV_SLAB, &p.mapV, full + st, s * 64, h, 0, qt * ppt, b);
+          } else {
+            tma_load_4d(q_dst + s * (ATC_BQ * 128), &p.mapQ, full + st, s * 64, h, qt * ATC_BQ, b);
+            tma_load_4d(k_dst + s * Cfg::KV_SLAB, &p.mapK, full + st, s * 64, h, 0, b);
+            tma_load_4d(v_dst + s * Cfg::KV_SLAB, &p.mapV, full + st, s * 64, h, 0, b);
+          }
+        }
+      };
+      for (int i = 0; i < NST && i < n_mine; ++i) load_item(i);
+      for (int i = 0; i < n_mine; ++i) {
+        const int st = i % NST;
+        const uint32_t sQ = base + st * Cfg::STAGE_BYTES;
+        const uint32_t sK = sQ + Cfg::Q_BYTES;
+        const uint32_t sV = sK + Cfg::KV_BYTES;
+        mbar_wait(full + st, (uint32_t)((i / NST) & 1));
+        if (i > 0) mbar_wait(s_free, (uint32_t)((i - 1) & 1));  // the warps hold S_{i-1}: its TMEM columns are free
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t qa = sQ + (ks >> 2) * (ATC_BQ * 128) + (ks & 3) * 32;
+          const uint32_t ka = sK + (ks >> 2) * Cfg::KV_SLAB + (ks & 3) * 32;
+          umma_f16_ss(tS, umma_desc_sw128(qa), umma_desc_sw128(ka), idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        if (NST > 1) {
+          // S_i complete => P V_{i-1} complete (the tensor pipe runs in issue order): stage (i - 1) % NST can be refilled
+          mbar_wait(s_full, (uint32_t)(i & 1));
+          if (i >= 1 && i - 1 + NST < n_mine) load_item(i - 1 + NST);
+        }
+        mbar_wait(p_full, (uint32_t)(i & 1));
+        if (i >= 2) mbar_wait(o_free + (i & 1), (uint32_t)(((i - 2) >> 1) & 1));  // the epilogue of item i - 2 has read this O
+        tc_fence_after();
+        const uint32_t tOi = tO + (uint32_t)(i & 1) * DP;
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const uint32_t pa = sP + (kk >> 2) * (ATC_BQ * 128) + (kk & 3) * 32;
+          const uint32_t va = sV + kk * 16 * 128;
+          umma_f16_ss(tOi, umma_desc_sw128(pa), umma_desc_mn_sw128(va, Cfg::KV_SLAB), idesc_o, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full + (i & 1));
+        if (NST == 1 && i + 1 < n_mine) {
+          mbar_wait(o_full + (i & 1), (uint32_t)((i >> 1) & 1));  // single stage: V_i is read by P V_i
+          load_item(i + 1);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // -------------------------------------------------------------------------- softmax + epilogue: thread = row
+    const int r = tid;  // 0..127 = TMEM lane
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float sl = p.scale_log2;
+    const int rx = r & 7;
+    if constexpr (PACK) {
+      // zero this row of the P tile once: only the row's own 32-column block is ever written afterwards
+#pragma unroll
+      for (int a = 0; a < KT / 64; ++a)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) st_shared_v4(sP + a * (ATC_BQ * 128) + r * 128 + (c << 4), 0u, 0u, 0u, 0u);
+    }
+    float inv_prev = 0.f;
+    auto epilogue = [&](int i, float inv) {
+      int qt, h, b;
+      decode(i, qt, h, b);
+      mbar_wait(o_full + (i & 1), (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tOi = tO + (uint32_t)(i & 1) * DP + lane_off;
+      int qrow = qt * ATC_BQ + r;
+      __half* dst;
+      if constexpr (PACK) {
+        const int pix = qt * ppt + (r >> p.pack_flog);
+        const int fr = r & ((1 << p.pack_flog) - 1);
+        dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)fr * p.o_seq_stride + pix) * p.ldo + h * D;
+        qrow = (pix < p.pack_hw) ? 0 : p.sq;
+      } else {
+        dst = p.o + ((int64_t)b * p.o_batch_stride + (int64_t)qrow * p.o_seq_stride) * p.ldo + h * D;
+      }
+#pragma unroll
+      for (int c = 0; c < DP; c += 16) {
+        uint32_t ov[16];
+        tmem_ld_32x16(tOi + c, ov);
+        tmem_ld_wait();
+        if (c + 16 >= DP) {  // last chunk is in registers: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free + (i & 1));
+        }
+        if (qrow < p.sq) {
+#pragma unroll
+          for (int k = 0; k < 16; k += 8) {
+            if (c + k < D) {
+              uint4 pk4;
+              pk4.x = pack_half2(__uint_as_float(ov[k]) * inv, __uint_as_float(ov[k + 1]) * inv);
+              pk4.y = pack_half2(__uint_as_float(ov[k + 2]) * inv, __uint_as_float(ov[k + 3]) * inv);
+              pk4.z = pack_half2(__uint_as_float(ov[k + 4]) * inv, __uint_as_float(ov[k + 5]) * inv);
+              pk4.w = pack_half2(__uint_as_float(ov[k + 6]) * inv, __uint_as_float(ov[k + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + c + k) = pk4;
+            }
+          }
+        }
+      }
+    };
+    for (int i = 0; i < n_mine; ++i) {
+      mbar_wait(s_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      float l = 0.f;
+      if constexpr (PACK) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tS + lane_off + 32 * warp, sv);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        float* s = reinterpret_cast<float*>(sv);
+        const int my_blk = r >> p.pack_flog;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (((32 * warp + c) >> p.pack_flog) != my_blk) s[c] = -INFINITY;
+        float mx = s[0];
+#pragma unroll
+        for (int c = 1; c < 32; ++c) mx = fmaxf(mx, s[c]);
+        const float mb = mx * sl;
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float e0 = ex2_approx(fmaf(s[c], sl, -mb));
+          const float e1 = ex2_approx(fmaf(s[c + 1], sl, -mb));
+          l += e0 + e1;
+          pk[c >> 1] = pack_half2(e0, e1);
+        }
+        // 32 keys = 64 bytes = chunks (warp & 1) * 4 .. + 3 of the row in 64-key atom (warp >> 1)
+        const uint32_t p_row = sP + (warp >> 1) * (ATC_BQ * 128) + r * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          st_shared_v4(p_row + ((((warp & 1) * 4 + c) ^ rx) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      } else {
+        uint32_t sv[2][32];
+        tmem_ld_32x32(tS + lane_off, sv[0]);
+        tmem_ld_32x32(tS + lane_off + 32, sv[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        float* s = reinterpret_cast<float*>(&sv[0][0]);
+        if (p.skv < KT) {
+#pragma unroll
+          for (int c = 0; c < KT; ++c)
+            if (c >= p.skv) s[c] = -INFINITY;
+        }
+        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+        for (int c = 4; c < KT; c += 4) {
+          mx0 = fmaxf(mx0, s[c]);
+          mx1 = fmaxf(mx1, s[c + 1]);
+          mx2 = fmaxf(mx2, s[c + 2]);
+          mx3 = fmaxf(mx3, s[c + 3]);
+        }
+        const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl;
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pk[KT / 2];
+#pragma unroll
+        for (int c = 0; c < KT; c += 2) {
+          const float e0 = ex2_approx(fmaf(s[c], sl, -mb));
+          const float e1 = ex2_approx(fmaf(s[c + 1], sl, -mb));
+          sum0 += e0;
+          sum1 += e1;
+          pk[c >> 1] = pack_half2(e0, e1);
+        }
+        l = sum0 + sum1;
+        const uint32_t p_row = sP + r * 128;
+#pragma unroll
+        for (int c = 0; c < KT / 8; ++c)
+          st_shared_v4(p_row + ((c ^ rx) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (i > 0) epilogue(i - 1, inv_prev);
+      inv_prev = 1.f / l;
+    }
+    if (n_mine > 0) epilogue(n_mine - 1, inv_prev);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  }
+}
+
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -864,20 +1181,93 @@ static int launch_attn_tc_any(const LsAttnArgs* a, bool pack, cudaStream_t strea
   return pack ? launch_attn_tc<D, true>(a, stream) : launch_attn_tc<D, false>(a, stream);
 }
 
+template <int D, bool PACK>
+static int launch_attn_one(const LsAttnArgs* a, cudaStream_t stream) {
+  using Cfg = AtoCfg<D, PACK>;
+  PFN_tmapEncodeTiled encode = atc_encode_fn();
+  LS_CHECK(encode != nullptr, "ls_attention: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  AttnOneParams p;
+  memset(&p, 0, sizeof(p));
+  int nb;
+  if constexpr (PACK) {
+    const int F = a->sq, hw = a->q_inner;
+    nb = a->batch / a->q_inner;
+    int flog = 0;
+    while ((1 << flog) < F) ++flog;
+    const int ppt = ATC_BQ / F;
+    if (encode_pack(encode, &p.mapQ, a->q, D, a->heads, F, hw, nb, a->ldq, a->q_seq_stride, a->q_inner_stride,
+                    a->q_outer_stride, ppt, "Q") ||
+        encode_pack(encode, &p.mapK, a->k, D, a->heads, F, hw, nb, a->ldk, a->kv_seq_stride, a->kv_inner_stride,
+                    a->kv_outer_stride, ppt, "K") ||
+        encode_pack(encode, &p.mapV, a->v, D, a->heads, F, hw, nb, a->ldv, a->kv_seq_stride, a->kv_inner_stride,
+                    a->kv_outer_stride, ppt, "V"))
+      return 1;
+    p.pack_flog = flog;
+    p.pack_hw = hw;
+    p.tiles_q = (hw + ppt - 1) / ppt;
+  } else {
+    nb = a->batch;
+    if (encode_bshd(encode, &p.mapQ, a->q, D, a->heads, a->sq, a->batch, a->ldq, a->q_seq_stride, a->q_outer_stride,
+                    ATC_BQ, "Q") ||
+        encode_bshd(encode, &p.mapK, a->k, D, a->heads, a->skv, a->batch, a->ldk, a->kv_seq_stride,
+                    a->kv_outer_stride, Cfg::KT, "K") ||
+        encode_bshd(encode, &p.mapV, a->v, D, a->heads, a->skv, a->batch, a->ldv, a->kv_seq_stride,
+                    a->kv_outer_stride, Cfg::KT, "V"))
+      return 1;
+    p.tiles_q = (a->sq + ATC_BQ - 1) / ATC_BQ;
+  }
+  p.o = reinterpret_cast<__half*>(a->out);
+  p.ldo = a->ldo;
+  p.sq = a->sq;
+  p.skv = a->skv;
+  p.o_batch_stride = a->q_outer_stride;
+  p.o_seq_stride = a->q_seq_stride;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.heads = a->heads;
+  const int64_t n_items = (int64_t)nb * p.tiles_q * a->heads;
+  LS_CHECK(n_items < (1ll << 30), "ls_attention: too many work items");
+  p.n_items = (int)n_items;
+  static bool attr_set_dev[16] = {};
+  bool& attr_set = attr_set_dev[dev_slot()];
+  if (!attr_set) {
+    LS_CUDA(cudaFuncSetAttribute(attn_one_kernel<D, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  int sms = 0;
+  LS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_slot()));
+  const int64_t slots = (int64_t)(sms > 0 ? sms : 148) * Cfg::CTAS_PER_SM;
+  const int grid = (int)(n_items < slots ? n_items : slots);
+  LS_CUDA(launch_k(attn_one_kernel<D, PACK>, dim3(grid), dim3(ATC_THREADS), (size_t)Cfg::SMEM, stream, p));
+  LS_CUDA(cudaGetLastError());
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+template <int D>
+static int launch_attn_one_any(const LsAttnArgs* a, bool pack, cudaStream_t stream) {
+  return pack ? launch_attn_one<D, true>(a, stream) : launch_attn_one<D, false>(a, stream);
+}
+
 // returns -1 when the problem is not one for this path (the caller then uses the warp-level kernels)
 int attention_tc_try(const LsAttnArgs* a, cudaStream_t stream) {
   if (!atc_enabled()) return -1;
-  // Which problems take this kernel.  Measured (profiles/r2d_attention_all_tcgen05.txt): the flash kernel is built for
-  // long key sequences - one CTA per (query tile, head) pays ~8-10 k clocks of setup and hand-shake latency - so on
-  // one- or two-tile problems it LOSES to the warp-level kernels: packed temporal 40.4 vs 23.8 us (level 0), 4x4 level
-  // 14.7 vs 8.5 us, 8x8 self 14.8 vs 12.6 us, audio cross-attention 21.2 vs 20.8 us.  Default: >= 128 queries and >= 2
-  // full key tiles.  LS_ATTN_TC_ALL=1 routes everything it can take (tests run both).
-  static int all = -1;
+  // Routing.  Long key sequences (>= 2 key tiles: the 32x32 / 16x16 spatial self-attention) take the flash kernel.  The
+  // problems whose keys fit one tile - audio cross-attention, 8x8 / 4x4 levels, temporal attention - have two tcgen05
+  // implementations here (LS_ATTN_ONE=1: the persistent one-tile kernel; LS_ATTN_TC_ALL=1: the flash kernel, packed
+  // temporal mode), both parity-green and both SLOWER than the warp-level kernels of attention.cu, which stay the
+  // default: level-0 temporal attention 24.7 us (mma.sync) vs 36-41 us (either tcgen05 kernel), 4x4 level 8.5 vs 12.9 us,
+  // audio cross-attention 20.8 vs 21.0 us (profiles/r2d_attention_all_tcgen05.txt, r2g_attention_one_tile.txt).  ncu on
+  // the one-tile kernel (profiles/r2g_attn_one_ncu_summary.txt): tensor pipe 10 % active, the softmax warps wait for S a
+  // third of the time, 1 600 L2 requests per (8 pixels x 1 head) item - these problems are bound by gathering 80-byte
+  // rows (q, k, v of one head out of a 1 920-byte token row), which a TMA box does no better than cp.async, and their
+  // 12 GFLOP are noise for any tensor path.
+  static int all = -1, one = -1;
   if (all < 0) {
     const char* e = getenv("LS_ATTN_TC_ALL");
     all = (e && e[0] == '1') ? 1 : 0;
+    const char* o = getenv("LS_ATTN_ONE");
+    one = (o && o[0] == '1') ? 1 : 0;
   }
-  if (!all && (a->q_inner != 1 || a->kv_inner != 1 || a->sq < ATC_BQ || a->skv < 2 * ATC_BKV)) return -1;
   bool pack = false;
   if (a->q_inner != 1 || a->kv_inner != 1) {
     // strided batches = temporal attention: packed mode needs self-attention geometry (same addressing for q and k/v),
@@ -898,6 +1288,20 @@ int attention_tc_try(const LsAttnArgs* a, cudaStream_t stream) {
        reinterpret_cast<uintptr_t>(a->out)) & 15)
     return -1;
   if (a->head_dim % 8) return -1;  // 16-byte rows per head for TMA and the vector stores
+  const bool long_keys = !pack && a->sq >= ATC_BQ && a->skv >= 2 * ATC_BKV;
+  const bool one_tile = pack ? (a->sq <= 32) : (a->skv <= ATC_BKV);
+  if (!long_keys && !all) {
+    if (!one || !one_tile) return -1;
+    switch (a->head_dim) {
+      case 16: return launch_attn_one_any<16>(a, pack, stream);
+      case 32: return launch_attn_one_any<32>(a, pack, stream);
+      case 40: return launch_attn_one_any<40>(a, pack, stream);
+      case 64: return launch_attn_one_any<64>(a, pack, stream);
+      case 80: return launch_attn_one_any<80>(a, pack, stream);
+      case 160: return launch_attn_one_any<160>(a, pack, stream);
+      default: return -1;
+    }
+  }
   switch (a->head_dim) {
     case 16: return launch_attn_tc_any<16>(a, pack, stream);
     case 32: return launch_attn_tc_any<32>(a, pack, stream);

@@ -42,6 +42,9 @@ extern std::atomic<int64_t> g_launch_count;
 // k-block and wraps each UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY waterfall loop (~75 / ~95 dependent
 // instructions per k-block).  With the WHOLE loop under one `elect.sync` predicate it knows, and emits the uniform
 // instructions back to back (~45 per k-block).  -DLS_GEMM_LANE0 keeps the old form for A/B runs.
+#ifndef LS_GEMM_DEFAULT_KBS
+#define LS_GEMM_DEFAULT_KBS 1
+#endif
 #ifdef LS_GEMM_LANE0
 #define LS_ONE_LANE() (lane == 0)
 #else
@@ -106,6 +109,8 @@ struct GemmKParams {
   int BN;  // tile width (multiple of 32, <= 256)
   int b_batched;
   int stages;
+  int kbs;  // 64-wide k-blocks per pipeline stage (1 or 2)
+  int slab_single;  // 1: every 32-column slab is staged and stored on its own (2 KB per warp: 16 KB of staging instead of 32)
   const float* bias;
   int bias_div;
   int bias_ld;
@@ -282,6 +287,74 @@ __device__ __forceinline__ uint32_t produce_kblock(uint32_t sa, uint32_t sb, con
   return ready;
 }
 
+// ---- two k-blocks per pipeline stage (p.kbs == 2): the pieces of produce_kblock / mma_kblock as separate calls.
+// One mbarrier round trip (probe + arm + commit) per stage costs each single-lane loop ~370 clocks whatever it issues
+// (profiles/r2_gemm_ablate_elect.txt, "nothing": the latency of two dependent mbarrier operations, not instruction
+// count); with 128 K columns per stage that cost is paid once per two swizzle atoms.
+__device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
+  uint32_t ready;
+  asm volatile(
+      "{\n.reg .pred P;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P;\n}"
+      : "=r"(ready) : "r"(bar), "r"(parity) : "memory");
+  return ready;
+}
+template <int CTAS>
+__device__ __forceinline__ void tma_a_4d(uint32_t dst, const CUtensorMap* map, uint32_t full_bar, int c0, int c1, int c2,
+                                         int c3) {
+  if constexpr (CTAS == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(full_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(full_bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void tma_b_3d(uint32_t dst, const CUtensorMap* map, uint32_t full_bar, int c0, int c1, int c2) {
+  if constexpr (CTAS == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(full_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(full_bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// the four K = 16 MMAs of one 64-wide k-block (no probe, no commit)
+template <int CTAS>
+__device__ __forceinline__ void mma_quad(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if constexpr (CTAS == 1)
+    asm volatile(
+        "{\n.reg .pred ACC, T;\n.reg .b64 a1, a2, a3, b1, b2, b3;\n"
+        "setp.ne.b32 ACC, %4, 0;\n setp.eq.b32 T, %3, %3;\n"
+        "add.s64 a1, %1, 2;\n add.s64 b1, %2, 2;\n add.s64 a2, %1, 4;\n add.s64 b2, %2, 4;\n"
+        "add.s64 a3, %1, 6;\n add.s64 b3, %2, 6;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, ACC;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, T;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, T;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, T;\n}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred ACC, T;\n.reg .b64 a1, a2, a3, b1, b2, b3;\n"
+        "setp.ne.b32 ACC, %4, 0;\n setp.eq.b32 T, %3, %3;\n"
+        "add.s64 a1, %1, 2;\n add.s64 b1, %2, 2;\n add.s64 a2, %1, 4;\n add.s64 b2, %2, 4;\n"
+        "add.s64 a3, %1, 6;\n add.s64 b3, %2, 6;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, ACC;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, T;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, T;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, T;\n}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 __device__ __forceinline__ void decode_m_tile(const GemmKParams& p, int mt, int& x0, int& y0, int& i0) {
   const int rest = (int)fdiv((uint32_t)mt, p.fd_tiles_x);
   const int tx = mt - rest * p.tiles_x;
@@ -382,15 +455,17 @@ template <int CTAS, bool GEGLU>
 __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   const int BN = p.BN;
   const int b_rows = BN / CTAS;  // B rows staged by each CTA
-  const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
+  const int kblock_bytes = A_STAGE_BYTES + b_rows * 128;  // one 64-wide k-block: A atom + B atom
+  const int stage_bytes = p.kbs * kblock_bytes;           // kbs == 2: [A0][A1][B0][B1]
   // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
   const uint32_t idesc = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t((BM * CTAS) >> 4) << 24);
 
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const int stages = p.stages;
   uint8_t* staging = smem + stages * stage_bytes;  // 1024-byte aligned (stage_bytes % 1024 == 0)
-  float* bias_sm = reinterpret_cast<float*>(staging + STAGING_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + BIAS_BYTES);
+  const int staging_bytes = p.slab_single ? STAGING_BYTES / 2 : STAGING_BYTES;
+  float* bias_sm = reinterpret_cast<float*>(staging + staging_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + staging_bytes + BIAS_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -466,6 +541,40 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         int tap = rem / p.seg_cblk[s];
         int cb = rem - tap * p.seg_cblk[s];
         int kcol = kb0 * BK;
+        if (p.kbs == 2) {
+          // two k-blocks per stage: one probe, one arm, up to four loads
+          for (int kb = kb0; kb < kb1; kb += 2) {
+            const int n_here = min(2, kb1 - kb);
+            if (!ready) mbar_wait(&empty_bar[stage], phase ^ 1u);
+            const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
+            const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint32_t fb = full0 + stage * 8;
+            ready = mbar_probe(empty0 + nstage * 8, nphase ^ 1u);
+            if (leader) mbar_expect_tx_u32(fb, (uint32_t)(n_here * kblock_bytes * CTAS));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (u < n_here) {
+                const int taps = p.seg_taps[s];
+                const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+                const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+                tma_a_4d<CTAS>(sa + u * A_STAGE_BYTES, &p.mapA[s], fb, cb * BK, x0 + dx, y0 + dy, i0);
+                tma_b_3d<CTAS>(sa + 2 * A_STAGE_BYTES + u * b_rows * 128, &p.mapB, fb, kcol, brow, bz);
+                kcol += BK;
+                if (++cb == p.seg_cblk[s]) {
+                  cb = 0;
+                  if (++tap == taps) {
+                    tap = 0;
+                    ++s;
+                  }
+                }
+              }
+            }
+            stage = nstage;
+            phase = nphase;
+          }
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int taps = p.seg_taps[s];
           const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
@@ -551,6 +660,27 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
 #endif
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        if (p.kbs == 2) {
+          for (int kb = kb0; kb < kb1; kb += 2) {
+            const int n_here = min(2, kb1 - kb);
+            if (!ready) mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
+            const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            ready = mbar_probe(full0 + nstage * 8, nphase);
+            mma_quad<CTAS>(d_tmem, umma_desc_sw128(sa), umma_desc_sw128(sa + 2 * A_STAGE_BYTES), idesc,
+                           kb != kb0 ? 1u : 0u);
+            if (n_here == 2)
+              mma_quad<CTAS>(d_tmem, umma_desc_sw128(sa + A_STAGE_BYTES),
+                             umma_desc_sw128(sa + 2 * A_STAGE_BYTES + b_rows * 128), idesc, 1u);
+            umma_commit_g<CTAS>(&empty_bar[stage]);
+            stage = nstage;
+            phase = nphase;
+          }
+          umma_commit_g<CTAS>(&tmem_full[acc]);
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
 #ifdef LS_GEMM_PROBE
           const long long mc0 = clock64();
@@ -601,7 +731,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       // Every warp stages and stores its own 32 rows of a slab (two 2 KB buffers, ping-pong): no block barrier and no
       // wait for the PREVIOUS store per slab.  (With one store per 128-row slab issued behind a 128-thread barrier
       // and a wait on the preceding store, each slab cost ~1500 clocks of latency: a K = 64 GEMM took as long as K = 320.)
-      uint8_t* my_stage = staging + warp * 2 * WSLAB_BYTES;  // 32 rows x 128 bytes
+      uint8_t* my_stage = staging + warp * (p.slab_single ? WSLAB_BYTES : 2 * WSLAB_BYTES);  // 32 rows x 128 (64) bytes
       constexpr int NSLAB_MAX = 4;  // split-K parking: slabs per group at BN = 256
       const int nslab = geglu ? BN / 64 : BN / 32;
       const int n_out_total = geglu ? p.N / 2 : p.N;
@@ -870,7 +1000,9 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           // stage address of this thread's row: pair = 128-byte rows, chunk c at c ^ (lane & 7) (SWIZZLE_128B);
           // trailing single slab = 64-byte rows, chunk c at c ^ ((lane >> 1) & 3) (SWIZZLE_64B)
           const int half_sel = hs;
-          const bool single = (half_sel == 0) && (s == n_mine - 1);
+          // slab_single launches (main-loop-bound, no residual: the 16 KB of staging saved buy one more pipeline stage)
+          // stage and store EVERY slab on its own, like the trailing slab of an odd count
+          const bool single = p.slab_single || ((half_sel == 0) && (s == n_mine - 1));
           if (has_res && hs == 0) {
             // the previous store has finished reading the buffer -> park this pair's residual chunks, request the next pair's
             const bool single_p = single;
@@ -912,7 +1044,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           }
           // stage.  Pair: row `lane` of the warp's buffer is 128 bytes, 16-byte chunk c sits at c ^ (lane & 7)
           // (SWIZZLE_128B).  Trailing single slab: 64-byte rows, chunk c at c ^ ((lane >> 1) & 3) (SWIZZLE_64B).
-          if (half_sel == 0 && !has_res) {  // the previous store has finished reading the buffer
+          if ((half_sel == 0 || p.slab_single) && !has_res) {  // the previous store has finished reading the buffer
             if (lane == 0) bulk_wait_group_read<0>();
             __syncwarp();
           }
@@ -933,7 +1065,8 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && m0 + q * 32 < p.M) {
-              tma_store_2d(single ? &p.mapOut32 : &p.mapOut, my_stage, ncol0 - half_sel * 32, (int)(m0 + q * 32));
+              tma_store_2d(single ? &p.mapOut32 : &p.mapOut, my_stage, single ? ncol0 : ncol0 - half_sel * 32,
+                           (int)(m0 + q * 32));
               bulk_commit_group();
             }
           }
@@ -1323,9 +1456,39 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.ldo = a->ldo;
   p.flags = a->flags;
 
-  const int stage_bytes = A_STAGE_BYTES + (BN / CTAS) * 128;
-  const int fixed = STAGING_BYTES + BIAS_BYTES + 192;  // + 20 mbarriers and the TMEM slot
+  static int env_kbs = -1;
+  if (env_kbs < 0) {
+    // 1 / 2 forces the k-blocks per pipeline stage.  Default 1: two per stage are 3-12 % SLOWER on every UNet / VAE shape
+    // (profiles/r2e_gemm_kbs.txt) - the coarser refill granularity costs more than the halved hand-shake saves.
+    const char* e = getenv("LS_GEMM_KBS");
+    env_kbs = e ? atoi(e) : 0;
+  }
+  // two k-blocks per stage halve the per-stage mbarrier hand-shake; they need at least two stages' worth of work
+  p.kbs = (env_kbs == 1 || env_kbs == 2) ? env_kbs : LS_GEMM_DEFAULT_KBS;
+  if (p.kb_per < 4) p.kbs = 1;
+  const int stage_bytes = p.kbs * (A_STAGE_BYTES + (BN / CTAS) * 128);
+  int fixed = STAGING_BYTES + BIAS_BYTES + 192;  // + 20 mbarriers and the TMEM slot
   int stages = (SMEM_BUDGET - fixed) / stage_bytes;
+  // Experiment kept behind LS_GEMM_SLAB_SINGLE: if main-loop-bound launches were bound by the operand bytes in flight,
+  // halving the staging area (slabs stored one by one from 2 KB per warp) to buy one more stage would pay.  It does not.
+  static int env_ss = -1;
+  if (env_ss < 0) {
+    // 1 forces it where legal, 2 = where it buys a stage.  Default OFF: measured neutral (profiles/r2f_gemm_slab_single.txt:
+    // 7 -> 8 stages at 256 x 160 changes the 3x3 convolutions by < 1 %), i.e. the main loop is not bound by bytes in flight.
+    const char* e = getenv("LS_GEMM_SLAB_SINGLE");
+    env_ss = e ? atoi(e) : 0;
+  }
+  {
+    const int fixed_s = STAGING_BYTES / 2 + BIAS_BYTES + 192;
+    const int stages_s = (SMEM_BUDGET - fixed_s) / stage_bytes;
+    const bool legal = p.tma_store && a->residual == nullptr && p.splits == 1 && !geglu;
+    const bool want = env_ss == 1 || (env_ss == 2 && p.kb_per >= 24 && stages_s > stages && stages < MAX_STAGES);
+    if (legal && want) {
+      p.slab_single = 1;
+      fixed = fixed_s;
+      stages = stages_s;
+    }
+  }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;

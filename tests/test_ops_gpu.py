@@ -313,13 +313,17 @@ def test_attention_packed_qkv(d, S):
     assert rel_l2(out, ref) < 3e-3
 
 
-@pytest.mark.parametrize("d,HW", [(40, 64), (80, 16), (160, 4)])
-def test_attention_temporal(d, HW):
+@pytest.mark.parametrize("d,HW,Fr", [(40, 64, 16), (80, 16, 16), (160, 4, 16), (40, 1024, 16), (40, 36, 8), (32, 10, 4),
+                                     (80, 20, 32), (40, 8, 24)])
+def test_attention_temporal(d, HW, Fr):
     """VersatileAttention (motion_module.py:262-313): sequences run over the 16 frames at each pixel, addressed by
-    stride inside the (b f) x HW token matrix; q, k, v come packed as one [rows, 3C] matrix."""
+    stride inside the (b f) x HW token matrix; q, k, v come packed as one [rows, 3C] matrix.  With LS_ATTN_ONE=1 /
+    LS_ATTN_TC_ALL=1 (see test_attention_every_shape_on_the_other_kernels) power-of-two frame counts <= 32 take the packed
+    tcgen05 kernels (128 / F pixels per tile, incl. tiles that run past the image: HW = 4, 10, 20, 36); 24 frames always
+    stay on the warp-level kernel."""
     L = _ops()
     g = torch.Generator(device="cpu").manual_seed(13)
-    B, Fr, heads = 2, 16, 8
+    B, heads = 2, 8
     C = heads * d
     rows = B * Fr * HW
     qkv = torch.randn(rows, 3 * C, generator=g).half().to(DEV)
@@ -407,14 +411,18 @@ def test_layout_and_time_embedding():
     assert rel_l2(yv, want) < 1e-5
 
 
-def test_attention_every_shape_on_the_tcgen05_kernel():
-    """LS_ATTN_TC_ALL=1 routes the audio cross-attention (50 keys), the 8x8 / 4x4 levels and the temporal attention
-    (packed: 128-row tiles of 128 / F pixels x F frames, block-diagonal mask) to the tcgen05 flash kernel instead of the
-    warp-level kernels.  The switch is read once per process, so the attention tests re-run in a child process."""
+@pytest.mark.parametrize("switch", ["LS_ATTN_TC_ALL=1", "LS_ATTN_ONE=1"])
+def test_attention_every_shape_on_the_other_kernels(switch):
+    """The one-key-tile problems (audio cross-attention, 8x8 / 4x4 levels, temporal attention) run on the warp-level
+    kernels of attention.cu by default (they are faster there).  LS_ATTN_ONE=1 routes them to the persistent one-tile
+    tcgen05 kernel, LS_ATTN_TC_ALL=1 to the tcgen05 flash kernel (packed temporal mode: block-diagonal mask over two key
+    tiles): both stay correct.
+    The switches are read once per process, so the attention tests re-run in a child process."""
     import subprocess
     import sys
 
-    env = dict(os.environ, LS_ATTN_TC_ALL="1")
+    name, val = switch.split("=")
+    env = dict(os.environ, **{name: val})
     res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k",
                           "attention and not every_shape", "--no-header", "-p", "no:cacheprovider"],
                          env=env, capture_output=True, text=True, timeout=600)
