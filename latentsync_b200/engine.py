@@ -97,6 +97,10 @@ class Plan:
         self.descs: List[str] = []
         self.op_flops: List[float] = []  # algorithmic FLOPs of each launch (2*M*N*K for GEMM/conv, 4*B*h*Sq*Sk*d for SDPA)
         self.op_bytes: List[float] = []  # algorithmic bytes of each GEMM launch: A once + W once + out (+ residual) once
+        # indices of launches that do NOT depend on the loop state and are therefore kept out of the captured graph
+        # (UNet: the time-embedding path = a function of t only, the audio K/V projection = a function of the audio only);
+        # `run()` still runs everything in order, `replay()` runs the graph without them, `run_hoisted()` runs them alone
+        self.hoisted: set = set()
 
     # ---- buffers
     def buf(self, rows, cols, dtype=torch.float16) -> Buf:
@@ -108,9 +112,16 @@ class Plan:
         return b
 
     # ---- execution
-    def run(self) -> None:
-        for fn in self.ops:
-            fn()
+    def run(self, hoisted: bool = True) -> None:
+        for i, fn in enumerate(self.ops):
+            if hoisted or i not in self.hoisted:
+                fn()
+
+    def run_hoisted(self, which=None) -> None:
+        """the launches kept out of the graph (all of them, or the given index range), eagerly on the current stream"""
+        for i in sorted(self.hoisted):
+            if which is None or which[0] <= i < which[1]:
+                self.ops[i]()
 
     def run_timed(self) -> Dict[str, Tuple[int, float]]:
         """eager run with a CUDA event pair around every launch: kind -> (launches, total ms).  Diagnostic only."""
@@ -152,7 +163,7 @@ class Plan:
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.run()
+            self.run(hoisted=False)
         self.graph = g
 
     def time_kind_in_graph(self, kind: Optional[str], reps: int = 5, exclude: Optional[str] = None) -> float:
@@ -160,7 +171,8 @@ class Plan:
         and timed with CUDA events: kernel time without the host launch gap that the per-launch event pairs of
         `run_timed` include (~3 us x launches).  Buffers keep whatever the last full run left in them (timing of these
         kernels does not depend on the values).  `kind=None, exclude="gemm"`: every launch EXCEPT that kind."""
-        fns = [fn for fn, k in zip(self.ops, self.kinds) if (kind is None or k == kind) and k != exclude]
+        fns = [fn for i, (fn, k) in enumerate(zip(self.ops, self.kinds))
+               if (kind is None or k == kind) and k != exclude and i not in self.hoisted]
         if not fns:
             return 0.0
         s = torch.cuda.Stream(device=self.device)
@@ -185,8 +197,9 @@ class Plan:
         return a.elapsed_time(b) / reps
 
     def replay(self) -> None:
+        """the graph (or, before capture, the same launches eagerly): everything except the hoisted launches"""
         if self.graph is None:
-            self.run()
+            self.run(hoisted=False)
         else:
             self.graph.replay()
 
@@ -199,11 +212,16 @@ class Plan:
         self.descs.append(desc)
         self.launches += 1
 
-    def flops(self, kind: Optional[str] = None) -> float:
-        return sum(f for k, f in zip(self.kinds, self.op_flops) if kind is None or k == kind)
+    def flops(self, kind: Optional[str] = None, in_graph_only: bool = False) -> float:
+        return sum(f for i, (k, f) in enumerate(zip(self.kinds, self.op_flops))
+                   if (kind is None or k == kind) and not (in_graph_only and i in self.hoisted))
 
-    def bytes(self, kind: Optional[str] = None) -> float:
-        return sum(b for k, b in zip(self.kinds, self.op_bytes) if kind is None or k == kind)
+    def bytes(self, kind: Optional[str] = None, in_graph_only: bool = False) -> float:
+        return sum(b for i, (k, b) in enumerate(zip(self.kinds, self.op_bytes))
+                   if (kind is None or k == kind) and not (in_graph_only and i in self.hoisted))
+
+    def count(self, kind: str, in_graph_only: bool = False) -> int:
+        return sum(1 for i, k in enumerate(self.kinds) if k == kind and not (in_graph_only and i in self.hoisted))
 
     def gemm(self, segs: Sequence[Tuple[int, int, int, int]], nimg: int, H: int, W: int, w: torch.Tensor, N: int,
              out_ptr: int, ldo: int, bias_ptr: int = 0, bias_div: int = 0, bias_ld: int = 0, residual_ptr: int = 0,
@@ -427,6 +445,31 @@ class UNetEngine:
             kcat = torch.cat(kw)
             w.put("kv.w", pack_1x1(kcat))
         self.cross_k = (c["cross_attention_dim"] + KPAD - 1) // KPAD * KPAD
+
+    def time_table(self, timesteps) -> torch.Tensor:
+        """[len(timesteps), tproj_total] fp32: for every timestep of a denoising loop, each ResnetBlock3D's
+        time_emb_proj(SiLU(time_embedding(t))) + conv1.bias (unet.py:376-382, resnet.py:190-205) - the same four launches
+        the plan makes for one t, batched over the loop's timesteps (they depend on t only, lipsync_pipeline.py:537-554)."""
+        lib, w, c = L.lib(), self.w, self.cfg
+        boc = c["block_out_channels"]
+        T = len(timesteps)
+        t = torch.tensor([float(v) for v in timesteps], dtype=torch.float32, device=self.device)
+        te0 = torch.empty(T, boc[0], dtype=torch.float32, device=self.device)
+        te1 = torch.empty(T, boc[0] * 4, dtype=torch.float32, device=self.device)
+        emb = torch.empty_like(te1)
+        table = torch.empty(T, self.tproj_total, dtype=torch.float32, device=self.device)
+        st = _stream()
+        _chk(lib.ls_timestep_embedding(t.data_ptr(), T, boc[0], te0.data_ptr(), st), "ls_timestep_embedding")
+        _chk(lib.ls_small_linear(te0.data_ptr(), T, boc[0], w.t["te1.w"].data_ptr(),
+                                 w.f32("time_embedding.linear_1.bias").data_ptr(), None, boc[0] * 4, 0, 1,
+                                 te1.data_ptr(), st), "ls_small_linear")
+        _chk(lib.ls_small_linear(te1.data_ptr(), T, boc[0] * 4, w.t["te2.w"].data_ptr(),
+                                 w.f32("time_embedding.linear_2.bias").data_ptr(), None, boc[0] * 4, 0, 0,
+                                 emb.data_ptr(), st), "ls_small_linear")
+        _chk(lib.ls_small_linear(emb.data_ptr(), T, boc[0] * 4, w.t["tproj.w"].data_ptr(), w.t["tproj.b"].data_ptr(),
+                                 w.t["tproj.add"].data_ptr(), self.tproj_total, 1, 0, table.data_ptr(), st),
+             "ls_small_linear")
+        return table
 
     # ---- packed-weight accessors used by the plan builder
     def qkv(self, p: str) -> torch.Tensor:
@@ -736,6 +779,7 @@ class UNetPlan(Plan):
         emb = self.static(B, boc[0] * 4, torch.float32)
         self.tproj = self.static(B, eng.tproj_total, torch.float32)
         assert c["flip_sin_to_cos"] and c["freq_shift"] == 0
+        n_te = len(self.ops)
         self.call("ls_timestep_embedding", self.t_in.ptr, B, boc[0], te0.ptr)
         self.call("ls_small_linear", te0.ptr, B, boc[0], w.t["te1.w"].data_ptr(),
                   w.f32("time_embedding.linear_1.bias").data_ptr(), None, boc[0] * 4, 0, 1, te1.ptr)
@@ -743,6 +787,7 @@ class UNetPlan(Plan):
                   w.f32("time_embedding.linear_2.bias").data_ptr(), None, boc[0] * 4, 0, 0, emb.ptr)
         self.call("ls_small_linear", emb.ptr, B, boc[0] * 4, w.t["tproj.w"].data_ptr(), w.t["tproj.b"].data_ptr(),
                   w.t["tproj.add"].data_ptr(), eng.tproj_total, 1, 0, self.tproj.ptr)
+        self.te_ops = (n_te, len(self.ops))
 
         # audio K/V for all 16 cross-attention layers: one GEMM (depends only on the audio => the pipeline runs
         # this sub-plan once per segment, see UNetPlan.kv_ops)
@@ -753,6 +798,9 @@ class UNetPlan(Plan):
             self.gemm([(self.audio_in.ptr, eng.cross_k, eng.cross_k, 1)], 1, 1, B * F * self.S, w.t["kv.w"],
                       eng.kv_total, self.audio_kv.ptr, eng.kv_total)
         self.kv_ops = (n_before, len(self.ops))
+        # neither depends on the latents: the denoising loop computes the time path for ALL its timesteps in one batched
+        # pass (UNetEngine.time_table) and the audio K/V once per segment; UNet3DConditionModel.forward runs both per call
+        self.hoisted = set(range(*self.te_ops)) | set(range(*self.kv_ops))
 
         # conv_in (unet.py:395)
         x = self.buf(rows0, boc[0])

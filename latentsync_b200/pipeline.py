@@ -183,6 +183,13 @@ class LipsyncPipeline:
         lib = L.lib()
         eps_dbg = torch.empty_like(lat) if trace is not None else None
         t_view = plan.t_in.tensor().view(-1)
+        # what does not depend on the latents runs ONCE per segment instead of once per step: the audio K/V projection of
+        # all 16 cross-attention layers (a function of the audio embeddings) and the time-embedding path of all timesteps
+        # (a function of t: one batched pass, row j = step j)
+        if S:
+            plan.run_hoisted(plan.kv_ops)
+        ttab = unet.engine().time_table(timesteps)
+        tproj = plan.tproj.tensor()
         for j, t in enumerate(timesteps):
             if teacher_latents is not None:
                 lat.copy_(teacher_latents[j].to(dev, torch.float32))
@@ -191,6 +198,7 @@ class LipsyncPipeline:
             L._check(lib.ls_concat13(lat.data_ptr(), mask.data_ptr(), masked.data_ptr(), ref.data_ptr(), nb, F, h * w,
                                      plan.x_in.ptr, st), "ls_concat13")
             t_view.fill_(float(t))
+            tproj.copy_(ttab[j].expand_as(tproj))
             plan.replay()  # noise_pred (:552-554)
             a_t, a_p = sch.step_coefficients(t)
             # CFG combine (:557-559) + DDIM step (:562) in one pass, latents updated in place
@@ -307,13 +315,18 @@ class LipsyncPipeline:
         t_view = plan.t_in.tensor().view(-1)
         x_stride = rows_seg * plan.x_in.cols * 2  # bytes per segment in the fp16 UNet input
         e_stride = rows_seg * plan.eps_out.cols * 4
-        for t in sch._host_timesteps:
+        if S:
+            plan.run_hoisted(plan.kv_ops)
+        ttab = unet.engine().time_table(sch._host_timesteps)
+        tproj = plan.tproj.tensor()
+        for j, t in enumerate(sch._host_timesteps):
             st = torch.cuda.current_stream().cuda_stream
             for i in range(n):
                 L._check(lib.ls_concat13(lats[i].data_ptr(), masks[i].data_ptr(), maskeds[i].data_ptr(),
                                          refs[i].data_ptr(), nb, F, h * w, plan.x_in.ptr + i * x_stride, st),
                          "ls_concat13")
             t_view.fill_(float(t))
+            tproj.copy_(ttab[j].expand_as(tproj))
             plan.replay()
             a_t, a_p = sch.step_coefficients(t)
             for i in range(n):

@@ -227,6 +227,7 @@ class UNet3DConditionModel(nn.Module):
                  "ls_ncfhw_to_cl")
         if S:
             plan.audio_in.tensor()[:, : ehs.shape[-1]].copy_(ehs.reshape(B * F * S, -1))
+        plan.run_hoisted()  # time-embedding path + audio K/V projection: not part of the graph (see engine.Plan.hoisted)
         plan.replay()
         out = torch.empty(B, self.config.out_channels, F, H, W, dtype=torch.float32, device=dev)
         L._check(lib.ls_cl_to_ncfhw(plan.eps_out.ptr, plan.eps_out.cols, B, self.config.out_channels, F, H * W,

@@ -325,6 +325,7 @@ def test_null_audio_shortcut_is_bitwise_identical(name, hw):
         plan.x_in.tensor().copy_(x)
         plan.audio_in.tensor().copy_(a)
         plan.t_in.tensor().fill_(501.0)
+        plan.run_hoisted()
         plan.replay()
         torch.cuda.synchronize()
         outs.append(plan.eps_out.tensor().clone())
@@ -369,6 +370,7 @@ def test_shared_prefix_plan_matches_full_plan(name, hw):
         plan.x_in.tensor().copy_(x)
         plan.audio_in.tensor().copy_(a)
         plan.t_in.tensor().fill_(301.0)
+        plan.run_hoisted()
         plan.replay()
         torch.cuda.synchronize()
         outs.append(plan.eps_out.tensor().clone())

@@ -16,6 +16,7 @@ plan.x_in.tensor().normal_()
 plan.audio_in.tensor().normal_()
 plan.t_in.tensor().fill_(501.0)
 plan.capture()
+plan.run_hoisted()  # time path + audio K/V: outside the graph
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 plan.replay()

@@ -21,7 +21,9 @@ torch.cuda.set_device(0)
 if which == "unet":
     eng = UNetEngine({k: v.cuda() for k, v in syn.unet_state_dict(cfg, 0).items()}, cfg, "cuda")
     hw = 16 if "tiny" in sys.argv else 32
-    plan = eng.plan(2, 16, hw, hw, 50)
+    # "short": the plan the pipeline (and bench.py) runs - null-audio shortcut + shared CFG prefix; default: the full plan
+    short = "short" in sys.argv
+    plan = eng.plan(2, 16, hw, hw, 50, uncond_zero=short, same_sample=short)
     plan.x_in.tensor().normal_()
     plan.audio_in.tensor().normal_()
     plan.t_in.tensor().fill_(951.0)
