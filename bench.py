@@ -229,6 +229,8 @@ def gpu_eager_baseline(dev, ddim: int = DDIM_STEPS, g: float = GUIDANCE):
             torch.cuda.synchronize(dev)
             ts.append(e0.elapsed_time(e1))
         fwd_ms = sorted(ts)[1]
+        P.decode_and_paste(vsd, seg["latents"], seg)  # warm-up of the decoder's cuDNN algorithm choices (untimed)
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         lat = P.denoise_segment(fn, seg, steps=ddim, guidance=g)
