@@ -42,6 +42,9 @@ extern std::atomic<int64_t> g_launch_count;
 // k-block and wraps each UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY waterfall loop (~75 / ~95 dependent
 // instructions per k-block).  With the WHOLE loop under one `elect.sync` predicate it knows, and emits the uniform
 // instructions back to back (~45 per k-block).  -DLS_GEMM_LANE0 keeps the old form for A/B runs.
+#ifndef LS_GEMM_DEFAULT_BRES
+#define LS_GEMM_DEFAULT_BRES 0
+#endif
 #ifndef LS_GEMM_DEFAULT_KBS
 #define LS_GEMM_DEFAULT_KBS 1
 #endif
@@ -110,6 +113,7 @@ struct GemmKParams {
   int b_batched;
   int stages;
   int kbs;  // 64-wide k-blocks per pipeline stage (1 or 2)
+  int bres;  // 1: the CTA's B tile (all k-blocks) stays resident in shared memory across its M tiles; stages hold A only
   int slab_single;  // 1: every 32-column slab is staged and stored on its own (2 KB per warp: 16 KB of staging instead of 32)
   const float* bias;
   int bias_div;
@@ -462,7 +466,10 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
 
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const int stages = p.stages;
-  uint8_t* staging = smem + stages * stage_bytes;  // 1024-byte aligned (stage_bytes % 1024 == 0)
+  // weight-resident mode: [B: num_kb x (b_rows x 128 B)] [A ring: stages x 16 KB] [staging] ...; otherwise [ring of A+B stages]
+  const int bres_bytes = p.bres ? p.num_kb * b_rows * 128 : 0;
+  const int ring_stage_bytes = p.bres ? A_STAGE_BYTES : stage_bytes;
+  uint8_t* staging = smem + bres_bytes + stages * ring_stage_bytes;  // 1024-byte aligned
   const int staging_bytes = p.slab_single ? STAGING_BYTES / 2 : STAGING_BYTES;
   float* bias_sm = reinterpret_cast<float*>(staging + staging_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + staging_bytes + BIAS_BYTES);
@@ -470,6 +477,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* b_full = tmem_empty + 3;  // weight-resident mode: the B tile has landed (8 bytes after the TMEM slot)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -492,6 +500,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(b_full, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       // one arrival per epilogue warp that reads the accumulator: all 8 (split-K, legacy path) or the 4 of the group
@@ -520,6 +529,45 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       long long pr_wait = 0, pr_miss = 0;
       const long long pr_t0 = clock64();
 #endif
+      if (p.bres) {
+        // Weight-resident mode (host: single CTA, no split-K, grid % n_tiles == 0 so that every tile of this CTA has the same
+        // n-tile, single un-batched B): the B tile is loaded ONCE, the ring carries A k-blocks only.  A K = 320 linear
+        // otherwise re-ingests the same 100 KB of weights for each of its M tiles - more than the 80 KB of A - and its
+        // main loop runs at 840 clk per k-block instead of 583 (profiles/r2l_gemm_epilogue_experiments.txt (8)).
+        const int nt0 = unit % p.n_tiles;
+        const uint32_t bfull = smem_u32(b_full);
+        mbar_expect_tx_u32(bfull, (uint32_t)bres_bytes);
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_b_3d<1>(smem_base + kb * b_rows * 128, &p.mapB, bfull, kb * BK, nt0 * BN, 0);
+        const uint32_t a_ring = smem_base + bres_bytes;
+        for (int w = unit; w < total_work; w += nunits) {
+          const int mu = w / p.n_tiles;
+          int x0, y0, i0;
+          decode_m_tile(p, mu, x0, y0, i0);
+          int s = 0, tap = 0, cb = 0;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int taps = p.seg_taps[s];
+            const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+            const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+            if (!ready) mbar_wait(&empty_bar[stage], phase ^ 1u);
+            const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
+            const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+            const uint32_t fb = full0 + stage * 8;
+            ready = mbar_probe(empty0 + nstage * 8, nphase ^ 1u);
+            mbar_expect_tx_u32(fb, (uint32_t)A_STAGE_BYTES);
+            tma_a_4d<1>(a_ring + stage * A_STAGE_BYTES, &p.mapA[s], fb, cb * BK, x0 + dx, y0 + dy, i0);
+            stage = nstage;
+            phase = nphase;
+            if (++cb == p.seg_cblk[s]) {
+              cb = 0;
+              if (++tap == taps) {
+                tap = 0;
+                ++s;
+              }
+            }
+          }
+        }
+      } else
       for (int w = unit; w < total_work; w += nunits) {
         const int tile = w / p.splits;
         const int sp = w - tile * p.splits;
@@ -660,6 +708,24 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
 #endif
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        if (p.bres) {
+          if (lt == 0) mbar_wait(b_full, 0u);
+          const uint32_t a_ring = smem_base + bres_bytes;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            if (!ready) mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
+            const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+            ready = mbar_probe(full0 + nstage * 8, nphase);
+            mma_quad<1>(d_tmem, umma_desc_sw128(a_ring + stage * A_STAGE_BYTES),
+                        umma_desc_sw128(smem_base + kb * b_rows * 128), idesc, kb != kb0 ? 1u : 0u);
+            umma_commit_g<1>(&empty_bar[stage]);
+            stage = nstage;
+            phase = nphase;
+          }
+          umma_commit_g<1>(&tmem_full[acc]);
+          continue;
+        }
         if (p.kbs == 2) {
           for (int kb = kb0; kb < kb1; kb += 2) {
             const int n_here = min(2, kb1 - kb);
@@ -1467,8 +1533,29 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.kbs = (env_kbs == 1 || env_kbs == 2) ? env_kbs : LS_GEMM_DEFAULT_KBS;
   if (p.kb_per < 4) p.kbs = 1;
   const int stage_bytes = p.kbs * (A_STAGE_BYTES + (BN / CTAS) * 128);
-  int fixed = STAGING_BYTES + BIAS_BYTES + 192;  // + 20 mbarriers and the TMEM slot
+  int fixed = STAGING_BYTES + BIAS_BYTES + 192;  // + 21 mbarriers and the TMEM slot
   int stages = (SMEM_BUDGET - fixed) / stage_bytes;
+  // Weight-resident mode for short-K launches whose whole B tile fits beside an A ring (K = 320 at BN = 160: 100 KB): the
+  // grid is trimmed to a multiple of n_tiles so that CTA c only ever sees n-tile c % n_tiles.  LS_GEMM_BRES=0 disables.
+  static int env_bres = -1;
+  if (env_bres < 0) {
+    const char* e = getenv("LS_GEMM_BRES");
+    env_bres = e ? atoi(e) : LS_GEMM_DEFAULT_BRES;
+  }
+  int bres_bytes = 0;
+  {
+    const int units0 = sms;
+    const long total0 = (long)p.m_tiles * p.n_tiles;
+    const int g_units = (units0 / p.n_tiles) * p.n_tiles;
+    const int b_bytes = p.num_kb * BN * 128;
+    const int a_stages = (SMEM_BUDGET - fixed - b_bytes) / A_STAGE_BYTES;
+    if (env_bres != 0 && CTAS == 1 && p.splits == 1 && p.kbs == 1 && !p.b_batched && g_units > 0 &&
+        b_bytes <= 112 * 1024 && a_stages >= 4 && total0 >= 2L * g_units) {
+      p.bres = 1;
+      bres_bytes = b_bytes;
+      stages = a_stages;
+    }
+  }
   // Experiment kept behind LS_GEMM_SLAB_SINGLE: if main-loop-bound launches were bound by the operand bytes in flight,
   // halving the staging area (slabs stored one by one from 2 KB per warp) to buy one more stage would pay.  It does not.
   static int env_ss = -1;
@@ -1481,7 +1568,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   {
     const int fixed_s = STAGING_BYTES / 2 + BIAS_BYTES + 192;
     const int stages_s = (SMEM_BUDGET - fixed_s) / stage_bytes;
-    const bool legal = p.tma_store && a->residual == nullptr && p.splits == 1 && !geglu;
+    const bool legal = p.tma_store && a->residual == nullptr && p.splits == 1 && !geglu && !p.bres;
     const bool want = env_ss == 1 || (env_ss == 2 && p.kb_per >= 24 && stages_s > stages && stages < MAX_STAGES);
     if (legal && want) {
       p.slab_single = 1;
@@ -1492,7 +1579,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  const size_t smem = p.bres ? (size_t)bres_bytes + (size_t)stages * A_STAGE_BYTES + fixed : (size_t)stages * stage_bytes + fixed;
 
   const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
   const long total = (long)m_units * p.n_tiles * p.splits;
@@ -1503,7 +1590,8 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     env_alt = e ? atoi(e) : 2;
   }
   p.epi_alt = (p.tma_store && p.splits == 1 && (env_alt == 1 || (env_alt == 2 && total >= 3L * units))) ? 1 : 0;
-  const int grid = (int)(total < units ? total : units) * CTAS;
+  int grid = (int)(total < units ? total : units) * CTAS;
+  if (p.bres) grid = (units / p.n_tiles) * p.n_tiles;  // every tile of a CTA shares its n-tile (total >= 2 x that, checked above)
   static bool attr_set_dev[16] = {};  // function attributes are per device
   int dev_attr = 0;
   LS_CUDA(cudaGetDevice(&dev_attr));

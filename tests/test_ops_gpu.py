@@ -427,3 +427,19 @@ def test_attention_every_shape_on_the_other_kernels(switch):
                           "attention and not every_shape", "--no-header", "-p", "no:cacheprovider"],
                          env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_gemm_weight_resident_mode():
+    """LS_GEMM_BRES=1 (off by default - it measured no faster, profiles/r2l_gemm_epilogue_experiments.txt (9)): a CTA of a
+    short-K launch keeps its weight tile in shared memory across its M tiles and streams only activations.  Same results as
+    an fp32 matmul on every shape that takes the mode (bias, residual, GEGLU, ragged M).  The switch is read once per
+    process, hence the child."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "bres_check.py")], env=dict(os.environ, LS_GEMM_BRES="1"),
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("M=")]
+    assert len(lines) >= 6 and all(l.rstrip().endswith("OK") for l in lines), res.stdout
