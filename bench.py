@@ -65,7 +65,7 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, index: int):
         self.index = index
@@ -89,7 +89,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, lim, reasons = [], [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
@@ -103,10 +103,17 @@ class ClockSampler:
             for n, v in zip(names, c[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+            try:  # board power: under sw_power_cap the SM clock is whatever fits the limit for the current kernel mix
+                pw.append(float(c[3]))
+                lim.append(float(c[9]))
+            except (ValueError, IndexError):
+                pass
         os.unlink(self.f.name)
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None,
+                "power_limit_w": max(lim) if lim else None}
 
 
 def _cfg_batch(seg):

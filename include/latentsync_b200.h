@@ -90,6 +90,29 @@ typedef struct LsGemmArgs {
   int32_t flags;
   int32_t tile_n; /* 0 = auto (wave-quantisation cost model); else a multiple of 32 (64 with GEGLU) up to 256 */
   int32_t cta_pair; /* 0 = auto; 1 = single-CTA 128 x tile_n tiles; 2 = CTA pairs (cta_group::2), 256 x tile_n tiles */
+  /* nn.LayerNorm folded into the nn.Linear that consumes it (attention.py:176-186,196-197; motion_module.py:208-216):
+   * with W' = W diag(gamma) as the B operand and the RAW activations x as A,
+   *   LN(x) W^T = rstd[m] (x W'^T)[m, n] - rstd[m] mean[m] col_sum[n] + (beta W^T + bias)[n],
+   * col_sum[n] = sum_k W'[n, k] (fp32 [N], of the fp16 operand; GEGLU: packed like the weight rows), the last term goes in
+   * `bias` (which may still select a row per `bias_div` output rows: the temporal sinusoid table times W^T).  The row
+   * statistics cost no pass of their own: the GEMM that PRODUCES x writes, per row, the (sum, sum of squares) of its
+   * output values (fp32, taken just before their rounding to fp16) as a few partials,
+   *   row_partials_out: fp32 [n_partials_out][partials_out_stride][2], n_partials_out == 3 * ceil(N / tile_n) (checked:
+   *   pass tile_n explicitly; three fixed column ranges per N tile, so that the values do not depend on the launch
+   *   geometry), part-major so that rows may be written by several launches (stride >= this launch's M);
+   * the consuming GEMM (K = the producer's N, one pointwise segment) sums them in part order (deterministic):
+   *   row_partials_in / n_partials_in / partials_in_stride: the producer's array, first row = this launch's row 0;
+   *   mean = S / K, rstd = 1 / sqrt(Q / K - mean^2 + ln_eps).
+   * Both need the staged fp16 epilogue (ldo % 8 == 0, contiguous rows, no fp32 output) and N % 32 == 0; neither uses
+   * split-K.  All NULL / 0 = plain GEMM. */
+  const float* col_sum;
+  const float* row_partials_in;
+  int32_t n_partials_in;
+  int64_t partials_in_stride;
+  float ln_eps;
+  float* row_partials_out;
+  int32_t n_partials_out;
+  int64_t partials_out_stride;
 } LsGemmArgs;
 
 int ls_gemm(const LsGemmArgs* args, void* stream);

@@ -46,6 +46,14 @@ class LsGemmArgs(C.Structure):
         ("flags", C.c_int32),
         ("tile_n", C.c_int32),
         ("cta_pair", C.c_int32),
+        ("col_sum", C.c_void_p),
+        ("row_partials_in", C.c_void_p),
+        ("n_partials_in", C.c_int32),
+        ("partials_in_stride", C.c_int64),
+        ("ln_eps", C.c_float),
+        ("row_partials_out", C.c_void_p),
+        ("n_partials_out", C.c_int32),
+        ("partials_out_stride", C.c_int64),
     ]
 
 
@@ -215,8 +223,21 @@ def gemm(
     tile_n: int = 0,
     b_batch_stride: int = 0,
     cta_pair: int = 0,
+    col_sum: Optional[torch.Tensor] = None,
+    row_partials_in: Optional[torch.Tensor] = None,
+    row_partials_out: Optional[torch.Tensor] = None,
+    ln_eps: float = 1e-5,
 ) -> None:
+    """row_partials_in / row_partials_out: fp32 [parts, rows, 2] (LsGemmArgs: LayerNorm folded into the consuming GEMM)"""
     a = LsGemmArgs()
+    a.col_sum = _ptr(col_sum)
+    for name, t in (("in", row_partials_in), ("out", row_partials_out)):
+        if t is not None:  # [parts, rows, 2], possibly a row range of a larger [parts, all_rows, 2] array
+            assert t.dtype == torch.float32 and t.dim() == 3 and t.stride(2) == 1 and t.stride(1) == 2 and t.stride(0) % 2 == 0
+            setattr(a, "row_partials_" + name, _ptr(t))
+            setattr(a, f"n_partials_{name}", t.shape[0])
+            setattr(a, f"partials_{name}_stride", t.stride(0) // 2)
+    a.ln_eps = ln_eps
     a.nseg = len(segs)
     ktot = 0
     for i, s in enumerate(segs):
@@ -410,6 +431,24 @@ def small_linear(x, B, K, W, bias, add, N, silu_in, silu_out, y) -> None:
 
 def timestep_embedding(t, B, dim, out) -> None:
     _check(lib().ls_timestep_embedding(_ptr(t), B, dim, _ptr(out), _stream()), "ls_timestep_embedding")
+
+
+def fold_layernorm(weight: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                   pe: Optional[torch.Tensor] = None):
+    """nn.LayerNorm(gamma, beta) followed by nn.Linear(weight [N, K], bias) as ONE GEMM on the raw activations
+    (LsGemmArgs.col_sum): returns (W' = W diag(gamma) as fp16 [N, K], col_sum fp32 [N] of that fp16 operand,
+    bias' = beta W^T + bias, fp32 [N]).  With `pe` ([F, K], the temporal sinusoid table added AFTER the norm,
+    motion_module.py:232-234) bias' is [F, N]: row f = (beta + pe[f]) W^T + bias."""
+    w32 = weight.float()
+    wg = (w32 * gamma.float()[None, :]).to(torch.float16)
+    col_sum = wg.float().sum(dim=1).contiguous()
+    if pe is None:
+        b2 = w32 @ beta.float()
+    else:
+        b2 = (beta.float()[None, :] + pe.float()) @ w32.t()
+    if bias is not None:
+        b2 = b2 + bias.float()
+    return wg.contiguous(), col_sum, b2.contiguous()
 
 
 def pack_geglu(weight: torch.Tensor, bias: Optional[torch.Tensor], tile_n: int):

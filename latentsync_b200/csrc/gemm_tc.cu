@@ -64,6 +64,7 @@ constexpr int MMA_WARP = 9;
 constexpr int WSLAB_BYTES = 32 * 64;           // one warp's share of a slab: 32 rows x 32 fp16 columns, SWIZZLE_64B
 constexpr int STAGING_BYTES = 8 * 2 * WSLAB_BYTES;  // 8 epilogue warps x (32 rows x 128 bytes): a pair of slabs each
 constexpr int BIAS_BYTES = 2 * 256 * 4;        // one bias row of 256 floats per epilogue group
+constexpr int COLSUM_BYTES = 2 * 256 * 4;      // folded-LayerNorm launches: one col_sum row per epilogue group
 constexpr int ACC_COLS = 256;                  // TMEM columns per accumulator
 constexpr int TMEM_COLS = 512;                 // two accumulators: the whole TMEM (one CTA per SM anyway)
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -130,6 +131,17 @@ struct GemmKParams {
   float* ws;             // split-K partials, fp32 [splits][M][N] (library-owned scratch)
   unsigned int* tickets; // one arrival counter per output tile (self-resetting)
   int64_t M;  // total output rows
+  // LayerNorm folded into this GEMM (LsGemmArgs.col_sum / row_partials_in): out = rstd (x W'^T) - rstd mean col_sum + bias,
+  // (mean, rstd) of row m from the producer's partials ln_in[i * ln_in_stride + m], i < ln_nparts_in, summed in order
+  const float2* ln_in;
+  const float* colsum;
+  int ln_nparts_in;
+  int64_t ln_in_stride;
+  float ln_eps, ln_inv_k;
+  // ... and the producer side (LsGemmArgs.row_partials_out): part 3 nt + k of row m = (sum, sum of squares) of the fp16
+  // values stored into slab range k of n-tile nt
+  float2* ln_out;
+  int64_t ln_out_stride;
 };
 
 // ----------------------------------------------------------------------------------------- pair-mode PTX wrappers
@@ -455,7 +467,10 @@ __device__ __forceinline__ void add_bias32(const GemmKParams& p, int64_t m, int 
 // tcgen05.ld in flight while the current one is converted (needs ~190 registers: spills, 71 vs 50 us on the K = 64,
 // N = 2560 probe); setmaxnreg with a third, shrunken warpgroup for the producer / issuer (ptxas then spills in the
 // producer / issuer loops at every split tried: 224/64, 208/96, 200/112, 192/128).
-template <int CTAS, bool GEGLU>
+// LN selects the folded-LayerNorm epilogues (separate instantiations: the plain kernels do not pay for them - the first
+// version of this fold, round 1, put the code into every launch and lost more there than the LayerNorm kernels cost):
+//   0 plain;  1 consumer: per-row scale / shift from the producer's partials;  2 producer: emits the partials.
+template <int CTAS, bool GEGLU, int LN>
 __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   const int BN = p.BN;
   const int b_rows = BN / CTAS;  // B rows staged by each CTA
@@ -478,6 +493,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint64_t* b_full = tmem_empty + 3;  // weight-resident mode: the B tile has landed (8 bytes after the TMEM slot)
+  float* colsum_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 192);  // LN == 1 launches only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -806,17 +822,30 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
       // bias row of the NEXT tile is fetched into registers one tile ahead and parked in a double-buffered smem row, so
       // its global-load latency never sits on the epilogue's critical path (ncu: 9 % of the stall samples before)
       float bias_next[2] = {0.f, 0.f};
+      float cs_next[2] = {0.f, 0.f};  // LN == 1: col_sum of the next tile's columns, parked like the bias row
       auto fetch_bias = [&](int w_next) {
-        if (w_next >= total_work || p.bias == nullptr) {
-          bias_next[0] = bias_next[1] = 0.f;
-          return;
-        }
+        bias_next[0] = bias_next[1] = 0.f;
+        if constexpr (LN == 1) cs_next[0] = cs_next[1] = 0.f;
+        if (w_next >= total_work || (LN != 1 && p.bias == nullptr)) return;
         const int tile = (int)fdiv((uint32_t)w_next, p.fd_splits);
         const int mu = (int)fdiv((uint32_t)tile, p.fd_n_tiles);
         const int nt = tile - mu * p.n_tiles;
         int x0, y0, i0;
         decode_m_tile(p, mu * CTAS + rank, x0, y0, i0);
         const int64_t m0 = ((int64_t)i0 * p.H + y0) * p.W + x0;
+        if constexpr (LN == 1) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c = gtid + 128 * k;
+            cs_next[k] = (c < BN && nt * BN + c < p.N) ? __ldg(p.colsum + nt * BN + c) : 0.f;
+          }
+          // the next tile's row partials -> L1 now, so that their L2 latency (two dependent rounds of loads: ~1400 clocks
+          // per tile on launches that are epilogue-bound anyway) is not paid at the top of that tile
+          if (m0 + r < p.M)
+            for (int i = 0; i < p.ln_nparts_in; ++i)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_in + (int64_t)i * p.ln_in_stride + m0 + r));
+          if (p.bias == nullptr) return;
+        }
         const int64_t brow_i = (p.bias_div > 0 && m0 < p.M) ? (int64_t)fdiv((uint32_t)m0, p.fd_bias_div) : 0;  // M < 2^31 here
         const float* brow = p.bias + brow_i * (int64_t)p.bias_ld + nt * BN;
 #pragma unroll
@@ -870,6 +899,40 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         float* my_bias = bias_sm + group * 256;
         my_bias[gtid] = bias_next[0];
         my_bias[gtid + 128] = bias_next[1];
+        // LN == 1: out = rs_a * acc + rs_c * col_sum[n] + bias[n]
+        float* my_cs = colsum_sm + group * 256;
+        float rs_a = 1.f, rs_c = 0.f;
+        if constexpr (LN == 1) {
+          my_cs[gtid] = cs_next[0];
+          my_cs[gtid + 128] = cs_next[1];
+          if (row_ok) {
+            // the producer's partial sums of this row, combined in part order (deterministic).  Six loads are issued
+            // together, then added in order (as a plain loop ptxas emits load -> add -> load: one latency per part,
+            // ~360 clocks each at the top of every tile; absent parts add an exact 0)
+            const float2* pp = p.ln_in + m;
+            float su = 0.f, sq = 0.f;
+            for (int i0 = 0; i0 < p.ln_nparts_in; i0 += 6) {
+              float2 t[6];
+#pragma unroll
+              for (int k = 0; k < 6; ++k)
+                t[k] = (i0 + k < p.ln_nparts_in) ? __ldg(pp + (int64_t)(i0 + k) * p.ln_in_stride) : make_float2(0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < 6; ++k) {
+                su += t[k].x;
+                sq += t[k].y;
+              }
+            }
+            const float mean = su * p.ln_inv_k;
+            const float rstd = rsqrtf(fmaxf(sq * p.ln_inv_k - mean * mean, 0.f) + p.ln_eps);
+            rs_a = rstd;
+            rs_c = -rstd * mean;
+          }
+        }
+        // LN == 2: this thread's row over three FIXED slab ranges of the tile, [0, nslab/2), [nslab/2, (nslab+1)/2),
+        // [(nslab+1)/2, nslab) - the only boundaries the groups ever split a tile at - so that the partials (and with them
+        // every bit downstream) do not depend on which group, or how many tiles per CTA, a launch geometry happens to use
+        float ln_su[3] = {0.f, 0.f, 0.f}, ln_sq[3] = {0.f, 0.f, 0.f};
+        const int ln_lo = nslab / 2, ln_hi = (nslab + 1) / 2;
         // (2) residual of the NEXT pair of slabs, requested one pair ahead with COALESCED loads: instruction i of a
         //     pair (32 rows x 128 bytes per warp) has lane l read 16-byte chunk (l & 7) of row 4 i + (l >> 3), i.e. four
         //     whole 128-byte lines per instruction.  (A thread reading its own row's 64 bytes - the layout the
@@ -878,7 +941,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         //     staging buffer: stored at the 128B-swizzled position the output chunk will take, read back by the row's
         //     thread (both patterns conflict-free), then overwritten by the output.
         uint4 res[8];
-        const bool has_res = (p.residual != nullptr);
+        const bool has_res = (LN != 1) && (p.residual != nullptr);  // a folded-LayerNorm consumer never adds a residual (host)
         auto fetch_res_pair = [&](int s0) {  // slabs j_lo + s0, j_lo + s0 + 1 (or the trailing single slab)
           const int j = j_lo + s0;
           const int ncol0 = nt * BN + j * 32;
@@ -1034,10 +1097,18 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 t = *reinterpret_cast<const float4*>(my_bias + j * 32 + e4 * 4);
-              f[e4 * 4] = __uint_as_float(v[e4 * 4]) + t.x;
-              f[e4 * 4 + 1] = __uint_as_float(v[e4 * 4 + 1]) + t.y;
-              f[e4 * 4 + 2] = __uint_as_float(v[e4 * 4 + 2]) + t.z;
-              f[e4 * 4 + 3] = __uint_as_float(v[e4 * 4 + 3]) + t.w;
+              if constexpr (LN == 1) {
+                const float4 c4 = *reinterpret_cast<const float4*>(my_cs + j * 32 + e4 * 4);
+                f[e4 * 4] = fmaf(rs_a, __uint_as_float(v[e4 * 4]), fmaf(rs_c, c4.x, t.x));
+                f[e4 * 4 + 1] = fmaf(rs_a, __uint_as_float(v[e4 * 4 + 1]), fmaf(rs_c, c4.y, t.y));
+                f[e4 * 4 + 2] = fmaf(rs_a, __uint_as_float(v[e4 * 4 + 2]), fmaf(rs_c, c4.z, t.z));
+                f[e4 * 4 + 3] = fmaf(rs_a, __uint_as_float(v[e4 * 4 + 3]), fmaf(rs_c, c4.w, t.w));
+              } else {
+                f[e4 * 4] = __uint_as_float(v[e4 * 4]) + t.x;
+                f[e4 * 4 + 1] = __uint_as_float(v[e4 * 4 + 1]) + t.y;
+                f[e4 * 4 + 2] = __uint_as_float(v[e4 * 4 + 2]) + t.z;
+                f[e4 * 4 + 3] = __uint_as_float(v[e4 * 4 + 3]) + t.w;
+              }
             }
           } else {
             uint32_t g[32];
@@ -1046,8 +1117,21 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             tmem_ld_wait();
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 bv = *reinterpret_cast<const float4*>(my_bias + j * 32 + e4 * 4);
-              const float4 bg = *reinterpret_cast<const float4*>(my_bias + BN / 2 + j * 32 + e4 * 4);
+              float4 bv = *reinterpret_cast<const float4*>(my_bias + j * 32 + e4 * 4);
+              float4 bg = *reinterpret_cast<const float4*>(my_bias + BN / 2 + j * 32 + e4 * 4);
+              if constexpr (LN == 1) {  // LayerNorm in front of the GEGLU projection: fix up value and gate pre-activations
+                const float4 cv = *reinterpret_cast<const float4*>(my_cs + j * 32 + e4 * 4);
+                const float4 cg = *reinterpret_cast<const float4*>(my_cs + BN / 2 + j * 32 + e4 * 4);
+                bv.x = fmaf(rs_c, cv.x, bv.x); bv.y = fmaf(rs_c, cv.y, bv.y);
+                bv.z = fmaf(rs_c, cv.z, bv.z); bv.w = fmaf(rs_c, cv.w, bv.w);
+                bg.x = fmaf(rs_c, cg.x, bg.x); bg.y = fmaf(rs_c, cg.y, bg.y);
+                bg.z = fmaf(rs_c, cg.z, bg.z); bg.w = fmaf(rs_c, cg.w, bg.w);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[e4 * 4 + e] = __float_as_uint(rs_a * __uint_as_float(v[e4 * 4 + e]));
+                  g[e4 * 4 + e] = __float_as_uint(rs_a * __uint_as_float(g[e4 * 4 + e]));
+                }
+              }
               f[e4 * 4] = (__uint_as_float(v[e4 * 4]) + bv.x) * gelu_erf_f(__uint_as_float(g[e4 * 4]) + bg.x);
               f[e4 * 4 + 1] =
                   (__uint_as_float(v[e4 * 4 + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[e4 * 4 + 1]) + bg.y);
@@ -1114,15 +1198,37 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             if (lane == 0) bulk_wait_group_read<0>();
             __syncwarp();
           }
+          float slab_su = 0.f, slab_sq = 0.f, slab_su2 = 0.f, slab_sq2 = 0.f;  // two chains each: ILP
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 u;
             __half2* h2 = reinterpret_cast<__half2*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1]);
+            if constexpr (LN == 2) {
+              // statistics of the fp32 values before their rounding to fp16 (two instructions per element; from the
+              // rounded halves it is three and a half, and these launches are bound by the epilogue's issue slots)
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                slab_su += f[c * 8 + e];
+                slab_su2 += f[c * 8 + e + 1];
+                slab_sq = fmaf(f[c * 8 + e], f[c * 8 + e], slab_sq);
+                slab_sq2 = fmaf(f[c * 8 + e + 1], f[c * 8 + e + 1], slab_sq2);
+              }
+            }
             uint8_t* dst = single ? my_stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)
                                   : my_stage + lane * 128 + (((half_sel * 4 + c) ^ (lane & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = u;
+          }
+          if constexpr (LN == 2) {
+            const int pid = (j >= ln_lo ? 1 : 0) + (j >= ln_hi ? 1 : 0);
+            slab_su += slab_su2;
+            slab_sq += slab_sq2;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              ln_su[k] += (pid == k) ? slab_su : 0.f;
+              ln_sq[k] += (pid == k) ? slab_sq : 0.f;
+            }
           }
           EP_STAMP(3 + (s & 3));
           if (half_sel == 1 || single || ncol0 + 32 >= n_out_total) {
@@ -1139,6 +1245,19 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         }
         }
         EP_STAMP(7);
+        if constexpr (LN == 2) {
+          if (row_ok) {  // 32 consecutive rows per warp: one coalesced 256-byte store per part
+            // every part is written exactly once per tile, by the group whose slab range contains it (zeros where the
+            // range is empty or lies beyond N)
+            const bool own[3] = {alt || group == 0,
+                                 alt || (group == 0 ? (n_first == ln_hi) : (n_first == ln_lo && ln_lo != ln_hi)),
+                                 alt || group == 1};
+            float2* dst = p.ln_out + (int64_t)(3 * nt) * p.ln_out_stride + m;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              if (own[k]) dst[(int64_t)k * p.ln_out_stride] = make_float2(ln_su[k], ln_sq[k]);
+          }
+        }
         named_bar_sync(1 + group, 128);  // every warp of the group has read the bias row: the next tile may overwrite it
         if (!released) {  // group had no slab inside N for this tile: still hand the accumulator back
           tc_fence_before();
@@ -1243,14 +1362,24 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   if (warp == MMA_WARP) tmem_dealloc_g<CTAS>(tmem_base, TMEM_COLS);
 }
 
-template <bool GEGLU>
+template <bool GEGLU, int LN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-  gemm_body<1, GEGLU>(p);
+  gemm_body<1, GEGLU, LN>(p);
 }
-template <bool GEGLU>
+template <bool GEGLU, int LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_pair_kernel(const __grid_constant__ GemmKParams p) {
-  gemm_body<2, GEGLU>(p);
+  gemm_body<2, GEGLU, LN>(p);
+}
+typedef void (*GemmKernelFn)(const GemmKParams);
+// [CTAS - 1][geglu][LN]; a GEGLU projection never produces LayerNorm partials (its output feeds a Linear)
+static GemmKernelFn gemm_kernel_of(int ctas, bool geglu, int ln) {
+  static const GemmKernelFn tab[2][2][3] = {
+      {{gemm_tc_kernel<false, 0>, gemm_tc_kernel<false, 1>, gemm_tc_kernel<false, 2>},
+       {gemm_tc_kernel<true, 0>, gemm_tc_kernel<true, 1>, nullptr}},
+      {{gemm_tc_pair_kernel<false, 0>, gemm_tc_pair_kernel<false, 1>, gemm_tc_pair_kernel<false, 2>},
+       {gemm_tc_pair_kernel<true, 0>, gemm_tc_pair_kernel<true, 1>, nullptr}}};
+  return tab[ctas - 1][geglu ? 1 : 0][ln];
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1395,6 +1524,27 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   // ---- tile width, CTA pairing and split-K factor
   const int sms = num_sms();
   const bool geglu = (a->flags & LS_EPI_GEGLU) != 0;
+  // folded LayerNorm (see LsGemmArgs): 1 = this GEMM consumes the producer's row partials, 2 = it produces them
+  const int ln_mode = a->row_partials_in != nullptr ? 1 : (a->row_partials_out != nullptr ? 2 : 0);
+  if (ln_mode != 0) {
+    LS_CHECK(a->row_partials_in == nullptr || a->row_partials_out == nullptr,
+             "ls_gemm: a GEMM either consumes or produces LayerNorm partials, not both");
+    LS_CHECK(p.tma_store && a->N % 32 == 0 && !p.b_batched,
+             "ls_gemm: LayerNorm partials need the staged fp16 epilogue (ldo %% 8 == 0, contiguous rows), N %% 32 == 0, no batching");
+  }
+  if (ln_mode == 1) {
+    LS_CHECK(a->residual == nullptr, "ls_gemm: a GEMM with a folded LayerNorm takes no residual");
+    LS_CHECK((reinterpret_cast<uintptr_t>(a->col_sum) & 15) == 0, "ls_gemm: col_sum must be 16-byte aligned");
+    LS_CHECK(a->col_sum != nullptr && a->n_partials_in >= 1 && a->n_partials_in <= 96 && a->partials_in_stride >= M &&
+                 a->ln_eps > 0.f && a->nseg == 1 && a->a_taps[0] == 1 &&
+                 (reinterpret_cast<uintptr_t>(a->row_partials_in) & 7) == 0,
+             "ls_gemm: row_partials_in needs col_sum, 1..96 parts with stride >= M, ln_eps > 0 and a single pointwise A segment");
+  }
+  if (ln_mode == 2) {
+    LS_CHECK(!geglu && !(a->flags & LS_EPI_SILU) && a->partials_out_stride >= M &&
+                 (reinterpret_cast<uintptr_t>(a->row_partials_out) & 7) == 0,
+             "ls_gemm: row_partials_out needs a plain (bias / residual) epilogue and stride >= M");
+  }
   static int env_ctas = -1;
   if (env_ctas < 0) {
     const char* e = getenv("LS_GEMM_CTAS");
@@ -1410,7 +1560,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   }
   // split-K only where SMs would idle: few output tiles, long K; needs the TMA-store epilogue and a plain GEMM
   const bool split_ok = env_split != 0 && p.tma_store && !geglu && !p.b_batched && !(a->flags & LS_EPI_SILU) &&
-                        (a->N % 8 == 0) && (a->bias_ld % 4 == 0);
+                        (a->N % 8 == 0) && (a->bias_ld % 4 == 0) && ln_mode == 0;
   int best_bn = 0, best_ctas = 1, best_split = 1;
   double best_cost = -1.0;
   const int step = geglu ? 64 : 32;
@@ -1448,6 +1598,18 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.n_tiles = (a->N + BN - 1) / BN;
   p.splits = best_split;
   p.kb_per = (p.num_kb + best_split - 1) / best_split;
+  if (ln_mode == 2)
+    LS_CHECK(a->n_partials_out == 3 * p.n_tiles,
+             "ls_gemm: row_partials_out holds n_partials_out = %d parts, this launch writes 3 * ceil(N / tile_n) = %d (N = %d, "
+             "tile_n = %d): pass tile_n explicitly", a->n_partials_out, 3 * p.n_tiles, a->N, BN);
+  p.ln_in = reinterpret_cast<const float2*>(a->row_partials_in);
+  p.colsum = a->col_sum;
+  p.ln_nparts_in = a->n_partials_in;
+  p.ln_in_stride = a->partials_in_stride;
+  p.ln_eps = a->ln_eps;
+  p.ln_inv_k = 1.0f / (float)ktot;
+  p.ln_out = reinterpret_cast<float2*>(a->row_partials_out);
+  p.ln_out_stride = a->partials_out_stride;
   if (best_split > 1) {
     int dev = 0;
     LS_CUDA(cudaGetDevice(&dev));
@@ -1533,7 +1695,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.kbs = (env_kbs == 1 || env_kbs == 2) ? env_kbs : LS_GEMM_DEFAULT_KBS;
   if (p.kb_per < 4) p.kbs = 1;
   const int stage_bytes = p.kbs * (A_STAGE_BYTES + (BN / CTAS) * 128);
-  int fixed = STAGING_BYTES + BIAS_BYTES + 192;  // + 21 mbarriers and the TMEM slot
+  int fixed = STAGING_BYTES + BIAS_BYTES + 192 + (ln_mode == 1 ? COLSUM_BYTES : 0);  // + 21 mbarriers and the TMEM slot
   int stages = (SMEM_BUDGET - fixed) / stage_bytes;
   // Weight-resident mode for short-K launches whose whole B tile fits beside an A ring (K = 320 at BN = 160: 100 KB): the
   // grid is trimmed to a multiple of n_tiles so that CTA c only ever sees n-tile c % n_tiles.  LS_GEMM_BRES=0 disables.
@@ -1549,7 +1711,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     const int g_units = (units0 / p.n_tiles) * p.n_tiles;
     const int b_bytes = p.num_kb * BN * 128;
     const int a_stages = (SMEM_BUDGET - fixed - b_bytes) / A_STAGE_BYTES;
-    if (env_bres != 0 && CTAS == 1 && p.splits == 1 && p.kbs == 1 && !p.b_batched && g_units > 0 &&
+    if (env_bres != 0 && ln_mode == 0 && CTAS == 1 && p.splits == 1 && p.kbs == 1 && !p.b_batched && g_units > 0 &&
         b_bytes <= 112 * 1024 && a_stages >= 4 && total0 >= 2L * g_units) {
       p.bres = 1;
       bres_bytes = b_bytes;
@@ -1568,7 +1730,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   {
     const int fixed_s = STAGING_BYTES / 2 + BIAS_BYTES + 192;
     const int stages_s = (SMEM_BUDGET - fixed_s) / stage_bytes;
-    const bool legal = p.tma_store && a->residual == nullptr && p.splits == 1 && !geglu && !p.bres;
+    const bool legal = p.tma_store && a->residual == nullptr && p.splits == 1 && !geglu && !p.bres && ln_mode == 0;
     const bool want = env_ss == 1 || (env_ss == 2 && p.kb_per >= 24 && stages_s > stages && stages < MAX_STAGES);
     if (legal && want) {
       p.slab_single = 1;
@@ -1598,23 +1760,21 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   LS_CHECK(dev_attr >= 0 && dev_attr < 16, "ls_gemm: device index %d out of range", dev_attr);
   bool& attr_set = attr_set_dev[dev_attr];
   if (!attr_set) {
-    LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    LS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    LS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    LS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    for (int c = 1; c <= 2; ++c)
+      for (int g = 0; g < 2; ++g)
+        for (int l = 0; l < 3; ++l)
+          if (GemmKernelFn fn = gemm_kernel_of(c, g != 0, l))
+            LS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     attr_set = true;
   }
   if (CTAS == 1 && p.splits > 1)
     // split-K CTAs meet at a per-tile ticket inside the kernel: cooperative launch = the driver guarantees that the
     // whole (single-wave) grid is resident, whatever else runs on the GPU
-    LS_CUDA(launch_coop_k(gemm_tc_kernel<false>, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), (cudaStream_t)(stream),
+    LS_CUDA(launch_coop_k(gemm_tc_kernel<false, 0>, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), (cudaStream_t)(stream),
                           p));
-  else if (CTAS == 1)
-    LS_CUDA(launch_k(geglu ? gemm_tc_kernel<true> : gemm_tc_kernel<false>, dim3(grid), dim3(GEMM_THREADS),
-                     (size_t)(smem), (cudaStream_t)(stream), p));
   else
-    LS_CUDA(launch_k(geglu ? gemm_tc_pair_kernel<true> : gemm_tc_pair_kernel<false>, dim3(grid), dim3(GEMM_THREADS),
-                     (size_t)(smem), (cudaStream_t)(stream), p));
+    LS_CUDA(launch_k(gemm_kernel_of(CTAS, geglu, ln_mode), dim3(grid), dim3(GEMM_THREADS), (size_t)(smem),
+                     (cudaStream_t)(stream), p));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;

@@ -21,6 +21,18 @@ from .spec import SD_VAE_FT_MSE_CONFIG, unet_config, validate_unet_config
 
 GEGLU_TILE = 256
 KPAD = 64  # GEMM K granularity (one 128-byte swizzle row of fp16)
+# nn.LayerNorm folded into the nn.Linear that consumes it (LsGemmArgs.col_sum / row_partials_*): the GEMM that writes the
+# residual stream emits per-row (sum, sum of squares) partials from its epilogue, the next GEMM reads the RAW stream with
+# W diag(gamma) and normalises in its own epilogue - no LayerNorm kernel, no normalised copy.  LS_FOLD_LN=0 keeps the
+# explicit kernels (A/B measurements; the level with < FOLD_LN_MIN_ROWS rows always keeps them: its GEMMs are split-K).
+FOLD_LN = os.environ.get("LS_FOLD_LN", "1") != "0"
+FOLD_LN_MIN_ROWS = 2048
+LN_TILE = 160  # tile width of every GEMM that emits partials (the cost model's own choice for N = 320 / 640 / 1280)
+
+
+def ln_parts(n: int) -> int:
+    """partials per row written by a producer GEMM of width n: three fixed column ranges per n-tile"""
+    return 3 * ((n + LN_TILE - 1) // LN_TILE)
 
 
 # --------------------------------------------------------------------------------------------------- buffers
@@ -52,10 +64,11 @@ class _Pool:
 class Buf:
     """[rows, cols] device matrix handle; closures recorded in a plan capture only `.ptr` (an int)."""
 
-    __slots__ = ("pool", "store", "ptr", "rows", "cols", "dtype")
+    __slots__ = ("pool", "store", "ptr", "rows", "cols", "dtype", "aux")
 
     def __init__(self, pool: _Pool, rows: int, cols: int, dtype=torch.float16):
         self.pool = pool
+        self.aux = None  # fp32 [ln_parts(cols)][rows][2] LayerNorm partials written by the GEMM(s) that produced this buffer
         self.rows, self.cols, self.dtype = rows, cols, dtype
         nbytes = rows * cols * torch.empty((), dtype=dtype).element_size()
         nbytes = (nbytes + 255) // 256 * 256
@@ -225,9 +238,17 @@ class Plan:
 
     def gemm(self, segs: Sequence[Tuple[int, int, int, int]], nimg: int, H: int, W: int, w: torch.Tensor, N: int,
              out_ptr: int, ldo: int, bias_ptr: int = 0, bias_div: int = 0, bias_ld: int = 0, residual_ptr: int = 0,
-             ldr: int = 0, flags: int = 0, tile_n: int = 0, b_batch_stride: int = 0, b_ptr: int = 0) -> None:
-        """segs: (ptr, channels, ld, taps).  w: packed fp16 [N, Ktot] tensor (kept alive by the engine) or b_ptr."""
+             ldr: int = 0, flags: int = 0, tile_n: int = 0, b_batch_stride: int = 0, b_ptr: int = 0,
+             col_sum_ptr: int = 0, parts_in: Optional[Tuple[int, int, int]] = None,
+             parts_out: Optional[Tuple[int, int, int]] = None) -> None:
+        """segs: (ptr, channels, ld, taps).  w: packed fp16 [N, Ktot] tensor (kept alive by the engine) or b_ptr.
+        parts_in / parts_out: (pointer to the first row, parts, stride in rows) of LayerNorm partials (LsGemmArgs)."""
         a = L.LsGemmArgs()
+        if parts_in is not None:
+            a.row_partials_in, a.n_partials_in, a.partials_in_stride = parts_in
+            a.col_sum, a.ln_eps = col_sum_ptr, 1e-5
+        if parts_out is not None:
+            a.row_partials_out, a.n_partials_out, a.partials_out_stride = parts_out
         a.nseg = len(segs)
         ktot = 0
         for i, (ptr, ch, ld, taps) in enumerate(segs):
@@ -254,7 +275,9 @@ class Plan:
         nbytes = (sum(M * ch * 2 for _, ch, _, _ in segs) + nb * N * ktot * 2 + M * n_out * (4 if flags & L.EPI_OUT_F32 else 2)
                   + (M * n_out * 2 if residual_ptr else 0))
         self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_gemm"), "gemm", 2.0 * M * N * ktot,
-                   f"M={M} N={N} K={ktot} img={nimg}x{H}x{W} segs={taps} flags={flags} batched={int(b_batch_stride != 0)}",
+                   f"M={M} N={N} K={ktot} img={nimg}x{H}x{W} segs={taps} flags={flags} batched={int(b_batch_stride != 0)}"
+                   + (" res" if residual_ptr else "") + (" ln=in" if parts_in is not None else "")
+                   + (" ln=out" if parts_out is not None else ""),
                    float(nbytes))
 
     def begin_stats(self, nfloats: int) -> None:
@@ -479,6 +502,26 @@ class UNetEngine:
                                             self.w.raw(p + ".to_v.weight")])))
         return self.w.t[name]
 
+    def folded(self, name: str, ln: str, weight_fn, bias_key: Optional[str] = None, geglu: bool = False,
+               pe: Optional[torch.Tensor] = None, repeat: int = 1):
+        """(W diag(gamma) fp16, col_sum fp32, bias' fp32) for LayerNorm `ln` followed by the Linear whose [N, K] weight
+        `weight_fn()` returns (_lib.fold_layernorm).  GEGLU projections are re-ordered per N tile like `geglu()`; with
+        `pe` ([F, K]) bias' is the per-frame table [(repeat F), N] (one row per (batch element, frame))."""
+        key = f"{name}#ln" + (f"pe{pe.shape[0]}x{repeat}" if pe is not None else "")
+        w = self.w
+        if key + ".w" not in w.t:
+            bias = w.raw(bias_key) if bias_key else None
+            wg, cs, b2 = L.fold_layernorm(weight_fn(), bias, w.raw(ln + ".weight"), w.raw(ln + ".bias"), pe=pe)
+            if geglu:
+                wg, b2 = L.pack_geglu(wg, b2, GEGLU_TILE)
+                cs = L.pack_geglu(cs[:, None], None, GEGLU_TILE)[0][:, 0]
+            if pe is not None and repeat > 1:
+                b2 = b2.repeat(repeat, 1)
+            w.put(key + ".w", wg.to(torch.float16))
+            w.put(key + ".cs", cs.float())
+            w.put(key + ".b", b2.float())
+        return w.t[key + ".w"], w.t[key + ".cs"], w.t[key + ".b"]
+
     def geglu(self, p: str) -> Tuple[torch.Tensor, torch.Tensor]:
         name = p + "#geglu"
         if name + ".w" not in self.w.t:
@@ -526,6 +569,7 @@ class UNetPlan(Plan):
         super().__init__(eng.device)
         self.eng = eng
         self.B, self.F, self.H, self.W, self.S = B, F, H, W, S
+        self._full_B = B  # self.B is temporarily 1 inside the shared prefix of same_sample plans
         self.uncond_zero = uncond_zero
         self.same_sample = same_sample
         self.taps: Dict[str, Tuple[Buf, int]] = {}  # name -> (buffer, level); filled only when LS_DEBUG_TAPS=1
@@ -589,28 +633,60 @@ class UNetPlan(Plan):
                       cout, bias_ptr=w.f32(r + ".conv2.bias").data_ptr(), residual_ptr=x1.ptr, ldr=cout)
         return out
 
-    def _linear(self, x: Buf, key: str, n: int, bias: bool = True, residual: Optional[Buf] = None) -> Buf:
+    def _fold(self, lvl: int, cc: int, pe: bool = False, halves: bool = False) -> bool:
+        """whether a LayerNorm of level `lvl` (width `cc`) is folded into the Linear that consumes it.  The decision only
+        depends on the level's full-batch geometry, never on the plan variant, so that the null-audio / shared-prefix
+        plans stay bit-identical to the full plan: `halves` marks the norms around the audio cross-attention, whose GEMMs
+        run on half the rows in those variants (they must still be >= FOLD_LN_MIN_ROWS: smaller GEMMs are split-K).  With
+        the temporal sinusoid table (`pe`) the per-frame bias row must be constant over a 128-row tile."""
+        h, wd = self._geo(lvl)
+        rows = self._full_B * self.F * h * wd
+        return (FOLD_LN and rows >= FOLD_LN_MIN_ROWS * (2 if halves else 1) and cc % 32 == 0
+                and (not pe or (h * wd) % 128 == 0))
+
+    def _with_parts(self, out: Buf) -> Buf:
+        out.aux = self.buf(ln_parts(out.cols) * out.rows, 2, torch.float32)
+        return out
+
+    @staticmethod
+    def _parts(x: Buf, row0: int = 0) -> Tuple[int, int, int]:
+        """(pointer, parts, stride) of x's LayerNorm partials starting at row `row0`"""
+        return (x.aux.ptr + row0 * 8, ln_parts(x.cols), x.rows)
+
+    def _linear(self, x: Buf, key: str, n: int, bias: bool = True, residual: Optional[Buf] = None,
+                stats: bool = False) -> Buf:
+        """`stats`: the output feeds a LayerNorm that is folded into the next GEMM - this GEMM's epilogue emits the
+        per-row partial sums of what it stores (out.aux)"""
         w = self.eng.w
         k = w.lin(key + ".weight").shape[1]
         assert k == x.cols
         out = self.buf(x.rows, n)
+        if stats:
+            self._with_parts(out)
         self.gemm([(x.ptr, k, k, 1)], 1, 1, x.rows, w.lin(key + ".weight"), n, out.ptr, n,
                   bias_ptr=w.f32(key + ".bias").data_ptr() if bias else 0,
-                  residual_ptr=residual.ptr if residual is not None else 0, ldr=n)
+                  residual_ptr=residual.ptr if residual is not None else 0, ldr=n,
+                  tile_n=LN_TILE if stats else 0, parts_out=self._parts(out) if stats else None)
         return out
 
-    def _ff(self, ln: str, ff: str, hs: Buf) -> Buf:
+    def _ff(self, ln: str, ff: str, hs: Buf, stats_next: bool = False) -> Buf:
         """x += FF(LN(x)); diffusers FeedForward/GEGLU (attention.py:171,197 ; motion_module.py:200,216)"""
         w = self.eng.w
         cc = hs.cols
-        n = self.buf(hs.rows, cc)
-        self.layernorm(hs.ptr, hs.rows, cc, w.f32(ln + ".weight"), w.f32(ln + ".bias"), n.ptr)
-        wp, bp = self.eng.geglu(ff + ".net.0.proj")
         gg = self.buf(hs.rows, 4 * cc)
-        self.gemm([(n.ptr, cc, cc, 1)], 1, 1, hs.rows, wp, 8 * cc, gg.ptr, 4 * cc, bias_ptr=bp.data_ptr(),
-                  flags=L.EPI_GEGLU, tile_n=GEGLU_TILE)
-        del n
-        return self._linear(gg, ff + ".net.2", cc, residual=hs)
+        if hs.aux is not None:  # LayerNorm folded into the GEGLU projection (the producer of hs emitted the partials)
+            wp, cs, bp = self.eng.folded(ff + ".net.0.proj", ln, lambda: w.raw(ff + ".net.0.proj.weight"),
+                                         ff + ".net.0.proj.bias", geglu=True)
+            self.gemm([(hs.ptr, cc, cc, 1)], 1, 1, hs.rows, wp, 8 * cc, gg.ptr, 4 * cc, bias_ptr=bp.data_ptr(),
+                      flags=L.EPI_GEGLU, tile_n=GEGLU_TILE, col_sum_ptr=cs.data_ptr(), parts_in=self._parts(hs))
+        else:
+            n = self.buf(hs.rows, cc)
+            self.layernorm(hs.ptr, hs.rows, cc, w.f32(ln + ".weight"), w.f32(ln + ".bias"), n.ptr)
+            wp, bp = self.eng.geglu(ff + ".net.0.proj")
+            self.gemm([(n.ptr, cc, cc, 1)], 1, 1, hs.rows, wp, 8 * cc, gg.ptr, 4 * cc, bias_ptr=bp.data_ptr(),
+                      flags=L.EPI_GEGLU, tile_n=GEGLU_TILE)
+            del n
+        return self._linear(gg, ff + ".net.2", cc, residual=hs, stats=stats_next)
 
     def _transformer(self, a: str, x: Buf, cc: int, lvl: int, shared: bool = False) -> Buf:
         """Transformer3DModel.forward (attention.py:82-124) + BasicTransformerBlock.forward (:174-199).
@@ -628,19 +704,29 @@ class UNetPlan(Plan):
         nrm = self.buf(rows, cc)
         self.groupnorm(x.ptr, cc, 0, 0, rows, hw, c["norm_num_groups"], w.f32(a + ".norm.weight"),
                        w.f32(a + ".norm.bias"), 1e-6, False, nrm.ptr)
-        hs = self._linear(nrm, a + ".proj_in", cc)
+        hs = self._linear(nrm, a + ".proj_in", cc, stats=self._fold(lvl, cc))
         del nrm
         t = a + ".transformer_blocks.0"
         # self-attention over the h*w tokens of each frame
         n = self.buf(rows, cc)
-        self.layernorm(hs.ptr, rows, cc, w.f32(t + ".norm1.weight"), w.f32(t + ".norm1.bias"), n.ptr)
         qkv = self.buf(rows, 3 * cc)
-        self.gemm([(n.ptr, cc, cc, 1)], 1, 1, rows, eng.qkv(t + ".attn1"), 3 * cc, qkv.ptr, 3 * cc)
+        if hs.aux is not None:
+            a1 = t + ".attn1"
+            wq, cs, bq = eng.folded(a1 + ".qkv", t + ".norm1", lambda: torch.cat(
+                [w.raw(a1 + ".to_q.weight"), w.raw(a1 + ".to_k.weight"), w.raw(a1 + ".to_v.weight")]))
+            self.gemm([(hs.ptr, cc, cc, 1)], 1, 1, rows, wq, 3 * cc, qkv.ptr, 3 * cc, bias_ptr=bq.data_ptr(),
+                      col_sum_ptr=cs.data_ptr(), parts_in=self._parts(hs))
+        else:
+            self.layernorm(hs.ptr, rows, cc, w.f32(t + ".norm1.weight"), w.f32(t + ".norm1.bias"), n.ptr)
+            self.gemm([(n.ptr, cc, cc, 1)], 1, 1, rows, eng.qkv(t + ".attn1"), 3 * cc, qkv.ptr, 3 * cc)
         o = n  # reuse
         self.attention(qkv.ptr, qkv.ptr + 2 * cc, qkv.ptr + 4 * cc, o.ptr, 3 * cc, 3 * cc, 3 * cc, cc, self.B * self.F,
                        heads, d, hw, hw)
         del qkv
-        hs2 = self._linear(o, t + ".attn1.to_out.0", cc, residual=hs)
+        cross = bool(c["add_audio_layer"] and self.audio_kv is not None)
+        # the next LayerNorm is norm2 -> to_q (the conditional half only when the first half carries null audio), or
+        # norm3 -> GEGLU projection when there is no audio layer
+        hs2 = self._linear(o, t + ".attn1.to_out.0", cc, residual=hs, stats=self._fold(lvl, cc, halves=cross))
         del o, n, hs
         hs = hs2
         if shared:
@@ -653,9 +739,14 @@ class UNetPlan(Plan):
             off = half * cc * 2  # bytes to the conditional half of an fp16 [rows][cc] buffer
             hoff = 0 if hs.rows == half else off  # a shared (one-element) hidden state serves both halves
             nh = self.buf(half, cc)
-            self.layernorm(hs.ptr + hoff, half, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), nh.ptr)
             qh = self.buf(half, cc)
-            self.gemm([(nh.ptr, cc, cc, 1)], 1, 1, half, w.lin(t + ".attn2.to_q.weight"), cc, qh.ptr, cc)
+            if hs.aux is not None:
+                wq, cs, bq = eng.folded(t + ".attn2.to_q", t + ".norm2", lambda: w.raw(t + ".attn2.to_q.weight"))
+                self.gemm([(hs.ptr + hoff, cc, cc, 1)], 1, 1, half, wq, cc, qh.ptr, cc, bias_ptr=bq.data_ptr(),
+                          col_sum_ptr=cs.data_ptr(), parts_in=self._parts(hs, hoff // (cc * 2)))
+            else:
+                self.layernorm(hs.ptr + hoff, half, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), nh.ptr)
+                self.gemm([(nh.ptr, cc, cc, 1)], 1, 1, half, w.lin(t + ".attn2.to_q.weight"), cc, qh.ptr, cc)
             koff, voff = eng.kv_off[a]
             ldkv = eng.kv_total
             kv_rows = self.F * self.S * ldkv * 2  # bytes to the conditional half of audio_kv
@@ -663,28 +754,39 @@ class UNetPlan(Plan):
                            nh.ptr, cc, ldkv, ldkv, cc, self.F, heads, d, hw, self.S)
             del qh
             hs2 = self.buf(rows, cc)
+            st3 = self._fold(lvl, cc, halves=True)  # norm3 folded into the GEGLU projection: both halves' producers emit partials
+            if st3:
+                self._with_parts(hs2)
+            tn = LN_TILE if st3 else 0
             ob = w.f32(t + ".attn2.to_out.0.bias").data_ptr()
             self.gemm([(nh.ptr, cc, cc, 1)], 1, 1, half, w.lin(t + ".attn2.to_out.0.weight"), cc, hs2.ptr + off, cc,
-                      bias_ptr=ob, residual_ptr=hs.ptr + hoff, ldr=cc)
+                      bias_ptr=ob, residual_ptr=hs.ptr + hoff, ldr=cc, tile_n=tn,
+                      parts_out=self._parts(hs2, half) if st3 else None)
             # unconditional rows: a K = 64 GEMM over zero operands is `bias + residual` in the GEMM's own epilogue
             if getattr(self, "_zero_a", None) is None:
                 self._zero_a = torch.zeros(self._rows(0) // 2, KPAD, dtype=torch.float16, device=eng.device)
                 self._zero_w = torch.zeros(max(c["block_out_channels"]), KPAD, dtype=torch.float16, device=eng.device)
             self.gemm([(self._zero_a.data_ptr(), KPAD, KPAD, 1)], 1, 1, half, self._zero_w[:cc], cc, hs2.ptr, cc,
-                      bias_ptr=ob, residual_ptr=hs.ptr, ldr=cc)
+                      bias_ptr=ob, residual_ptr=hs.ptr, ldr=cc, tile_n=tn, parts_out=self._parts(hs2) if st3 else None)
             del nh, hs
             hs = hs2
         elif c["add_audio_layer"] and self.audio_kv is not None:
             # cross-attention: frame f attends to its own S audio tokens (attention.py:183-194)
             n = self.buf(rows, cc)
-            self.layernorm(hs.ptr, rows, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), n.ptr)
-            q = self._linear(n, t + ".attn2.to_q", cc, bias=False)
+            if hs.aux is not None:
+                wq, cs, bq = eng.folded(t + ".attn2.to_q", t + ".norm2", lambda: w.raw(t + ".attn2.to_q.weight"))
+                q = self.buf(rows, cc)
+                self.gemm([(hs.ptr, cc, cc, 1)], 1, 1, rows, wq, cc, q.ptr, cc, bias_ptr=bq.data_ptr(),
+                          col_sum_ptr=cs.data_ptr(), parts_in=self._parts(hs))
+            else:
+                self.layernorm(hs.ptr, rows, cc, w.f32(t + ".norm2.weight"), w.f32(t + ".norm2.bias"), n.ptr)
+                q = self._linear(n, t + ".attn2.to_q", cc, bias=False)
             koff, voff = eng.kv_off[a]
             ldkv = eng.kv_total
             self.attention(q.ptr, self.audio_kv.ptr + 2 * koff, self.audio_kv.ptr + 2 * voff, n.ptr, cc, ldkv, ldkv,
                            cc, self.B * self.F, heads, d, hw, self.S)
             del q
-            hs2 = self._linear(n, t + ".attn2.to_out.0", cc, residual=hs)
+            hs2 = self._linear(n, t + ".attn2.to_out.0", cc, residual=hs, stats=self._fold(lvl, cc, halves=True))
             del n, hs
             hs = hs2
         hs = self._ff(t + ".norm3", t + ".ff", hs)
@@ -713,7 +815,11 @@ class UNetPlan(Plan):
         nrm = self.buf(rows, cc)
         self.groupnorm(x.ptr, cc, 0, 0, rows, hw, c["norm_num_groups"], w.f32(t + ".norm.weight"),
                        w.f32(t + ".norm.bias"), 1e-6, False, nrm.ptr)
-        hs = self._linear(nrm, t + ".proj_in", cc)
+        def has_pe(ab: str) -> bool:
+            return w.has(ab + ".pos_encoder.pe")
+
+        hs = self._linear(nrm, t + ".proj_in", cc,
+                          stats=self._fold(lvl, cc, has_pe(f"{t}.transformer_blocks.0.attention_blocks.0")))
         del nrm
         addr = (hw, self.F * hw, 1, hw)
         i = 0
@@ -730,18 +836,31 @@ class UNetPlan(Plan):
                     pe = w.t[name]
                     assert pe.shape[0] == self.F, "more frames than temporal_position_encoding_max_len"
                 n = self.buf(rows, cc)
-                self.layernorm(hs.ptr, rows, cc, w.f32(f"{blk}.norms.{k}.weight"), w.f32(f"{blk}.norms.{k}.bias"),
-                               n.ptr, pe=pe, rows_per_frame=hw, nframes=self.F)
                 qkv = self.buf(rows, 3 * cc)
-                self.gemm([(n.ptr, cc, cc, 1)], 1, 1, rows, eng.qkv(ab), 3 * cc, qkv.ptr, 3 * cc)
+                if hs.aux is not None:
+                    # (LN(x) + pe[frame]) W^T: the sinusoid term becomes one bias row per (batch element, frame)
+                    wq, cs, bq = eng.folded(ab + ".qkv", f"{blk}.norms.{k}", lambda: torch.cat(
+                        [w.raw(ab + ".to_q.weight"), w.raw(ab + ".to_k.weight"), w.raw(ab + ".to_v.weight")]),
+                        pe=pe, repeat=self.B)
+                    self.gemm([(hs.ptr, cc, cc, 1)], 1, 1, rows, wq, 3 * cc, qkv.ptr, 3 * cc, bias_ptr=bq.data_ptr(),
+                              bias_div=hw if pe is not None else 0, bias_ld=3 * cc if pe is not None else 0,
+                              col_sum_ptr=cs.data_ptr(), parts_in=self._parts(hs))
+                else:
+                    self.layernorm(hs.ptr, rows, cc, w.f32(f"{blk}.norms.{k}.weight"), w.f32(f"{blk}.norms.{k}.bias"),
+                                   n.ptr, pe=pe, rows_per_frame=hw, nframes=self.F)
+                    self.gemm([(n.ptr, cc, cc, 1)], 1, 1, rows, eng.qkv(ab), 3 * cc, qkv.ptr, 3 * cc)
                 self.attention(qkv.ptr, qkv.ptr + 2 * cc, qkv.ptr + 4 * cc, n.ptr, 3 * cc, 3 * cc, 3 * cc, cc,
                                self.B * hw, heads, d, self.F, self.F, q_addr=addr, kv_addr=addr)
                 del qkv
-                hs2 = self._linear(n, ab + ".to_out.0", cc, residual=hs)
+                nxt = f"{blk}.attention_blocks.{k + 1}"
+                st = self._fold(lvl, cc, has_pe(nxt)) if w.has(nxt + ".to_q.weight") else self._fold(lvl, cc)
+                hs2 = self._linear(n, ab + ".to_out.0", cc, residual=hs, stats=st)
                 del n, hs
                 hs = hs2
                 k += 1
-            hs = self._ff(blk + ".ff_norm", blk + ".ff", hs)
+            nxt = f"{t}.transformer_blocks.{i + 1}"
+            hs = self._ff(blk + ".ff_norm", blk + ".ff", hs, stats_next=w.has(nxt + ".ff_norm.weight") and self._fold(
+                lvl, cc, has_pe(nxt + ".attention_blocks.0")))
             i += 1
         return self._linear(hs, t + ".proj_out", cc, residual=x)
 

@@ -256,6 +256,98 @@ def test_layernorm_and_pe(C):
     assert rel_l2(out, ref2) < 1e-3
 
 
+@pytest.mark.parametrize("M,C,N,mode,pair", [(33000, 320, 960, "plain", 1), (33000, 320, 960, "plain", 2),
+                                             (1000, 640, 640, "plain", 0), (2048, 1280, 3840, "plain", 0),
+                                             (33000, 320, 2560, "geglu", 0), (2048, 1280, 10240, "geglu", 2),
+                                             (32768, 320, 960, "pe", 0), (8192, 640, 1920, "pe", 2)])
+def test_layernorm_folded_into_gemm(M, C, N, mode, pair):
+    """nn.LayerNorm -> nn.Linear (attention.py:176-186,196-197; motion_module.py:208-216,232-234) with NO LayerNorm pass:
+    the GEMM that produces x (bias + residual epilogue) emits per-row (sum, sum of squares) partials of the fp16 values
+    it stores, the consuming GEMM runs on the raw x with W diag(gamma) and applies
+    out = rstd (x W'^T) - rstd mean col_sum + (beta W^T + bias) in its epilogue (before the GEGLU gate; with the temporal
+    sinusoid table as a per-frame bias row).  33000 rows: >= 3 tiles per CTA (the epilogue groups take alternate tiles)
+    and a ragged last tile; 1000 / 2048 rows: both groups share every tile."""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(21)
+    K0 = 320
+    a0 = torch.randn(M, K0, generator=g).half().to(DEV)
+    w0 = (torch.randn(C, K0, generator=g) / K0 ** 0.5).half().to(DEV)
+    b0 = (0.7 + 0.2 * torch.randn(C, generator=g)).to(DEV)  # row mean comparable to the spread
+    res = (torch.randn(M, C, generator=g) * 1.5).half().to(DEV)
+    x = torch.empty(M, C, dtype=torch.float16, device=DEV)
+    nparts = 3 * (C // 160)
+    parts = torch.full((nparts, M, 2), float("nan"), dtype=torch.float32, device=DEV)
+    L.gemm([L.Seg(a0, K0, K0, 1)], 1, 1, M, w0, C, x, C, bias=b0, residual=res, ldr=C, tile_n=160, cta_pair=pair,
+           row_partials_out=parts)
+    xf = x.float()
+    want = a0.float() @ w0.float().t() + b0 + res.float()
+    assert rel_l2(x, want) < 1e-3
+    assert not torch.isnan(parts).any()
+    # (the sums are taken before the rounding to fp16: they match the stored values to the rounding noise of C halves)
+    assert torch.allclose(parts[..., 0].sum(0), xf.sum(1), atol=5e-2, rtol=1e-4)
+    assert torch.allclose(parts[..., 1].sum(0), (xf * xf).sum(1), rtol=5e-4)
+    with pytest.raises(RuntimeError):  # the part count is part of the contract
+        L.gemm([L.Seg(a0, K0, K0, 1)], 1, 1, M, w0, C, x, C, bias=b0, tile_n=128, row_partials_out=parts)
+
+    w = (torch.randn(N, C, generator=g) / C ** 0.5).to(DEV)
+    bias = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.3 * torch.randn(C, generator=g)).to(DEV)
+    ln = F.layer_norm(xf, (C,), gamma, beta, 1e-5)
+    flags, tile, n_out, bias_div, bias_ld = 0, 0, N, 0, 0
+    if mode == "pe":
+        Fr = 16
+        hw = M // (2 * Fr)
+        pe = torch.randn(Fr, C, generator=g).to(DEV)
+        wg, cs, b2 = L.fold_layernorm(w, bias, gamma, beta, pe=pe)
+        b2 = b2.repeat(2, 1).contiguous()  # one bias row per (batch element, frame)
+        bias_div, bias_ld = hw, N
+        ref = (ln.reshape(2, Fr, hw, C) + pe[None, :, None, :]).reshape(M, C) @ w.t() + bias
+    else:
+        wg, cs, b2 = L.fold_layernorm(w, bias, gamma, beta)
+        ref = ln @ w.t() + bias
+    if mode == "geglu":
+        wg, b2 = L.pack_geglu(wg, b2, 256)
+        cs = L.pack_geglu(cs[:, None], None, 256)[0][:, 0].contiguous()
+        ref = ref[:, : N // 2] * F.gelu(ref[:, N // 2:])
+        n_out, flags, tile = N // 2, L.EPI_GEGLU, 256
+    out = torch.empty(M, n_out, dtype=torch.float16, device=DEV)
+    L.gemm([L.Seg(x, C, C, 1)], 1, 1, M, wg.contiguous(), N, out, n_out, bias=b2, bias_div=bias_div, bias_ld=bias_ld,
+           flags=flags, tile_n=tile, cta_pair=pair, col_sum=cs, row_partials_in=parts)
+    assert rel_l2(out, ref) < 2e-3
+    out2 = torch.empty_like(out)
+    L.gemm([L.Seg(x, C, C, 1)], 1, 1, M, wg.contiguous(), N, out2, n_out, bias=b2, bias_div=bias_div, bias_ld=bias_ld,
+           flags=flags, tile_n=tile, cta_pair=pair, col_sum=cs, row_partials_in=parts)
+    assert torch.equal(out, out2)
+
+
+def test_layernorm_partials_from_two_launches():
+    """the rows of one activation may come from two producer launches (the classifier-free-guidance halves of the audio
+    cross-attention, engine.py): part-major layout with an explicit stride; the consumer may also read a row range"""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(23)
+    M, C, N = 4096, 640, 640
+    half = M // 2
+    a0 = torch.randn(M, C, generator=g).half().to(DEV)
+    w0 = (torch.randn(C, C, generator=g) / C ** 0.5).half().to(DEV)
+    x = torch.empty(M, C, dtype=torch.float16, device=DEV)
+    parts = torch.full((3 * (C // 160), M, 2), float("nan"), dtype=torch.float32, device=DEV)
+    for e in range(2):
+        L.gemm([L.Seg(a0[e * half:], C, C, 1)], 1, 1, half, w0, C, x[e * half:], C, tile_n=160,
+               row_partials_out=parts[:, e * half:(e + 1) * half])
+    xf = x.float()
+    assert torch.allclose(parts[..., 0].sum(0), xf.sum(1), atol=5e-2, rtol=1e-4)
+    w = (torch.randn(N, C, generator=g) / C ** 0.5).to(DEV)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.3 * torch.randn(C, generator=g)).to(DEV)
+    wg, cs, b2 = L.fold_layernorm(w, None, gamma, beta)
+    out = torch.empty(half, N, dtype=torch.float16, device=DEV)
+    L.gemm([L.Seg(x[half:], C, C, 1)], 1, 1, half, wg, N, out, N, bias=b2, col_sum=cs,
+           row_partials_in=parts[:, half:])
+    ref = F.layer_norm(xf[half:], (C,), gamma, beta, 1e-5) @ w.t()
+    assert rel_l2(out, ref) < 2e-3
+
+
 def test_softmax_and_transpose():
     L = _ops()
     g = torch.Generator(device="cpu").manual_seed(11)
