@@ -113,6 +113,18 @@ typedef struct LsGemmArgs {
   float* row_partials_out;
   int32_t n_partials_out;
   int64_t partials_out_stride;
+  /* nn.GroupNorm statistics from the epilogue of the GEMM that PRODUCES the normalised tensor (resnet.py:185,207;
+   * attention.py:96; motion_module.py:139 - the reference runs a reduction pass over the tensor for each of them):
+   *   gn_partials_out: fp32 [M / 128][gn_partials_ld][2]; entry (t, u) = (sum, sum of squares) over output rows
+   *   [128 t, 128 t + 128) and output columns [gn_unit u, gn_unit (u + 1)) of the fp16 values this launch stores.
+   * gn_unit = the largest column count that divides the channels-per-group of every GroupNorm reading the tensor (also
+   * of a concatenation it is part of).  Needs M % 128 == 0, N % gn_unit == 0, the staged fp16 epilogue without SiLU /
+   * GEGLU, and a tile width with N % tile_n == 0 and tile_n % gn_unit == 0 (the automatic choice honours this; an
+   * explicit tile_n must).  Summation order is fixed and independent of the launch geometry (deterministic, and
+   * identical for any split of the rows over several launches).  No split-K.  ls_groupnorm_parts consumes the array. */
+  float* gn_partials_out;
+  int32_t gn_unit;
+  int32_t gn_partials_ld;
 } LsGemmArgs;
 
 int ls_gemm(const LsGemmArgs* args, void* stream);
@@ -138,6 +150,14 @@ int ls_groupnorm_apply(const void* x1, int32_t c1, const void* x2, int32_t c2, i
 int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t c2, int64_t rows, int32_t rows_per_inst,
                  int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu, float* stats_scratch,
                  void* y, void* stream);
+/* GroupNorm (+ SiLU) whose statistics come from the GEMM(s) that produced x1 / x2 (LsGemmArgs.gn_partials_out: parts =
+ * fp32 [rows / 128][ld][2] per `unit` columns, first tile = the tile of row 0 of x): no reduction pass over the tensor, no
+ * cross-CTA rendezvous - each CTA sums the partials of its instance's groups in a fixed order and makes one
+ * read-modify-write pass.  rows_per_inst % 128 == 0; `unit` divides (c1 + c2) / groups and c1.  parts2 / ld2 belong to x2.
+ * Replaces nn.GroupNorm exactly like ls_groupnorm (resnet.py:185-187,207-215; attention.py:96; motion_module.py:139). */
+int ls_groupnorm_parts(const void* x1, int32_t c1, const float* parts1, int32_t ld1, const void* x2, int32_t c2,
+                       const float* parts2, int32_t ld2, int64_t rows, int32_t rows_per_inst, int32_t groups, int32_t unit,
+                       const float* gamma, const float* beta, float eps, int32_t silu, void* y, void* stream);
 /* LayerNorm over C (nn.LayerNorm defaults, attention.py:145,157,172; motion_module.py:195,201), optionally adding
  * the temporal sinusoidal table pe[frame][C] (motion_module.py:232-234) with frame = (row / rows_per_frame) % nframes.
  * pe may be NULL. */
@@ -257,6 +277,19 @@ int ls_restore_faces(const LsRestoreArgs* args, void* stream);
  *   y[b][n] = act_out( sum_k act_in(x[b][k]) * W[n][k] + bias[n] ) (+ add[n]);  x, y, bias, add fp32; W fp16. */
 int ls_small_linear(const float* x, int32_t B, int32_t K, const void* W, const float* bias, const float* add,
                     int32_t N, int32_t silu_in, int32_t silu_out, float* y, void* stream);
+/* ---------------------------------------------------------------------------------------------------------
+ * Whisper-tiny front end: the encoder itself is ls_gemm / ls_layernorm / ls_attention
+ * launches (latentsync_b200/whisper.py); these are its two layout helpers.
+ * ------------------------------------------------------------------------------------------------------- */
+/* nn.Conv1d(kernel 3, padding 1, stride 1 or 2) as a GEMM operand (latentsync/whisper/whisper/model.py:133-134,149-150):
+ * x fp16 [n][T][C] -> y fp16 [n][To][3][C], To = (T - 1) / stride + 1 (zeros outside the sequence). */
+int ls_im2col1d(const void* x, int32_t n, int32_t T, int32_t C, int32_t stride, void* y, void* stream);
+/* Audio2Feature.get_sliced_feature for all video frames in one launch (latentsync/whisper/audio2feature.py:24-48,
+ * 85-100): out[i][k * L + l][:] = layers[l][clamp(first[i] + k, 0, T - 1)][:] for k < K, l < L.  layers fp16
+ * [L][layer_stride][C] (the embedding and every block output of the encoder), first int32 [n] (device), out fp16 or
+ * fp32 (out_f32 != 0) [n][K * L][C]. */
+int ls_whisper_chunks(const void* layers, int64_t layer_stride, int32_t L, int32_t T, int32_t C, const int32_t* first,
+                      int32_t n, int32_t K, int32_t out_f32, void* out, void* stream);
 /* sinusoidal timestep embedding (diffusers get_timestep_embedding, flip_sin_to_cos=True, shift=0): out fp32 [B][dim] */
 int ls_timestep_embedding(const float* t, int32_t B, int32_t dim, float* out, void* stream);
 int ls_fill_zero(void* p, int64_t bytes, void* stream);

@@ -54,6 +54,9 @@ class LsGemmArgs(C.Structure):
         ("row_partials_out", C.c_void_p),
         ("n_partials_out", C.c_int32),
         ("partials_out_stride", C.c_int64),
+        ("gn_partials_out", C.c_void_p),
+        ("gn_unit", C.c_int32),
+        ("gn_partials_ld", C.c_int32),
     ]
 
 
@@ -119,6 +122,8 @@ SYMBOLS = {
     "ls_groupnorm_stats": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
     "ls_groupnorm_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _i32, _vp, _vp]),
     "ls_groupnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp]),
+    "ls_groupnorm_parts": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _f32, _i32,
+                                     _vp, _vp]),
     "ls_layernorm": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp]),
     "ls_attention": (C.c_int, [C.POINTER(LsAttnArgs), _vp]),
     "ls_softmax_rows": (C.c_int, [_vp, _i64, _i32, _f32, _vp, _vp]),
@@ -137,6 +142,8 @@ SYMBOLS = {
     "ls_small_linear": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "ls_timestep_embedding": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "ls_fill_zero": (C.c_int, [_vp, _i64, _vp]),
+    "ls_im2col1d": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ls_whisper_chunks": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
     "ls_restore_faces": (C.c_int, [C.POINTER(LsRestoreArgs), _vp]),
 }
 
@@ -227,9 +234,16 @@ def gemm(
     row_partials_in: Optional[torch.Tensor] = None,
     row_partials_out: Optional[torch.Tensor] = None,
     ln_eps: float = 1e-5,
+    gn_partials_out: Optional[torch.Tensor] = None,
+    gn_unit: int = 0,
 ) -> None:
-    """row_partials_in / row_partials_out: fp32 [parts, rows, 2] (LsGemmArgs: LayerNorm folded into the consuming GEMM)"""
+    """row_partials_in / row_partials_out: fp32 [parts, rows, 2] (LsGemmArgs: LayerNorm folded into the consuming GEMM);
+    gn_partials_out: fp32 [rows / 128, N / gn_unit (or more), 2] (GroupNorm statistics from this GEMM's epilogue)"""
     a = LsGemmArgs()
+    if gn_partials_out is not None:
+        t = gn_partials_out
+        assert t.dtype == torch.float32 and t.dim() == 3 and t.stride(2) == 1 and t.stride(1) == 2 and t.stride(0) % 2 == 0
+        a.gn_partials_out, a.gn_unit, a.gn_partials_ld = _ptr(t), gn_unit, t.stride(0) // 2
     a.col_sum = _ptr(col_sum)
     for name, t in (("in", row_partials_in), ("out", row_partials_out)):
         if t is not None:  # [parts, rows, 2], possibly a row range of a larger [parts, all_rows, 2] array
@@ -300,6 +314,17 @@ def groupnorm_fused(x1, c1, x2, c2, rows, rows_per_inst, groups, gamma, beta, ep
         lib().ls_groupnorm(_ptr(x1), c1, _ptr(x2), c2, rows, rows_per_inst, groups, _ptr(gamma), _ptr(beta), eps,
                            int(silu), _ptr(stats), _ptr(out), _stream()),
         "ls_groupnorm",
+    )
+
+
+def groupnorm_parts(x1, c1, parts1, x2, c2, parts2, rows, rows_per_inst, groups, unit, gamma, beta, eps, silu, out) -> None:
+    """parts: fp32 [rows / 128, >= c / unit, 2] written by the GEMM(s) that produced x (gemm(gn_partials_out=...))"""
+    ld1 = parts1.stride(0) // 2
+    ld2 = parts2.stride(0) // 2 if parts2 is not None else 0
+    _check(
+        lib().ls_groupnorm_parts(_ptr(x1), c1, _ptr(parts1), ld1, _ptr(x2), c2, _ptr(parts2), ld2, rows, rows_per_inst,
+                                 groups, unit, _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(out), _stream()),
+        "ls_groupnorm_parts",
     )
 
 

@@ -65,6 +65,7 @@ constexpr int WSLAB_BYTES = 32 * 64;           // one warp's share of a slab: 32
 constexpr int STAGING_BYTES = 8 * 2 * WSLAB_BYTES;  // 8 epilogue warps x (32 rows x 128 bytes): a pair of slabs each
 constexpr int BIAS_BYTES = 2 * 256 * 4;        // one bias row of 256 floats per epilogue group
 constexpr int COLSUM_BYTES = 2 * 256 * 4;      // folded-LayerNorm launches: one col_sum row per epilogue group
+constexpr int GN_SM_BYTES_PER_COL = 2 * 4 * 8;  // LN == 3: float2 column sums [2 slots][4 row quarters][BN]
 constexpr int ACC_COLS = 256;                  // TMEM columns per accumulator
 constexpr int TMEM_COLS = 512;                 // two accumulators: the whole TMEM (one CTA per SM anyway)
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -142,6 +143,10 @@ struct GemmKParams {
   // values stored into slab range k of n-tile nt
   float2* ln_out;
   int64_t ln_out_stride;
+  // GroupNorm statistics of the OUTPUT (LsGemmArgs.gn_partials_out, LN == 3): per 128-row tile and per `gn_unit` consecutive
+  // output columns the (sum, sum of squares) of the fp16 values stored, gn_out[(m0 / 128) * gn_ld + column / gn_unit]
+  float2* gn_out;
+  int gn_unit, gn_ld, gn_upt;  // gn_upt = BN / gn_unit: units per tile
 };
 
 // ----------------------------------------------------------------------------------------- pair-mode PTX wrappers
@@ -461,6 +466,44 @@ __device__ __forceinline__ void add_bias32(const GemmKParams& p, int64_t m, int 
   }
 }
 
+
+// ------------------------------------------------------------------------- LN == 3: column sums of a staged slab
+// (sum, sum of squares) over the warp's 32 rows of the fp16 values just staged for the TMA store - exactly the values the
+// consuming GroupNorm will read.  The association is the same for both staging layouts, so that the partials do not depend
+// on how a launch happens to split its slabs: rows 0..15 ascending, rows 16 + (i ^ 1) for i = 0..15, then first + second.
+// Pair layout (128-byte rows, SWIZZLE_128B): lane l owns columns 2l, 2l + 1 of the 64; every load touches one row = 32 banks.
+__device__ __forceinline__ void gn_colsum_pair(const uint8_t* st, int lane, float2* dst) {
+  float s0a = 0.f, s1a = 0.f, q0a = 0.f, q1a = 0.f, s0b = 0.f, s1b = 0.f, q0b = 0.f, q1b = 0.f;
+  const int ch = lane >> 2, sub = (lane & 3) * 4;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int ra = i, rb = 16 + (i ^ 1);
+    const __half2 ha = *reinterpret_cast<const __half2*>(st + ra * 128 + ((ch ^ (ra & 7)) << 4) + sub);
+    const __half2 hb = *reinterpret_cast<const __half2*>(st + rb * 128 + ((ch ^ (rb & 7)) << 4) + sub);
+    const float2 a = __half22float2(ha), b = __half22float2(hb);
+    s0a += a.x; s1a += a.y; q0a = fmaf(a.x, a.x, q0a); q1a = fmaf(a.y, a.y, q1a);
+    s0b += b.x; s1b += b.y; q0b = fmaf(b.x, b.x, q0b); q1b = fmaf(b.y, b.y, q1b);
+  }
+  *reinterpret_cast<float4*>(dst + 2 * lane) = make_float4(s0a + s0b, q0a + q0b, s1a + s1b, q1a + q1b);
+}
+// Single-slab layout (64-byte rows, SWIZZLE_64B): lane l owns columns 2 (l & 15), + 1 over the row half l >> 4; the two
+// halves read rows of opposite parity (different 16-bank halves), then meet by one shuffle.
+__device__ __forceinline__ void gn_colsum_single(const uint8_t* st, int lane, float2* dst) {
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const int cp = lane & 15, hi = lane >> 4;
+  const int ch = cp >> 2, sub = (cp & 3) * 4;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = hi ? 16 + (i ^ 1) : i;
+    const __half2 h = *reinterpret_cast<const __half2*>(st + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4) + sub);
+    const float2 a = __half22float2(h);
+    s0 += a.x; s1 += a.y; q0 = fmaf(a.x, a.x, q0); q1 = fmaf(a.y, a.y, q1);
+  }
+  const float t0 = __shfl_xor_sync(0xffffffffu, s0, 16), t1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+  const float u0 = __shfl_xor_sync(0xffffffffu, q0, 16), u1 = __shfl_xor_sync(0xffffffffu, q1, 16);
+  if (hi == 0) *reinterpret_cast<float4*>(dst + 2 * cp) = make_float4(s0 + t0, q0 + u0, s1 + t1, q1 + u1);
+}
+
 // ----------------------------------------------------------------------------------------------------- kernel body
 // GEGLU is a template parameter: the plain instantiation carries no gate accumulator (161 instead of 168 registers - 168
 // is the limit with 10 warps, 3 on one SM sub-partition).  Tried on top of it and dropped: keeping the NEXT slab's
@@ -469,7 +512,8 @@ __device__ __forceinline__ void add_bias32(const GemmKParams& p, int64_t m, int 
 // producer / issuer loops at every split tried: 224/64, 208/96, 200/112, 192/128).
 // LN selects the folded-LayerNorm epilogues (separate instantiations: the plain kernels do not pay for them - the first
 // version of this fold, round 1, put the code into every launch and lost more there than the LayerNorm kernels cost):
-//   0 plain;  1 consumer: per-row scale / shift from the producer's partials;  2 producer: emits the partials.
+//   0 plain;  1 consumer: per-row scale / shift from the producer's partials;  2 producer: emits the partials;
+//   3 GroupNorm producer: per 128-row tile and column unit the (sum, sum of squares) of the stored values (gn_out).
 template <int CTAS, bool GEGLU, int LN>
 __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   const int BN = p.BN;
@@ -494,6 +538,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint64_t* b_full = tmem_empty + 3;  // weight-resident mode: the B tile has landed (8 bytes after the TMEM slot)
   float* colsum_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 192);  // LN == 1 launches only
+  float2* gn_sm = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full_bar) + 192);     // LN == 3 launches only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1241,6 +1286,13 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
                            (int)(m0 + q * 32));
               bulk_commit_group();
             }
+            if constexpr (LN == 3) {
+              // column sums of what was just staged (the store only reads the buffer) -> this quarter's row of gn_sm.
+              // Host: N % BN == 0, so a pair is never cut short by the end of N.
+              float2* grow = gn_sm + (size_t)((alt ? group : 0) * 4 + q) * BN;
+              if (single) gn_colsum_single(my_stage, lane, grow + j * 32);
+              else gn_colsum_pair(my_stage, lane, grow + (j - 1) * 32);
+            }
           }
         }
         }
@@ -1257,6 +1309,29 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             for (int k = 0; k < 3; ++k)
               if (own[k]) dst[(int64_t)k * p.ln_out_stride] = make_float2(ln_su[k], ln_sq[k]);
           }
+        }
+        if constexpr (LN == 3) {
+          // tile-level reduction of the column sums: quarters in order, then the columns of each unit in order.  With
+          // alternate tiles a group owns its tile (and its slot of gn_sm); otherwise both groups share the tile.
+          const int nthr = alt ? 128 : 256;
+          const int tid = alt ? gtid : warp * 32 + lane;
+          float2* base = gn_sm + (size_t)(alt ? group : 0) * 4 * BN;
+          if (alt) named_bar_sync(1 + group, 128); else named_bar_sync(3, 256);
+          for (int c = tid; c < BN; c += nthr) {
+            const float2 a = base[c], b = base[BN + c], c2 = base[2 * BN + c], d = base[3 * BN + c];
+            base[c] = make_float2(((a.x + b.x) + c2.x) + d.x, ((a.y + b.y) + c2.y) + d.y);
+          }
+          if (alt) named_bar_sync(1 + group, 128); else named_bar_sync(3, 256);
+          if (tid < p.gn_upt && tile_ok) {
+            float su = 0.f, sq = 0.f;
+            const float2* src = base + tid * p.gn_unit;
+            for (int i = 0; i < p.gn_unit; ++i) {
+              su += src[i].x;
+              sq += src[i].y;
+            }
+            p.gn_out[(m0 >> 7) * (int64_t)p.gn_ld + nt * p.gn_upt + tid] = make_float2(su, sq);
+          }
+          if (!alt) named_bar_sync(3, 256);  // the other group must not start the next tile's sums before these reads
         }
         named_bar_sync(1 + group, 128);  // every warp of the group has read the bias row: the next tile may overwrite it
         if (!released) {  // group had no slab inside N for this tile: still hand the accumulator back
@@ -1372,13 +1447,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   gemm_body<2, GEGLU, LN>(p);
 }
 typedef void (*GemmKernelFn)(const GemmKParams);
-// [CTAS - 1][geglu][LN]; a GEGLU projection never produces LayerNorm partials (its output feeds a Linear)
+// [CTAS - 1][geglu][LN]; a GEGLU projection never produces LayerNorm / GroupNorm partials (its output feeds a Linear)
 static GemmKernelFn gemm_kernel_of(int ctas, bool geglu, int ln) {
-  static const GemmKernelFn tab[2][2][3] = {
-      {{gemm_tc_kernel<false, 0>, gemm_tc_kernel<false, 1>, gemm_tc_kernel<false, 2>},
-       {gemm_tc_kernel<true, 0>, gemm_tc_kernel<true, 1>, nullptr}},
-      {{gemm_tc_pair_kernel<false, 0>, gemm_tc_pair_kernel<false, 1>, gemm_tc_pair_kernel<false, 2>},
-       {gemm_tc_pair_kernel<true, 0>, gemm_tc_pair_kernel<true, 1>, nullptr}}};
+  static const GemmKernelFn tab[2][2][4] = {
+      {{gemm_tc_kernel<false, 0>, gemm_tc_kernel<false, 1>, gemm_tc_kernel<false, 2>, gemm_tc_kernel<false, 3>},
+       {gemm_tc_kernel<true, 0>, gemm_tc_kernel<true, 1>, nullptr, nullptr}},
+      {{gemm_tc_pair_kernel<false, 0>, gemm_tc_pair_kernel<false, 1>, gemm_tc_pair_kernel<false, 2>,
+        gemm_tc_pair_kernel<false, 3>},
+       {gemm_tc_pair_kernel<true, 0>, gemm_tc_pair_kernel<true, 1>, nullptr, nullptr}}};
   return tab[ctas - 1][geglu ? 1 : 0][ln];
 }
 
@@ -1525,10 +1601,11 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   const int sms = num_sms();
   const bool geglu = (a->flags & LS_EPI_GEGLU) != 0;
   // folded LayerNorm (see LsGemmArgs): 1 = this GEMM consumes the producer's row partials, 2 = it produces them
-  const int ln_mode = a->row_partials_in != nullptr ? 1 : (a->row_partials_out != nullptr ? 2 : 0);
+  // ... 3 = it produces GroupNorm partials of its output (gn_partials_out)
+  const int ln_mode = a->row_partials_in != nullptr ? 1 : (a->row_partials_out != nullptr ? 2 : (a->gn_partials_out != nullptr ? 3 : 0));
   if (ln_mode != 0) {
-    LS_CHECK(a->row_partials_in == nullptr || a->row_partials_out == nullptr,
-             "ls_gemm: a GEMM either consumes or produces LayerNorm partials, not both");
+    LS_CHECK((a->row_partials_in != nullptr) + (a->row_partials_out != nullptr) + (a->gn_partials_out != nullptr) == 1,
+             "ls_gemm: a GEMM consumes LayerNorm partials, produces them, or produces GroupNorm partials - one of the three");
     LS_CHECK(p.tma_store && a->N % 32 == 0 && !p.b_batched,
              "ls_gemm: LayerNorm partials need the staged fp16 epilogue (ldo %% 8 == 0, contiguous rows), N %% 32 == 0, no batching");
   }
@@ -1544,6 +1621,12 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     LS_CHECK(!geglu && !(a->flags & LS_EPI_SILU) && a->partials_out_stride >= M &&
                  (reinterpret_cast<uintptr_t>(a->row_partials_out) & 7) == 0,
              "ls_gemm: row_partials_out needs a plain (bias / residual) epilogue and stride >= M");
+  }
+  if (ln_mode == 3) {
+    LS_CHECK(!geglu && !(a->flags & LS_EPI_SILU) && M % BM == 0 && a->gn_unit >= 1 && a->N % a->gn_unit == 0 &&
+                 a->gn_partials_ld >= a->N / a->gn_unit && (reinterpret_cast<uintptr_t>(a->gn_partials_out) & 7) == 0,
+             "ls_gemm: gn_partials_out needs a plain (bias / residual) epilogue, M %% 128 == 0, N %% gn_unit == 0, "
+             "gn_partials_ld >= N / gn_unit");
   }
   static int env_ctas = -1;
   if (env_ctas < 0) {
@@ -1572,6 +1655,8 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
       if (a->tile_n != 0 && bn != a->tile_n) continue;
       if (geglu && (a->N % bn != 0)) continue;
       if (bn > 32 && bn - 32 >= a->N && a->tile_n == 0) continue;  // wider than the problem
+      // GroupNorm partials: whole units per tile, and no tile cut short by the end of N
+      if (ln_mode == 3 && (a->N % bn != 0 || bn % a->gn_unit != 0)) continue;
       for (int sp = 1; sp <= 8; ++sp) {
         if (env_split >= 2 && split_ok && ctas == 1 && sp != env_split && p.num_kb >= 4 * env_split) continue;  // forced
         if (sp > 1) {
@@ -1610,6 +1695,12 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.ln_inv_k = 1.0f / (float)ktot;
   p.ln_out = reinterpret_cast<float2*>(a->row_partials_out);
   p.ln_out_stride = a->partials_out_stride;
+  if (ln_mode == 3) {
+    p.gn_out = reinterpret_cast<float2*>(a->gn_partials_out);
+    p.gn_unit = a->gn_unit;
+    p.gn_ld = a->gn_partials_ld;
+    p.gn_upt = BN / a->gn_unit;
+  }
   if (best_split > 1) {
     int dev = 0;
     LS_CUDA(cudaGetDevice(&dev));
@@ -1695,7 +1786,8 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   p.kbs = (env_kbs == 1 || env_kbs == 2) ? env_kbs : LS_GEMM_DEFAULT_KBS;
   if (p.kb_per < 4) p.kbs = 1;
   const int stage_bytes = p.kbs * (A_STAGE_BYTES + (BN / CTAS) * 128);
-  int fixed = STAGING_BYTES + BIAS_BYTES + 192 + (ln_mode == 1 ? COLSUM_BYTES : 0);  // + 21 mbarriers and the TMEM slot
+  int fixed = STAGING_BYTES + BIAS_BYTES + 192 + (ln_mode == 1 ? COLSUM_BYTES : 0) +
+              (ln_mode == 3 ? GN_SM_BYTES_PER_COL * BN : 0);  // + 21 mbarriers and the TMEM slot
   int stages = (SMEM_BUDGET - fixed) / stage_bytes;
   // Weight-resident mode for short-K launches whose whole B tile fits beside an A ring (K = 320 at BN = 160: 100 KB): the
   // grid is trimmed to a multiple of n_tiles so that CTA c only ever sees n-tile c % n_tiles.  LS_GEMM_BRES=0 disables.
@@ -1762,7 +1854,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   if (!attr_set) {
     for (int c = 1; c <= 2; ++c)
       for (int g = 0; g < 2; ++g)
-        for (int l = 0; l < 3; ++l)
+        for (int l = 0; l < 4; ++l)
           if (GemmKernelFn fn = gemm_kernel_of(c, g != 0, l))
             LS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     attr_set = true;

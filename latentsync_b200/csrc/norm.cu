@@ -393,6 +393,155 @@ __global__ void __launch_bounds__(256, 3) gn_fused_kernel(const __half* __restri
 
 
 // -------------------------------------------------------------------------------------------------------------
+// GroupNorm from the producer's partials: the GEMM that wrote x also wrote, per 128-row tile and per `unit` columns, the
+// (sum, sum of squares) of what it stored (LsGemmArgs.gn_partials_out).  No statistics pass over the tensor and no
+// cross-CTA rendezvous: every CTA sums the few partials of its instance's groups (fixed order: deterministic), then makes
+// ONE read-modify-write pass over its rows.  grid = (chunks * csplit, instances): a CTA owns a row chunk and 1 / csplit of
+// the channels (whole groups), so that wide concatenations do not make every CTA read every partial.
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) gn_parts_kernel(const __half* __restrict__ x1, int c1, const float2* __restrict__ p1,
+                                                          int ld1, const __half* __restrict__ x2, int c2,
+                                                          const float2* __restrict__ p2, int ld2, int rows_per_inst,
+                                                          int rows_per_chunk, int groups, int unit, int csplit,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, int silu, __half* __restrict__ y) {
+  pdl_prologue();
+  __shared__ float s_stats[64];
+  const int C = c1 + c2;
+  const int cg = C / groups;
+  const int upg = cg / unit;       // units per group
+  const int cs = (int)blockIdx.x % csplit;
+  const int chunk = (int)blockIdx.x / csplit;
+  const int Cl = C / csplit;       // this CTA's channels [cbeg, cbeg + Cl): whole groups, whole 8-channel vectors
+  const int cbeg = cs * Cl;
+  const int g0 = cbeg / cg, ng = Cl / cg;
+  const int inst = blockIdx.y;
+  const int tpi = rows_per_inst >> 7;  // 128-row tiles per instance
+  const int u1 = c1 / unit;            // units of the first source
+  // (1) statistics: tpg threads per group (a power of two, all of them inside one warp) take the group's tiles
+  //     part, part + tpg, ... x its units into four interleaved chains - every load of the CTA is in flight at once - then
+  //     chains and threads are folded in a fixed order
+  {
+    int tpg = 32;
+    while (tpg > 1 && tpg * ng > (int)blockDim.x) tpg >>= 1;
+    const int gi = (int)threadIdx.x / tpg, part = (int)threadIdx.x % tpg;
+    float su[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (gi < ng) {
+      const int ug0 = (g0 + gi) * upg;
+      const float2* b1 = p1 + (int64_t)inst * tpi * ld1;
+      const float2* b2 = p2 + (int64_t)inst * tpi * ld2 - u1;
+      // chain k takes the tiles part + (8 i + k) tpg: eight (x upg) independent loads per trip, static register indices
+      int t = part;
+      for (; t + 7 * tpg < tpi; t += 8 * tpg)
+        for (int ul = 0; ul < upg; ++ul) {
+          const int ug = ug0 + ul;
+          float2 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int64_t tt = t + k * tpg;
+            v[k] = (ug < u1) ? __ldg(b1 + tt * ld1 + ug) : __ldg(b2 + tt * ld2 + ug);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            su[k] += v[k].x;
+            sq[k] += v[k].y;
+          }
+        }
+      for (; t < tpi; t += tpg)
+        for (int ul = 0; ul < upg; ++ul) {
+          const int ug = ug0 + ul;
+          const float2 v = (ug < u1) ? __ldg(b1 + (int64_t)t * ld1 + ug) : __ldg(b2 + (int64_t)t * ld2 + ug);
+          su[0] += v.x;
+          sq[0] += v.y;
+        }
+    }
+    float a = ((su[0] + su[1]) + (su[2] + su[3])) + ((su[4] + su[5]) + (su[6] + su[7]));
+    float b = ((sq[0] + sq[1]) + (sq[2] + sq[3])) + ((sq[4] + sq[5]) + (sq[6] + sq[7]));
+    for (int o = tpg >> 1; o >= 1; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (gi < ng && part == 0) {
+      s_stats[2 * gi] = a;
+      s_stats[2 * gi + 1] = b;
+    }
+  }
+  __syncthreads();
+  // (2) one pass: thread = (row lane, 8-channel vector), scale / shift of its vector in registers
+  const int nvec = Cl >> 3;
+  const int RL = (nvec <= (int)blockDim.x) ? (int)blockDim.x / nvec : 1;
+  const int rl = (nvec <= (int)blockDim.x) ? (int)threadIdx.x / nvec : 0;
+  const int cv0 = (nvec <= (int)blockDim.x) ? (int)threadIdx.x % nvec : (int)threadIdx.x;
+  const int cvstep = (nvec <= (int)blockDim.x) ? nvec : (int)blockDim.x;
+  const int64_t row0 = (int64_t)inst * rows_per_inst + (int64_t)chunk * rows_per_chunk;
+  int64_t row_end = row0 + rows_per_chunk;
+  const int64_t inst_end = (int64_t)(inst + 1) * rows_per_inst;
+  if (row_end > inst_end) row_end = inst_end;
+  const float inv_n = 1.f / ((float)rows_per_inst * (float)cg);
+  if (rl < RL) {
+    for (int cv = cv0; cv < nvec; cv += cvstep) {
+      const int c = cbeg + cv * 8;
+      float sa8[8], sb8[8];
+      {
+        const float4 ga0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 ga1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float4 be0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float4 be1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        const float ga[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
+        const float be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int gi = (c + e) / cg - g0;
+          const float mean = s_stats[2 * gi] * inv_n;
+          float var = s_stats[2 * gi + 1] * inv_n - mean * mean;
+          var = fmaxf(var, 0.f);
+          sa8[e] = rsqrtf(var + eps) * ga[e];
+          sb8[e] = be[e] - mean * sa8[e];
+        }
+      }
+      const __half* src = (c < c1) ? (x1 + c) : (x2 + (c - c1));
+      const int ld = (c < c1) ? c1 : c2;
+      auto apply_store = [&](const uint4& u, int64_t row) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+        uint4 w;
+        __half2* o2 = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          float a = f.x * sa8[2 * e] + sb8[2 * e];
+          float b = f.y * sa8[2 * e + 1] + sb8[2 * e + 1];
+          if (silu) {
+            a = silu_f(a);
+            b = silu_f(b);
+          }
+          o2[e] = __floats2half2_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>(y + row * C + c) = w;
+      };
+      int64_t row = row0 + rl;
+      for (; row + 7 * RL < row_end; row += 8 * RL) {
+        uint4 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row + k * RL) * ld));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) apply_store(u[k], row + k * RL);
+      }
+      for (; row + 1 * RL < row_end; row += 2 * RL) {
+        uint4 u[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row + k * RL) * ld));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) apply_store(u[k], row + k * RL);
+      }
+      for (; row < row_end; row += RL) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + row * ld));
+        apply_store(u, row);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // Cluster GroupNorm: one thread-block CLUSTER per instance.  Every CTA copies its rows ONCE into shared memory
 // (cp.async, the whole chunk in flight), reduces them there, the CTAs exchange their 64 (group, stat) partials through
 // distributed shared memory behind a hardware cluster barrier, and each CTA normalises its rows from shared memory.
@@ -1044,6 +1193,56 @@ extern "C" int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t 
   LS_CUDA(launch_coop_k(gn_fused_kernel, dim3(chunks, ninst), dim3(threads), smem, (cudaStream_t)stream,
                    (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, rpc, groups, sc.partial(), sc.tickets(),
                    gamma, beta, eps, silu, (__half*)y));
+  LS_CUDA(cudaGetLastError());
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// GroupNorm (+ SiLU) of the virtual concatenation [x1 | x2] from the partials their producing GEMMs wrote
+// (LsGemmArgs.gn_partials_out): no statistics pass, no rendezvous, one launch.
+extern "C" int ls_groupnorm_parts(const void* x1, int32_t c1, const float* parts1, int32_t ld1, const void* x2, int32_t c2,
+                                  const float* parts2, int32_t ld2, int64_t rows, int32_t rows_per_inst, int32_t groups,
+                                  int32_t unit, const float* gamma, const float* beta, float eps, int32_t silu, void* y,
+                                  void* stream) {
+  if (!x2) c2 = 0;
+  const int C = c1 + c2;
+  LS_CHECK(x1 && parts1 && gamma && beta && y && rows > 0 && rows_per_inst > 0 && rows % rows_per_inst == 0 &&
+               (c2 == 0 || parts2 != nullptr),
+           "ls_groupnorm_parts: bad args");
+  LS_CHECK(groups > 0 && groups <= 32 && C % groups == 0 && C % 8 == 0 && c1 % 8 == 0,
+           "ls_groupnorm_parts: C=%d groups=%d unsupported", C, groups);
+  const int cg = C / groups;
+  LS_CHECK(rows_per_inst % 128 == 0 && unit >= 1 && cg % unit == 0 && c1 % unit == 0 && ld1 >= c1 / unit &&
+               (c2 == 0 || ld2 >= c2 / unit),
+           "ls_groupnorm_parts: rows_per_inst %d must be a multiple of 128, unit %d must divide C / groups = %d and c1 = %d",
+           rows_per_inst, unit, cg, c1);
+  LS_CHECK((reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
+           "ls_groupnorm_parts: gamma / beta must be 16-byte aligned");
+  // channel split: whole groups and whole 8-channel vectors per CTA, at least 240 channels each
+  int csplit = 1;
+  for (int s2 = 8; s2 > 1; s2 >>= 1) {
+    if (C % s2 != 0) continue;
+    const int cl = C / s2;
+    if (cl >= 240 && cl % cg == 0 && cl % 8 == 0) {
+      csplit = s2;
+      break;
+    }
+  }
+  // one wave of three CTAs per SM: with more, the second round pays the per-CTA latency chain (partials -> scale / shift
+  // -> first loads) again
+  int ninst, chunks, rpc;
+  int dev = 0, sms = 148;
+  LS_CUDA(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int target = 3 * sms / csplit;
+  gn_chunking(rows, rows_per_inst, target < 1 ? 1 : target, ninst, chunks, rpc);
+  while (chunks > 1 && (int64_t)chunks * csplit * ninst > 3 * sms) {  // gn_chunking rounds up: stay inside the wave
+    rpc += 1;
+    chunks = (rows_per_inst + rpc - 1) / rpc;
+  }
+  LS_CUDA(launch_k(gn_parts_kernel, dim3(chunks * csplit, ninst), dim3(256), (size_t)0, (cudaStream_t)stream,
+                   (const __half*)x1, c1, (const float2*)parts1, ld1, (const __half*)x2, c2, (const float2*)parts2, ld2,
+                   rows_per_inst, rpc, groups, unit, csplit, gamma, beta, eps, silu, (__half*)y));
   LS_CUDA(cudaGetLastError());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return 0;

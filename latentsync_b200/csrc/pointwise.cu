@@ -389,21 +389,33 @@ extern "C" int ls_preprocess_u8(const void* img, int32_t n, int32_t H, int32_t W
 
 // torchvision resize(face, (oh, ow), antialias=True) [= aten::_upsample_bilinear2d_aa, align_corners = false] followed
 // by (x / 2 + 0.5).clamp(0, 1) * 255 -> uint8 and "c h w -> h w c" (lipsync_pipeline.py:350-355).
-// Separable triangle filter whose support grows with the down-scale factor; weights normalised per output index.
+// BYTE-exact restatement of that operator's CPU kernel for float tensors (oracle/resize_ref.py states the arithmetic and is
+// pinned to torch itself): separable triangle filter, horizontal pass first into a float32 value, a pass whose size does
+// not change is skipped; window and weights in the operator's own mixed float / double arithmetic, weights normalised
+// by a float DIVISION; and the accumulation order of the x86 builds with FMA: first tap a plain product, the next
+// 4 floor((n - 1) / 4) taps product and sum rounded separately (gcc vectorises ATen's loop four taps at a time with an
+// in-order reduction), the remaining taps fused.  __fmul_rn / __fadd_rn / __fmaf_rn keep nvcc from re-contracting.
 __device__ __forceinline__ void aa_window(int i, float scale, int in_size, int& lo, int& size, float& center,
                                           float& invscale) {
-  const float support = scale >= 1.0f ? scale : 1.0f;  // interp_size / 2 * scale, interp_size = 2
-  center = scale * ((float)i + 0.5f);
-  invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
-  lo = max((int)(center - support + 0.5f), 0);
-  size = min((int)(center + support + 0.5f), in_size) - lo;
+  const float support = scale >= 1.0f ? scale : 1.0f;  // (interp_size * 0.5) * scale, interp_size = 2
+  center = (float)((double)scale * ((double)i + 0.5));
+  invscale = scale >= 1.0f ? (float)(1.0 / (double)scale) : 1.0f;
+  const int max_interp = (int)ceilf(support) * 2 + 1;
+  lo = max((int)((double)(center - support) + 0.5), 0);
+  size = min((int)((double)(center + support) + 0.5), in_size) - lo;
+  size = min(max(size, 0), max_interp);
 }
 __device__ __forceinline__ float aa_weight(int j, int lo, float center, float invscale) {
-  const float x = fabsf(((float)(j + lo) - center + 0.5f) * invscale);
-  return x < 1.0f ? 1.0f - x : 0.0f;
+  const float t = (float)(j + lo) - center;                       // int64 - float -> float in the operator
+  const float x = fabsf((float)(((double)t + 0.5) * (double)invscale));
+  return x < 1.0f ? (float)(1.0 - (double)x) : 0.0f;
+}
+// acc <- next tap, in the operator's order (see above): j = tap index >= 1, nv = 4 floor((n - 1) / 4)
+__device__ __forceinline__ float aa_acc(float acc, float s, float w, int j, int nv) {
+  return j <= nv ? __fadd_rn(acc, __fmul_rn(s, w)) : __fmaf_rn(s, w, acc);
 }
 
-constexpr int AA_MAX_TAPS = 16;  // support of a 7x down-scale
+constexpr int AA_MAX_TAPS = 17;  // 2 ceil(scale) + 1: down-scales up to 8x
 
 __global__ void resize_aa_u8_kernel(const float* __restrict__ x, int n, int H, int W, int oh, int ow, float sy,
                                     float sx, uint8_t* __restrict__ out) {
@@ -414,30 +426,48 @@ __global__ void resize_aa_u8_kernel(const float* __restrict__ x, int n, int H, i
   const int ox = (int)(idx % ow);
   const int oy = (int)((idx / ow) % oh);
   const int64_t i = idx / ((int64_t)ow * oh);
-  int xlo, xn, ylo, yn;
-  float xc, xi, yc, yi;
-  aa_window(ox, sx, W, xlo, xn, xc, xi);
-  aa_window(oy, sy, H, ylo, yn, yc, yi);
-  xn = min(xn, AA_MAX_TAPS);
-  yn = min(yn, AA_MAX_TAPS);
-  float wx[AA_MAX_TAPS];
-  float wxs = 0.f, wys = 0.f;
-  for (int j = 0; j < xn; ++j) {
-    wx[j] = aa_weight(j, xlo, xc, xi);
-    wxs += wx[j];
+  const bool hpass = (ow != W), vpass = (oh != H);
+  int xlo = ox, xn = 1, ylo = oy, yn = 1;
+  float xc = 0.f, xi = 1.f, yc = 0.f, yi = 1.f;
+  float wx[AA_MAX_TAPS], wy[AA_MAX_TAPS];
+  wx[0] = wy[0] = 1.0f;
+  if (hpass) {
+    aa_window(ox, sx, W, xlo, xn, xc, xi);
+    xn = min(xn, AA_MAX_TAPS);
+    float tot = 0.f;
+    for (int j = 0; j < xn; ++j) {
+      wx[j] = aa_weight(j, xlo, xc, xi);
+      tot = __fadd_rn(tot, wx[j]);
+    }
+    if (tot != 0.f)
+      for (int j = 0; j < xn; ++j) wx[j] = __fdiv_rn(wx[j], tot);
   }
-  for (int j = 0; j < yn; ++j) wys += aa_weight(j, ylo, yc, yi);
-  const float wxn = wxs != 0.f ? 1.0f / wxs : 0.f, wyn = wys != 0.f ? 1.0f / wys : 0.f;
+  if (vpass) {
+    aa_window(oy, sy, H, ylo, yn, yc, yi);
+    yn = min(yn, AA_MAX_TAPS);
+    float tot = 0.f;
+    for (int j = 0; j < yn; ++j) {
+      wy[j] = aa_weight(j, ylo, yc, yi);
+      tot = __fadd_rn(tot, wy[j]);
+    }
+    if (tot != 0.f)
+      for (int j = 0; j < yn; ++j) wy[j] = __fdiv_rn(wy[j], tot);
+  }
+  const int xnv = ((xn - 1) / 4) * 4, ynv = ((yn - 1) / 4) * 4;
   for (int c = 0; c < 3; ++c) {
     const float* plane = x + (i * 3 + c) * (int64_t)H * W;
     float acc = 0.f;
     for (int r = 0; r < yn; ++r) {
       const float* row = plane + (int64_t)(ylo + r) * W + xlo;
-      float h = 0.f;  // horizontal pass first, like the separable ATen kernel
-      for (int j = 0; j < xn; ++j) h += row[j] * (wx[j] * wxn);
-      acc += h * (aa_weight(r, ylo, yc, yi) * wyn);
+      float h = row[0];
+      if (hpass) {  // horizontal pass of this input row (the operator's float32 temporary)
+        h = __fmul_rn(row[0], wx[0]);
+        for (int j = 1; j < xn; ++j) h = aa_acc(h, row[j], wx[j], j, xnv);
+      }
+      if (!vpass) acc = h;
+      else acc = (r == 0) ? __fmul_rn(h, wy[0]) : aa_acc(acc, h, wy[r], r, ynv);
     }
-    const float v = fminf(fmaxf(acc / 2.0f + 0.5f, 0.0f), 1.0f) * 255.0f;
+    const float v = __fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(acc, 0.5f), 0.5f), 0.0f), 1.0f), 255.0f);
     out[idx * 3 + c] = (uint8_t)v;  // truncation, as tensor.to(torch.uint8)
   }
 }
@@ -446,7 +476,7 @@ extern "C" int ls_resize_aa_u8(const float* x, int32_t n, int32_t H, int32_t W, 
                                void* stream) {
   LS_CHECK(x && out && n > 0 && H > 0 && W > 0 && oh > 0 && ow > 0, "ls_resize_aa_u8: bad args");
   const float sy = (float)H / (float)oh, sx = (float)W / (float)ow;
-  LS_CHECK(2.f * (sy > 1.f ? sy : 1.f) + 1.f <= (float)AA_MAX_TAPS && 2.f * (sx > 1.f ? sx : 1.f) + 1.f <= (float)AA_MAX_TAPS,
+  LS_CHECK(2.f * ceilf(sy > 1.f ? sy : 1.f) + 1.f <= (float)AA_MAX_TAPS && 2.f * ceilf(sx > 1.f ? sx : 1.f) + 1.f <= (float)AA_MAX_TAPS,
            "ls_resize_aa_u8: down-scale factor beyond %d taps", AA_MAX_TAPS);
   const int64_t total = (int64_t)n * oh * ow;
   LS_CUDA(launch_k(resize_aa_u8_kernel, dim3(blocks_for(total, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, x, n,
@@ -477,6 +507,93 @@ extern "C" int ls_small_linear(const float* x, int32_t B, int32_t K, const void*
 extern "C" int ls_timestep_embedding(const float* t, int32_t B, int32_t dim, float* out, void* stream) {
   LS_CHECK(t && out && B > 0 && dim % 2 == 0, "ls_timestep_embedding: bad args");
   LS_CUDA(launch_k(timestep_embedding_kernel, dim3(blocks_for((int64_t)B * dim, 128)), dim3(128), (size_t)(0), (cudaStream_t)((cudaStream_t)stream), t, B, dim, out));
+  LS_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------- Whisper front end helpers
+// nn.Conv1d(kernel_size = 3, padding = 1, stride s) as a GEMM (latentsync/whisper/whisper/model.py:133-134,149-150):
+// x fp16 [n][T][C] -> y fp16 [n][To][3][C], To = (T - 1) / s + 1, tap k of output t reads input s t - 1 + k (zero outside)
+__global__ void im2col1d_kernel(const __half* __restrict__ x, int n, int T, int C, int stride, int To,
+                                __half* __restrict__ y) {
+  pdl_prologue();
+  const int nvec = C >> 3;
+  const int64_t total = (int64_t)n * To * 3 * nvec;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % nvec);
+    int64_t r = idx / nvec;
+    const int k = (int)(r % 3);
+    r /= 3;
+    const int to = (int)(r % To);
+    const int i = (int)(r / To);
+    const int ti = stride * to - 1 + k;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (ti >= 0 && ti < T) u = *reinterpret_cast<const uint4*>(x + ((int64_t)i * T + ti) * C + v * 8);
+    *reinterpret_cast<uint4*>(y + (((int64_t)i * To + to) * 3 + k) * C + v * 8) = u;
+  }
+}
+
+extern "C" int ls_im2col1d(const void* x, int32_t n, int32_t T, int32_t C, int32_t stride, void* y, void* stream) {
+  LS_CHECK(x && y && n > 0 && T > 0 && C % 8 == 0 && (stride == 1 || stride == 2), "ls_im2col1d: bad args");
+  const int To = (T - 1) / stride + 1;
+  const int64_t total = (int64_t)n * To * 3 * (C / 8);
+  unsigned blocks = blocks_for(total, 256);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  LS_CUDA(launch_k(im2col1d_kernel, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __half*)x, n, T, C,
+                   stride, To, (__half*)y));
+  LS_LAUNCHED();
+  return 0;
+}
+
+// Audio2Feature.get_sliced_feature for every video frame at once (latentsync/whisper/audio2feature.py:24-48,85-100):
+// out[i][k * L + l][:] = layers[l][clamp(first[i] + k, 0, T - 1)][:], k < K (the reference's left_idx .. right_idx - 1 with
+// both ends clamped), l < L (the encoder's embedding and block outputs).  layers: fp16 [L][layer_stride rows][C];
+// out: fp16 or fp32 [n][K * L][C].  first[i] = int(i * 50 / fps) - 2 * audio_feat_length[0] is computed by the caller with
+// the reference's own float arithmetic.
+template <typename OutT>
+__global__ void whisper_chunks_kernel(const __half* __restrict__ layers, int64_t layer_stride, int L, int T, int C,
+                                      const int* __restrict__ first, int n, int K, OutT* __restrict__ out) {
+  pdl_prologue();
+  const int nvec = C >> 3;
+  const int64_t total = (int64_t)n * K * L * nvec;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % nvec);
+    int64_t r = idx / nvec;
+    const int l = (int)(r % L);
+    r /= L;
+    const int k = (int)(r % K);
+    const int i = (int)(r / K);
+    int t = first[i] + k;
+    t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+    const uint4 u = *reinterpret_cast<const uint4*>(layers + ((int64_t)l * layer_stride + t) * C + v * 8);
+    OutT* dst = out + (((int64_t)i * K + k) * L + l) * C + v * 8;
+    if constexpr (sizeof(OutT) == 2) {
+      *reinterpret_cast<uint4*>(dst) = u;
+    } else {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+      const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]),
+                   d = __half22float2(h2[3]);
+      *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(c.x, c.y, d.x, d.y);
+    }
+  }
+}
+
+extern "C" int ls_whisper_chunks(const void* layers, int64_t layer_stride, int32_t L, int32_t T, int32_t C,
+                                 const int32_t* first, int32_t n, int32_t K, int32_t out_f32, void* out, void* stream) {
+  LS_CHECK(layers && first && out && L > 0 && T > 0 && C % 8 == 0 && n > 0 && K > 0 && layer_stride >= T,
+           "ls_whisper_chunks: bad args");
+  const int64_t total = (int64_t)n * K * L * (C / 8);
+  unsigned blocks = blocks_for(total, 256);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  if (out_f32)
+    LS_CUDA(launch_k(whisper_chunks_kernel<float>, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)stream,
+                     (const __half*)layers, layer_stride, L, T, C, (const int*)first, n, K, (float*)out));
+  else
+    LS_CUDA(launch_k(whisper_chunks_kernel<__half>, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)stream,
+                     (const __half*)layers, layer_stride, L, T, C, (const int*)first, n, K, (__half*)out));
   LS_LAUNCHED();
   return 0;
 }

@@ -28,6 +28,12 @@ KPAD = 64  # GEMM K granularity (one 128-byte swizzle row of fp16)
 FOLD_LN = os.environ.get("LS_FOLD_LN", "1") != "0"
 FOLD_LN_MIN_ROWS = 2048
 LN_TILE = 160  # tile width of every GEMM that emits partials (the cost model's own choice for N = 320 / 640 / 1280)
+# nn.GroupNorm statistics from the epilogue of the GEMM that produces the normalised tensor (LsGemmArgs.gn_partials_out ->
+# ls_groupnorm_parts): the norm becomes one read-modify-write pass without a reduction pass or a grid rendezvous.
+# LS_GN_PARTS=0 keeps the self-contained kernels (A/B measurements).  Levels with < GN_PARTS_MIN_ROWS rows keep them too
+# (their convolutions are split-K and the tensors are latency-, not bandwidth-bound).
+GN_PARTS = os.environ.get("LS_GN_PARTS", "1") != "0"
+GN_PARTS_MIN_ROWS = 2048
 
 
 def ln_parts(n: int) -> int:
@@ -54,6 +60,12 @@ class _Pool:
         self.all.append(t)
         return t
 
+    def fresh(self, nbytes: int) -> torch.Tensor:
+        """storage that no earlier launch of the plan has ever written (never taken from the free lists)"""
+        t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.all.append(t)
+        return t
+
     def give(self, t: torch.Tensor) -> None:
         self.free.setdefault(t.numel(), []).append(t)
 
@@ -64,15 +76,17 @@ class _Pool:
 class Buf:
     """[rows, cols] device matrix handle; closures recorded in a plan capture only `.ptr` (an int)."""
 
-    __slots__ = ("pool", "store", "ptr", "rows", "cols", "dtype", "aux")
+    __slots__ = ("pool", "store", "ptr", "rows", "cols", "dtype", "aux", "gnp", "gnu")
 
-    def __init__(self, pool: _Pool, rows: int, cols: int, dtype=torch.float16):
+    def __init__(self, pool: _Pool, rows: int, cols: int, dtype=torch.float16, fresh: bool = False):
         self.pool = pool
         self.aux = None  # fp32 [ln_parts(cols)][rows][2] LayerNorm partials written by the GEMM(s) that produced this buffer
+        self.gnp = None  # fp32 [rows / 128][cols / gnu][2] GroupNorm partials written by the producing GEMM(s)
+        self.gnu = 0     # columns per GroupNorm partial
         self.rows, self.cols, self.dtype = rows, cols, dtype
         nbytes = rows * cols * torch.empty((), dtype=dtype).element_size()
         nbytes = (nbytes + 255) // 256 * 256
-        self.store = pool.take(nbytes)
+        self.store = pool.fresh(nbytes) if fresh else pool.take(nbytes)
         self.ptr = self.store.data_ptr()
 
     def __del__(self):
@@ -120,7 +134,10 @@ class Plan:
         return Buf(self.pool, rows, cols, dtype)
 
     def static(self, rows, cols, dtype=torch.float16) -> Buf:
-        b = Buf(self.pool, rows, cols, dtype)
+        """a buffer that lives as long as the plan (inputs, outputs, zero-padded operands).  Always FRESH storage: a
+        recycled block may still be the target of launches recorded earlier in the plan, which would overwrite what the
+        builder puts here now (e.g. the zero padding columns of a narrow GEMM output) when the plan runs."""
+        b = Buf(self.pool, rows, cols, dtype, fresh=True)
         self.keep.append(b)
         return b
 
@@ -240,10 +257,13 @@ class Plan:
              out_ptr: int, ldo: int, bias_ptr: int = 0, bias_div: int = 0, bias_ld: int = 0, residual_ptr: int = 0,
              ldr: int = 0, flags: int = 0, tile_n: int = 0, b_batch_stride: int = 0, b_ptr: int = 0,
              col_sum_ptr: int = 0, parts_in: Optional[Tuple[int, int, int]] = None,
-             parts_out: Optional[Tuple[int, int, int]] = None) -> None:
+             parts_out: Optional[Tuple[int, int, int]] = None, gn_out: Optional[Tuple[int, int, int]] = None) -> None:
         """segs: (ptr, channels, ld, taps).  w: packed fp16 [N, Ktot] tensor (kept alive by the engine) or b_ptr.
-        parts_in / parts_out: (pointer to the first row, parts, stride in rows) of LayerNorm partials (LsGemmArgs)."""
+        parts_in / parts_out: (pointer to the first row, parts, stride in rows) of LayerNorm partials (LsGemmArgs).
+        gn_out: (pointer to the first tile, unit, ld) of GroupNorm partials (LsGemmArgs.gn_partials_out)."""
         a = L.LsGemmArgs()
+        if gn_out is not None:
+            a.gn_partials_out, a.gn_unit, a.gn_partials_ld = gn_out
         if parts_in is not None:
             a.row_partials_in, a.n_partials_in, a.partials_in_stride = parts_in
             a.col_sum, a.ln_eps = col_sum_ptr, 1e-5
@@ -277,7 +297,7 @@ class Plan:
         self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_gemm"), "gemm", 2.0 * M * N * ktot,
                    f"M={M} N={N} K={ktot} img={nimg}x{H}x{W} segs={taps} flags={flags} batched={int(b_batch_stride != 0)}"
                    + (" res" if residual_ptr else "") + (" ln=in" if parts_in is not None else "")
-                   + (" ln=out" if parts_out is not None else ""),
+                   + (" ln=out" if parts_out is not None else "") + (" gn=out" if gn_out is not None else ""),
                    float(nbytes))
 
     def begin_stats(self, nfloats: int) -> None:
@@ -298,6 +318,42 @@ class Plan:
         self._emit(lambda: _chk(fn(x1, c1, x2p, c2, rows, rows_per_inst, groups, g, b, eps, int(silu), sp, out_ptr,
                                    _stream()), "ls_groupnorm"), "groupnorm", 0.0,
                    f"rows={rows} C={cc} rows_per_inst={rows_per_inst} silu={int(silu)}", 2.0 * rows * cc * 2)
+
+    def groupnorm_parts(self, x1: int, c1: int, p1: int, ld1: int, x2: int, c2: int, p2: int, ld2: int, rows: int,
+                        rows_per_inst: int, groups: int, unit: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                        silu: bool, out_ptr: int) -> None:
+        """GroupNorm from the partials of the producing GEMM(s) (ls_groupnorm_parts)"""
+        fn = self.lib.ls_groupnorm_parts
+        g, b = gamma.data_ptr(), beta.data_ptr()
+        x2p, p2p = (x2 or None), (p2 or None)
+        cc = c1 + c2
+        self._emit(lambda: _chk(fn(x1, c1, p1, ld1, x2p, c2, p2p, ld2, rows, rows_per_inst, groups, unit, g, b, eps,
+                                   int(silu), out_ptr, _stream()), "ls_groupnorm_parts"), "groupnorm", 0.0,
+                   f"rows={rows} C={cc} rows_per_inst={rows_per_inst} silu={int(silu)} parts", 2.0 * rows * cc * 2)
+
+    def gn(self, srcs, rows: int, rows_per_inst: int, groups: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+           silu: bool, out_ptr: int) -> None:
+        """GroupNorm of the virtual concatenation of srcs = [(Buf, channels)] (one or two), rows starting at each
+        buffer's row 0: from the producers' partials when every source carries them, else the self-contained kernel"""
+        (x1, c1) = srcs[0]
+        (x2, c2) = srcs[1] if len(srcs) > 1 else (None, 0)
+        cg = (c1 + c2) // groups
+        unit = x1.gnu
+        if (all(b.gnp is not None and b.gnu == unit for b, _ in srcs) and rows_per_inst % 128 == 0 and unit > 0
+                and (c1 + c2) % groups == 0 and cg % unit == 0 and c1 % unit == 0):
+            self.groupnorm_parts(x1.ptr, c1, x1.gnp.ptr, x1.cols // unit, x2.ptr if x2 is not None else 0, c2,
+                                 x2.gnp.ptr if x2 is not None else 0, (x2.cols // unit) if x2 is not None else 0, rows,
+                                 rows_per_inst, groups, unit, gamma, beta, eps, silu, out_ptr)
+        else:
+            self.groupnorm(x1.ptr, c1, x2.ptr if x2 is not None else 0, c2, rows, rows_per_inst, groups, gamma, beta, eps,
+                           silu, out_ptr)
+
+    def with_gn_parts(self, out: Buf, unit: int) -> Tuple[int, int, int]:
+        """attach a GroupNorm-partials array to `out`; returns the gn_out argument of the GEMM that writes all of it"""
+        assert out.rows % 128 == 0 and out.cols % unit == 0
+        out.gnp = self.buf(out.rows // 128, (out.cols // unit) * 2, torch.float32)
+        out.gnu = unit
+        return (out.gnp.ptr, unit, out.cols // unit)
 
     def layernorm(self, x: int, rows: int, Cc: int, gamma: torch.Tensor, beta: torch.Tensor, out_ptr: int,
                   pe: Optional[torch.Tensor] = None, rows_per_frame: int = 1, nframes: int = 1) -> None:
@@ -591,6 +647,19 @@ class UNetPlan(Plan):
         if self.debug:
             self.taps[name] = (x, lvl)
 
+    def _gn_unit(self, lvl: int, n: int) -> int:
+        """columns per GroupNorm partial for a block-level tensor of level `lvl` and width `n` whose producing GEMM emits
+        the statistics of its output, or 0: that level keeps the self-contained GroupNorm kernels.  Like `_fold` the
+        decision depends on the level's full-batch geometry only, so that plan variants stay bit-identical."""
+        c = self.eng.cfg
+        unit = c["block_out_channels"][0] // c["norm_num_groups"]  # divides C / groups of every norm, concatenations included
+        h, wd = self._geo(lvl)
+        per_b = self.F * h * wd
+        if (not GN_PARTS or self._full_B * per_b < GN_PARTS_MIN_ROWS or per_b % 128 != 0 or unit < 1 or n % unit != 0
+                or any(ch % unit for ch in c["block_out_channels"])):
+            return 0
+        return unit if any(n % bn == 0 and bn % unit == 0 for bn in range(32, 257, 32)) else 0
+
     def tap_tensor(self, name: str) -> torch.Tensor:
         """debug: activation `name` as (B, C, F, h, w) fp32"""
         x, lvl = self.taps[name]
@@ -610,27 +679,28 @@ class UNetPlan(Plan):
         x1, c1 = srcs[0]
         x2p, c2 = (srcs[1][0].ptr, srcs[1][1]) if len(srcs) > 1 else (0, 0)
         g, eps = c["norm_num_groups"], c["norm_eps"]
+        gu = self._gn_unit(lvl, cout)  # both convolutions emit the GroupNorm statistics of what they store
         y1 = self.buf(rows, cin)
-        self.groupnorm(x1.ptr, c1, x2p, c2, rows, per_b, g, w.f32(r + ".norm1.weight"), w.f32(r + ".norm1.bias"), eps,
-                       True, y1.ptr)
+        self.gn(srcs, rows, per_b, g, w.f32(r + ".norm1.weight"), w.f32(r + ".norm1.bias"), eps, True, y1.ptr)
         h1 = self.buf(rows, cout)
         toff = eng.tproj_off[r]
         self.gemm([(y1.ptr, cin, cin, 9)], self.B * self.F, h, wd, w.conv(r + ".conv1.weight"), cout, h1.ptr, cout,
-                  bias_ptr=self.tproj.ptr + toff * 4, bias_div=per_b, bias_ld=eng.tproj_total)
+                  bias_ptr=self.tproj.ptr + toff * 4, bias_div=per_b, bias_ld=eng.tproj_total,
+                  gn_out=self.with_gn_parts(h1, gu) if gu else None)
         del y1
         y2 = self.buf(rows, cout)
-        self.groupnorm(h1.ptr, cout, 0, 0, rows, per_b, g, w.f32(r + ".norm2.weight"), w.f32(r + ".norm2.bias"), eps,
-                       True, y2.ptr)
+        self.gn([(h1, cout)], rows, per_b, g, w.f32(r + ".norm2.weight"), w.f32(r + ".norm2.bias"), eps, True, y2.ptr)
         del h1
         out = self.buf(rows, cout)
+        gno = self.with_gn_parts(out, gu) if gu else None
         if w.has(r + ".conv_shortcut.weight"):
             wp, bp = eng.conv2_with_shortcut(r, [ch for _, ch in srcs])
             segs = [(y2.ptr, cout, cout, 9)] + [(b.ptr, ch, ch, 1) for b, ch in srcs]
-            self.gemm(segs, self.B * self.F, h, wd, wp, cout, out.ptr, cout, bias_ptr=bp.data_ptr())
+            self.gemm(segs, self.B * self.F, h, wd, wp, cout, out.ptr, cout, bias_ptr=bp.data_ptr(), gn_out=gno)
         else:
             assert len(srcs) == 1 and c1 == cout
             self.gemm([(y2.ptr, cout, cout, 9)], self.B * self.F, h, wd, w.conv(r + ".conv2.weight"), cout, out.ptr,
-                      cout, bias_ptr=w.f32(r + ".conv2.bias").data_ptr(), residual_ptr=x1.ptr, ldr=cout)
+                      cout, bias_ptr=w.f32(r + ".conv2.bias").data_ptr(), residual_ptr=x1.ptr, ldr=cout, gn_out=gno)
         return out
 
     def _fold(self, lvl: int, cc: int, pe: bool = False, halves: bool = False) -> bool:
@@ -654,19 +724,21 @@ class UNetPlan(Plan):
         return (x.aux.ptr + row0 * 8, ln_parts(x.cols), x.rows)
 
     def _linear(self, x: Buf, key: str, n: int, bias: bool = True, residual: Optional[Buf] = None,
-                stats: bool = False) -> Buf:
+                stats: bool = False, gn: int = 0) -> Buf:
         """`stats`: the output feeds a LayerNorm that is folded into the next GEMM - this GEMM's epilogue emits the
-        per-row partial sums of what it stores (out.aux)"""
+        per-row partial sums of what it stores (out.aux).  `gn` (columns per partial): the output feeds a GroupNorm -
+        the epilogue emits its per-tile statistics (out.gnp)."""
         w = self.eng.w
         k = w.lin(key + ".weight").shape[1]
-        assert k == x.cols
+        assert k == x.cols and not (stats and gn)
         out = self.buf(x.rows, n)
         if stats:
             self._with_parts(out)
         self.gemm([(x.ptr, k, k, 1)], 1, 1, x.rows, w.lin(key + ".weight"), n, out.ptr, n,
                   bias_ptr=w.f32(key + ".bias").data_ptr() if bias else 0,
                   residual_ptr=residual.ptr if residual is not None else 0, ldr=n,
-                  tile_n=LN_TILE if stats else 0, parts_out=self._parts(out) if stats else None)
+                  tile_n=LN_TILE if stats else 0, parts_out=self._parts(out) if stats else None,
+                  gn_out=self.with_gn_parts(out, gn) if gn else None)
         return out
 
     def _ff(self, ln: str, ff: str, hs: Buf, stats_next: bool = False) -> Buf:
@@ -702,8 +774,8 @@ class UNetPlan(Plan):
         heads = c["attention_head_dim"]
         d = cc // heads
         nrm = self.buf(rows, cc)
-        self.groupnorm(x.ptr, cc, 0, 0, rows, hw, c["norm_num_groups"], w.f32(a + ".norm.weight"),
-                       w.f32(a + ".norm.bias"), 1e-6, False, nrm.ptr)
+        self.gn([(x, cc)], rows, hw, c["norm_num_groups"], w.f32(a + ".norm.weight"), w.f32(a + ".norm.bias"), 1e-6,
+                False, nrm.ptr)
         hs = self._linear(nrm, a + ".proj_in", cc, stats=self._fold(lvl, cc))
         del nrm
         t = a + ".transformer_blocks.0"
@@ -795,12 +867,15 @@ class UNetPlan(Plan):
             key = a + ".proj_out"
             out = self.buf(rows, cc)
             half = rows // 2
+            gu = self._gn_unit(lvl, cc)
+            gno = self.with_gn_parts(out, gu) if gu else None
             for e in range(2):
                 o8 = e * half * cc * 2
+                g8 = (gno[0] + e * (half // 128) * gno[2] * 8, gno[1], gno[2]) if gno else None  # tiles of this half
                 self.gemm([(hs.ptr + o8, cc, cc, 1)], 1, 1, half, w.lin(key + ".weight"), cc, out.ptr + o8, cc,
-                          bias_ptr=w.f32(key + ".bias").data_ptr(), residual_ptr=x.ptr, ldr=cc)
+                          bias_ptr=w.f32(key + ".bias").data_ptr(), residual_ptr=x.ptr, ldr=cc, gn_out=g8)
             return out
-        return self._linear(hs, a + ".proj_out", cc, residual=x)
+        return self._linear(hs, a + ".proj_out", cc, residual=x, gn=self._gn_unit(lvl, cc))
 
     def _motion(self, m: str, x: Buf, cc: int, lvl: int) -> Buf:
         """VanillaTemporalModule (motion_module.py:126-151,203-218,262-313).  The "(b f) s c -> (b s) f c" transposes
@@ -813,8 +888,8 @@ class UNetPlan(Plan):
         d = cc // heads
         t = m + ".temporal_transformer"
         nrm = self.buf(rows, cc)
-        self.groupnorm(x.ptr, cc, 0, 0, rows, hw, c["norm_num_groups"], w.f32(t + ".norm.weight"),
-                       w.f32(t + ".norm.bias"), 1e-6, False, nrm.ptr)
+        self.gn([(x, cc)], rows, hw, c["norm_num_groups"], w.f32(t + ".norm.weight"), w.f32(t + ".norm.bias"), 1e-6,
+                False, nrm.ptr)
         def has_pe(ab: str) -> bool:
             return w.has(ab + ".pos_encoder.pe")
 
@@ -862,14 +937,15 @@ class UNetPlan(Plan):
             hs = self._ff(blk + ".ff_norm", blk + ".ff", hs, stats_next=w.has(nxt + ".ff_norm.weight") and self._fold(
                 lvl, cc, has_pe(nxt + ".attention_blocks.0")))
             i += 1
-        return self._linear(hs, t + ".proj_out", cc, residual=x)
+        return self._linear(hs, t + ".proj_out", cc, residual=x, gn=self._gn_unit(lvl, cc))
 
     def _conv3x3(self, key: str, x: Buf, cin: int, cout: int, lvl: int) -> Buf:
         h, wd = self._geo(lvl)
         w = self.eng.w
         out = self.buf(self._rows(lvl), cout)
+        gu = self._gn_unit(lvl, cout)
         self.gemm([(x.ptr, cin, cin, 9)], self.B * self.F, h, wd, w.conv(key + ".weight"), cout, out.ptr, cout,
-                  bias_ptr=w.f32(key + ".bias").data_ptr())
+                  bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=self.with_gn_parts(out, gu) if gu else None)
         return out
 
     # -- whole forward ----------------------------------------------------------------------------------------
@@ -923,8 +999,10 @@ class UNetPlan(Plan):
 
         # conv_in (unet.py:395)
         x = self.buf(rows0, boc[0])
+        gu = self._gn_unit(0, boc[0])
         self.gemm([(self.x_in.ptr, cin_pad, cin_pad, 9)], B * F, self.H, self.W,
-                  w.conv("conv_in.weight"), boc[0], x.ptr, boc[0], bias_ptr=w.f32("conv_in.bias").data_ptr())
+                  w.conv("conv_in.weight"), boc[0], x.ptr, boc[0], bias_ptr=w.f32("conv_in.bias").data_ptr(),
+                  gn_out=self.with_gn_parts(x, gu) if gu else None)
         skips: List[Tuple[Buf, int]] = [(x, boc[0])]
         self._tap("conv_in", x, 0)
         ch = boc[0]
@@ -956,8 +1034,9 @@ class UNetPlan(Plan):
                 self.call("ls_im2col_s2", x.ptr, B * F, h, wd, ch, cols.ptr)
                 key = f"{p}.downsamplers.0.conv"
                 y = self.buf(self._rows(i + 1), ch)
+                gu = self._gn_unit(i + 1, ch)
                 self.gemm([(cols.ptr, 9 * ch, 9 * ch, 1)], 1, 1, self._rows(i + 1), w.conv(key + ".weight"), ch, y.ptr,
-                          ch, bias_ptr=w.f32(key + ".bias").data_ptr())
+                          ch, bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=self.with_gn_parts(y, gu) if gu else None)
                 del cols
                 x = y
                 skips.append((x, ch))
@@ -993,8 +1072,8 @@ class UNetPlan(Plan):
                 del up
         # conv_norm_out -> SiLU -> conv_out (unet.py:464-466)
         y = self.buf(rows0, ch)
-        self.groupnorm(x.ptr, ch, 0, 0, rows0, F * self.H * self.W, c["norm_num_groups"], w.f32("conv_norm_out.weight"),
-                       w.f32("conv_norm_out.bias"), c["norm_eps"], True, y.ptr)
+        self.gn([(x, ch)], rows0, F * self.H * self.W, c["norm_num_groups"], w.f32("conv_norm_out.weight"),
+                w.f32("conv_norm_out.bias"), c["norm_eps"], True, y.ptr)
         self.gemm([(y.ptr, ch, ch, 9)], B * F, self.H, self.W, w.conv("conv_out.weight"), c["out_channels"],
                   self.eps_out.ptr, c["out_channels"], bias_ptr=w.f32("conv_out.bias").data_ptr(), flags=L.EPI_OUT_F32)
         del x, y
@@ -1037,15 +1116,24 @@ class VAEPlan(Plan):
     def _gn(self, key: str, x: Buf, cc: int, hw: int, silu: bool) -> Buf:
         w = self.eng.w
         y = self.buf(x.rows, cc)
-        self.groupnorm(x.ptr, cc, 0, 0, x.rows, hw, self.eng.cfg["norm_num_groups"], w.f32(key + ".weight"),
-                       w.f32(key + ".bias"), 1e-6, silu, y.ptr)
+        self.gn([(x, cc)], x.rows, hw, self.eng.cfg["norm_num_groups"], w.f32(key + ".weight"), w.f32(key + ".bias"),
+                1e-6, silu, y.ptr)
         return y
+
+    def _gn_out(self, out: Buf, hw: int):
+        """gn_out argument of the GEMM that writes `out` when `out` feeds a GroupNorm over hw rows per image (the
+        statistics then come from that GEMM's epilogue, ls_groupnorm_parts), else None"""
+        unit = out.cols // self.eng.cfg["norm_num_groups"]
+        if (not GN_PARTS or hw % 128 != 0 or out.rows % 128 != 0 or unit < 1 or out.cols % unit != 0
+                or not any(out.cols % bn == 0 and bn % unit == 0 for bn in range(32, 257, 32))):
+            return None
+        return self.with_gn_parts(out, unit)
 
     def _conv(self, key: str, x: Buf, cin: int, cout: int, h: int, wd: int) -> Buf:
         w = self.eng.w
         out = self.buf(x.rows, cout)
         self.gemm([(x.ptr, cin, cin, 9)], self.nimg, h, wd, w.conv(key + ".weight"), cout, out.ptr, cout,
-                  bias_ptr=w.f32(key + ".bias").data_ptr())
+                  bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=self._gn_out(out, h * wd))
         return out
 
     def _resnet(self, r: str, x: Buf, cin: int, cout: int, h: int, wd: int) -> Buf:
@@ -1057,21 +1145,22 @@ class VAEPlan(Plan):
         y2 = self._gn(r + ".norm2", h1, cout, h * wd, True)
         del h1
         out = self.buf(x.rows, cout)
+        gno = self._gn_out(out, h * wd)
         if w.has(r + ".conv_shortcut.weight"):
             wp, bp = self.eng.conv_sc(r, cin)
             self.gemm([(y2.ptr, cout, cout, 9), (x.ptr, cin, cin, 1)], self.nimg, h, wd, wp, cout, out.ptr, cout,
-                      bias_ptr=bp.data_ptr())
+                      bias_ptr=bp.data_ptr(), gn_out=gno)
         else:
             self.gemm([(y2.ptr, cout, cout, 9)], self.nimg, h, wd, w.conv(r + ".conv2.weight"), cout, out.ptr, cout,
-                      bias_ptr=w.f32(r + ".conv2.bias").data_ptr(), residual_ptr=x.ptr, ldr=cout)
+                      bias_ptr=w.f32(r + ".conv2.bias").data_ptr(), residual_ptr=x.ptr, ldr=cout, gn_out=gno)
         return out
 
-    def _lin(self, x: Buf, key: str, n: int, residual: Optional[Buf] = None) -> Buf:
+    def _lin(self, x: Buf, key: str, n: int, residual: Optional[Buf] = None, gn_hw: int = 0) -> Buf:
         w = self.eng.w
         out = self.buf(x.rows, n)
         self.gemm([(x.ptr, x.cols, x.cols, 1)], 1, 1, x.rows, w.lin(key + ".weight"), n, out.ptr, n,
                   bias_ptr=w.f32(key + ".bias").data_ptr(), residual_ptr=residual.ptr if residual is not None else 0,
-                  ldr=n)
+                  ldr=n, gn_out=self._gn_out(out, gn_hw) if gn_hw else None)
         return out
 
     def _mid_attention(self, a: str, x: Buf, cc: int, h: int, wd: int) -> Buf:
@@ -1094,7 +1183,7 @@ class VAEPlan(Plan):
         o = self.buf(x.rows, cc)
         self.gemm([(pr.ptr, hw, hw, 1)], self.nimg, 1, hw, None, cc, o.ptr, cc, b_batch_stride=cc * hw, b_ptr=vt.ptr)
         del pr, vt
-        return self._lin(o, a + ".to_out.0", cc, residual=x)
+        return self._lin(o, a + ".to_out.0", cc, residual=x, gn_hw=hw)
 
     def _build(self) -> None:
         eng, w, c = self.eng, self.eng.w, self.eng.cfg
@@ -1179,7 +1268,7 @@ class VAEEncodePlan(VAEPlan):
                 h, wd = h // 2, wd // 2
                 y = self.buf(rows, ch)
                 self.gemm([(cols.ptr, 9 * ch, 9 * ch, 1)], 1, 1, rows, w.conv(key + ".weight"), ch, y.ptr, ch,
-                          bias_ptr=w.f32(key + ".bias").data_ptr())
+                          bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=self._gn_out(y, h * wd))
                 del cols
                 x = y
         x = self._resnet("encoder.mid_block.resnets.0", x, ch, ch, h, wd)

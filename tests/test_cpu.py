@@ -417,3 +417,26 @@ def test_bench_prints_exactly_one_stdout_line():
     lines = res.stdout.splitlines()
     assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "x", "value": 1.5}, res.stdout
     assert "library noise on stdout" in res.stderr and "raw fd 1 noise" in res.stderr
+
+
+def test_resize_oracle_is_pinned_to_torch_itself():
+    """oracle/resize_ref.py restates the CPU kernel of aten::_upsample_bilinear2d_aa - what
+    torchvision.transforms.functional.resize(face, size, antialias=True) runs at lipsync_pipeline.py:350 - operation by
+    operation.  On hosts whose PyTorch dispatches to the FMA builds of that kernel (AVX2 / AVX512) the restatement
+    reproduces torch BIT for bit, up-scaling, down-scaling (windows up to 15 taps) and single-axis passes alike; the
+    GPU kernel is then held to the restatement byte for byte (tests/test_model_gpu.py)."""
+    import numpy as np
+    import torch.nn.functional as F
+
+    from oracle import pipeline_ref as P
+    from oracle import resize_ref as R
+
+    if torch.backends.cpu.get_cpu_capability() not in ("AVX2", "AVX512"):
+        pytest.skip("this host's ATen CPU kernels are built without FMA: another accumulation order")
+    g = torch.Generator().manual_seed(5)
+    for (H, W) in ((256, 256), (96, 160)):
+        x = torch.rand(2, 3, H, W, generator=g) * 2.4 - 1.2
+        for (oh, ow) in ((210, 280), (256, 256), (311, 287), (96, 128), (37, 41), (H, 100), (300, W), (700, 640)):
+            ref = F.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False, antialias=True).numpy()
+            assert np.array_equal(R.resize_aa(x.numpy(), oh, ow), ref), (H, W, oh, ow)
+            assert np.array_equal(R.restore_faces_u8(x.numpy(), oh, ow), P.restore_faces_u8(x, oh, ow).numpy())

@@ -237,6 +237,102 @@ def test_groupnorm(c1, c2, rows_per_inst, ninst, silu):
     assert torch.equal(out2, out3)  # deterministic, and the self-resetting tickets survive a relaunch
 
 
+@pytest.mark.parametrize("M,K,N,unit,pair,conv", [
+    (32768, 320, 320, 10, 1, False),    # level-0 short-K linear: >= 3 tiles per CTA (alternate tiles), 160-wide tiles
+    (32768, 320, 320, 10, 2, False),    # CTA pairs
+    (2048, 1280, 1280, 10, 0, False),   # both epilogue groups share every tile (3 + 2 slabs, trailing single slab)
+    (8192, 640, 640, 10, 0, True),      # 3x3 convolution, 16 x 16 images
+    (4096, 128, 256, 8, 0, False),      # VAE-like: unit 8, any tile width dividing N
+    (16384, 256, 128, 4, 0, True),      # 128-wide tiles, unit 4
+])
+def test_groupnorm_partials_from_gemm_epilogue(M, K, N, unit, pair, conv):
+    """nn.GroupNorm without a statistics pass (resnet.py:185-187,207-215; attention.py:96; motion_module.py:139): the GEMM
+    that produces x writes per 128-row tile and per `unit` columns the (sum, sum of squares) of the fp16 values it stores;
+    ls_groupnorm_parts sums them per (instance, group) and normalises in one pass.  Checked: the partials against the
+    stored tensor, the norm against F.group_norm for per-frame and joint instances, bitwise determinism, and that the
+    partials do not depend on the launch geometry (the same rows produced by two half-size launches)."""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(33)
+    bias = (0.5 + 0.3 * torch.randn(N, generator=g)).to(DEV)
+    res = (torch.randn(M, N, generator=g) * 1.5).half().to(DEV)
+    x = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    U = N // unit
+    parts = torch.full((M // 128, U, 2), float("nan"), dtype=torch.float32, device=DEV)
+    if conv:
+        side = 16
+        nimg = M // (side * side)
+        a = torch.randn(nimg, K, side, side, generator=g).half().to(DEV)
+        w = (torch.randn(N, K, 3, 3, generator=g) / (9 * K) ** 0.5).half().to(DEV)
+        segs, geo, wp = [L.Seg(cl(a), K, K, 9)], (nimg, side, side), pack_conv_w(w)
+        want = cl(F.conv2d(a.float(), w.float(), padding=1)) + bias + res.float()
+    else:
+        a = torch.randn(M, K, generator=g).half().to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).half().to(DEV)
+        segs, geo, wp = [L.Seg(a, K, K, 1)], (1, 1, M), w
+        want = a.float() @ w.float().t() + bias + res.float()
+    L.gemm(segs, *geo, wp, N, x, N, bias=bias, residual=res, ldr=N, cta_pair=pair, gn_partials_out=parts, gn_unit=unit)
+    assert rel_l2(x, want) < 1e-3
+    assert not torch.isnan(parts).any()
+    xf = x.float().reshape(M // 128, 128, U, unit)
+    assert torch.allclose(parts[..., 0], xf.sum((1, 3)), atol=2e-2, rtol=1e-5)
+    assert torch.allclose(parts[..., 1], (xf * xf).sum((1, 3)), rtol=1e-4)
+    # same launch again: bitwise; the two halves of the rows as separate launches (other tile-to-CTA assignment): bitwise
+    parts2 = torch.full_like(parts, float("nan"))
+    x2 = torch.empty_like(x)
+    L.gemm(segs, *geo, wp, N, x2, N, bias=bias, residual=res, ldr=N, cta_pair=pair, gn_partials_out=parts2, gn_unit=unit)
+    assert torch.equal(parts, parts2) and torch.equal(x, x2)
+    if not conv:
+        half = M // 2
+        parts3 = torch.full_like(parts, float("nan"))
+        for e in range(2):
+            L.gemm([L.Seg(a[e * half:], K, K, 1)], 1, 1, half, w, N, x2[e * half:], N, bias=bias, residual=res[e * half:],
+                   ldr=N, gn_partials_out=parts3[e * (half // 128):], gn_unit=unit)
+        assert torch.equal(parts, parts3) and torch.equal(x, x2)
+    # the norm: per-frame-like instances (1024 rows) and one joint instance per half, channels-per-group = N / 32
+    gamma = (1 + 0.2 * torch.randn(N, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(N, generator=g)).to(DEV)
+    for rpi in (1024, M // 2):
+        for silu in (False, True):
+            out = torch.empty_like(x)
+            L.groupnorm_parts(x, N, parts, None, 0, None, M, rpi, 32, unit, gamma, beta, 1e-5, silu, out)
+            ref = F.group_norm(x.float().reshape(M // rpi, rpi, N).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+            ref = (F.silu(ref) if silu else ref).permute(0, 2, 1).reshape(M, N)
+            assert rel_l2(out, ref) < 2e-3
+            out_b = torch.empty_like(x)
+            L.groupnorm_parts(x, N, parts, None, 0, None, M, rpi, 32, unit, gamma, beta, 1e-5, silu, out_b)
+            assert torch.equal(out, out_b)
+    with pytest.raises(RuntimeError):  # an explicit tile width must hold whole units and divide N
+        L.gemm(segs, *geo, wp, N, x2, N, bias=bias, tile_n=96, gn_partials_out=parts2, gn_unit=unit)
+
+
+@pytest.mark.parametrize("c1,c2,rpi,ninst", [(640, 320, 16384, 2), (1280, 640, 1024, 2), (320, 320, 256, 8),
+                                             (1280, 1280, 1024, 2)])
+def test_groupnorm_parts_of_a_virtual_concat(c1, c2, rpi, ninst):
+    """norm1 of the up blocks reads torch.cat([hidden, skip]) (unet_blocks.py:624,745): groups straddle the two sources
+    (960 channels: 30 per group), each source brings the partials of its own producer; wide tensors are split over the
+    channels as well as the rows (csplit)"""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(35)
+    rows, unit = rpi * ninst, 10
+    srcs = []
+    for c in (c1, c2):
+        a = torch.randn(rows, 64, generator=g).half().to(DEV)
+        w = (torch.randn(c, 64, generator=g) / 8).half().to(DEV)
+        b = (0.3 * torch.randn(c, generator=g)).to(DEV)
+        x = torch.empty(rows, c, dtype=torch.float16, device=DEV)
+        parts = torch.empty(rows // 128, c // unit, 2, dtype=torch.float32, device=DEV)
+        L.gemm([L.Seg(a, 64, 64, 1)], 1, 1, rows, w, c, x, c, bias=b, gn_partials_out=parts, gn_unit=unit)
+        srcs.append((x, parts))
+    C = c1 + c2
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    out = torch.empty(rows, C, dtype=torch.float16, device=DEV)
+    L.groupnorm_parts(srcs[0][0], c1, srcs[0][1], srcs[1][0], c2, srcs[1][1], rows, rpi, 32, unit, gamma, beta, 1e-5, True, out)
+    xx = torch.cat([srcs[0][0], srcs[1][0]], 1).float()
+    ref = F.silu(F.group_norm(xx.reshape(ninst, rpi, C).permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+    assert rel_l2(out, ref.reshape(rows, C)) < 2e-3
+
+
 @pytest.mark.parametrize("C", [320, 640, 1280])
 def test_layernorm_and_pe(C):
     L = _ops()
