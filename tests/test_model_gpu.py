@@ -7,6 +7,7 @@ PSNR >= 40 dB.  Operands are fp16 with fp32 accumulation (bf16 op
 """
 import os
 
+import numpy as np
 import pytest
 import torch
 
