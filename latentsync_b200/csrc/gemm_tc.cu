@@ -989,7 +989,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         const bool has_res = (LN != 1) && (p.residual != nullptr);  // a folded-LayerNorm consumer never adds a residual (host)
         auto fetch_res_pair = [&](int s0) {  // slabs j_lo + s0, j_lo + s0 + 1 (or the trailing single slab)
           const int j = j_lo + s0;
-          const int ncol0 = nt * BN + j * 32;
+          const int ncol0 = (geglu ? nt * (BN / 2) : nt * BN) + j * 32;  // output column, as in the slab loop below
           const bool single = (j == j_hi - 1);
           const int64_t mrow0 = m0 + q * 32;
 #pragma unroll

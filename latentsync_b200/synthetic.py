@@ -129,3 +129,27 @@ def restore_case(seed: int, H: int, W: int, scale=(1.2, 1.6), origin=(-20.0, 60.
     o = np.array([rng.uniform(*origin), rng.uniform(*origin)])
     A = np.concatenate([R, (-R @ o)[:, None]], axis=1)
     return frame, face, A
+
+
+def whisper_encoder_state_dict(dims: Dict[str, int], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 CPU state_dict of `Whisper.encoder` with the checkpoint's key names (whisper.encoder_param_spec): same
+    distributions as above (LayerNorm weights U(0.8, 1.2)), `positional_embedding` = the sinusoid buffer of
+    latentsync/whisper/whisper/model.py:48-55"""
+    from .whisper import encoder_param_spec, sinusoids
+
+    sd = {}
+    for name, shape in encoder_param_spec(dims).items():
+        if name.endswith("positional_embedding"):
+            sd[name] = sinusoids(shape[0], shape[1])
+        elif len(shape) == 1:
+            is_ln_w = name.endswith(("_ln.weight", "ln_post.weight"))
+            sd[name] = uniform(seed + 15485863, name, shape, 0.8, 1.2) if is_ln_w else uniform(seed + 15485863, name, shape, -0.1, 0.1)
+        else:
+            a = math.sqrt(3.0 / int(np.prod(shape[1:])))
+            sd[name] = uniform(seed + 15485863, name, shape, -a, a)
+    return sd
+
+
+def mel_like(seed: int, n_mels: int, n_frames: int) -> torch.Tensor:
+    """stand-in for a log-mel spectrogram (whisper/audio.py:120-123 maps it into about [-1, 1.5])"""
+    return (approx_normal(seed, "mel", (n_mels, n_frames)) * 0.5 + 0.2).clamp(-1.0, 1.6)

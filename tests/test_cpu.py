@@ -440,3 +440,42 @@ def test_resize_oracle_is_pinned_to_torch_itself():
             ref = F.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False, antialias=True).numpy()
             assert np.array_equal(R.resize_aa(x.numpy(), oh, ow), ref), (H, W, oh, ow)
             assert np.array_equal(R.restore_faces_u8(x.numpy(), oh, ow), P.restore_faces_u8(x, oh, ow).numpy())
+
+
+def test_whisper_oracle_vs_reference_golden():
+    """oracle/whisper_ref.py against outputs of the reference's OWN modules
+    (latentsync/whisper/whisper/model.py AudioEncoder, latentsync/whisper/audio2feature.py Audio2Feature), generated
+    by oracle/make_golden_whisper.py in the build container"""
+    from latentsync_b200 import synthetic as syn
+    from oracle import whisper_ref as W
+
+    g = torch.load(os.path.join(GOLDEN, "whisper_small.pt"))
+    sd = syn.whisper_encoder_state_dict(g["dims"], seed=g["seed"])
+    mel = torch.stack([syn.mel_like(s, 80, 2 * g["dims"]["n_audio_ctx"]) for s in g["mel_seeds"]])
+    emb = W.encoder_embeddings(sd, g["dims"], mel)
+    assert emb.shape == g["embeddings"].shape
+    assert rel_l2(emb, g["embeddings"].float()) < 5e-4  # the fixture is stored as fp16
+    g = torch.load(os.path.join(GOLDEN, "whisper_tiny.pt"))
+    sd = syn.whisper_encoder_state_dict(g["dims"], seed=g["seed"])
+    emb = W.encoder_embeddings(sd, g["dims"], syn.mel_like(g["mel_seed"], 80, 3000)[None])
+    assert emb.shape == (1, 5, 1500, 384)
+    assert rel_l2(emb[:, :, ::g["stride"]], g["embeddings"]) < 1e-5
+    # window loop: 2.4 windows -> 1500 + 1500 + 600 positions
+    small = {**g["dims"], "n_audio_ctx": 40, "n_audio_layer": 1}
+    sd = syn.whisper_encoder_state_dict(small, seed=1)
+    assert W.audio2feat(sd, small, syn.mel_like(3, 80, 192)).shape == (96, 2, 384)
+    assert W.audio2feat(sd, small, syn.mel_like(3, 80, 191)).shape == (40 + 40 + 15, 2, 384)
+    # slicing: index lists and chunk contents of the reference's get_sliced_feature / feature2chunks
+    c = torch.load(os.path.join(GOLDEN, "whisper_chunks.pt"))
+    feat = syn.approx_normal(c["feat_seed"], "feat", (c["T"], 5, 8))
+    for fps, case in c["cases"].items():
+        fpsv = float(fps) if "." in fps else int(fps)
+        chunks = W.feature2chunks(feat, fpsv)
+        assert len(chunks) == case["n"] and chunks[0].shape == (50, 8)
+        assert [W.sliced_indices(c["T"], i, fpsv) for i in range(case["n"])] == case["idx"]
+        assert abs(torch.stack(chunks).double().sum().item() - case["checksum"]) < 1e-9
+    from latentsync_b200.whisper import mel_filterbank
+
+    fb = mel_filterbank()
+    for r, row in c["mel_rows"].items():  # rows of whisper/assets/mel_filters.npz
+        assert torch.allclose(fb[r], row, atol=1e-8, rtol=0)

@@ -112,6 +112,15 @@ def test_gemm_geglu():
         hg = a.float() @ w.float().t() + b
         ref = hg[:, :inner] * F.gelu(hg[:, inner:])
         assert rel_l2(out, ref) < 2e-3, tile_n
+        # with a residual (added after the gate): several N tiles, ragged M (the Whisper front end's second convolution:
+        # GELU through the GEGLU epilogue + positional embedding, whisper/model.py:150-154)
+        res = torch.randn(M, inner, generator=g).half().to(DEV)
+        for rows in (M, M - 100):
+            out2 = torch.zeros(M, inner, dtype=torch.float16, device=DEV)
+            L.gemm([L.Seg(a, C, C, 1)], 1, 1, rows, wp, 2 * inner, out2, inner, bias=bp, residual=res, ldr=inner,
+                   flags=L.EPI_GEGLU, tile_n=tile_n)
+            assert rel_l2(out2[:rows], ref[:rows] + res[:rows].float()) < 2e-3, tile_n
+            assert not out2[rows:].any()
 
 
 def test_gemm_batched():
