@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(256, 3) gn_parts_kernel(const __half* __restri
   const int tpi = rows_per_inst >> 7;  // 128-row tiles per instance
   const int u1 = c1 / unit;            // units of the first source
   // (1) statistics: tpg threads per group (a power of two, all of them inside one warp) take the group's tiles
-  //     part, part + tpg, ... x its units into four interleaved chains - every load of the CTA is in flight at once - then
-  //     chains and threads are folded in a fixed order
+  //     part, part + tpg, ... x its units into eight interleaved chains - every load of the CTA is in flight at once -
+  //     then chains and threads are folded in a fixed order
   {
     int tpg = 32;
     while (tpg > 1 && tpg * ng > (int)blockDim.x) tpg >>= 1;
@@ -430,30 +430,32 @@ __global__ void __launch_bounds__(256, 3) gn_parts_kernel(const __half* __restri
       const int ug0 = (g0 + gi) * upg;
       const float2* b1 = p1 + (int64_t)inst * tpi * ld1;
       const float2* b2 = p2 + (int64_t)inst * tpi * ld2 - u1;
-      // chain k takes the tiles part + (8 i + k) tpg: eight (x upg) independent loads per trip, static register indices
-      int t = part;
-      for (; t + 7 * tpg < tpi; t += 8 * tpg)
-        for (int ul = 0; ul < upg; ++ul) {
-          const int ug = ug0 + ul;
+      // unit by unit: chain k takes the unit's tiles part + (8 i + k) tpg - eight independent loads per trip, static
+      // register indices, 32-bit offsets from one base pointer per unit
+      const int cnt = (tpi - part + tpg - 1) / tpg;  // tiles of this thread
+      for (int ul = 0; ul < upg; ++ul) {
+        const int ug = ug0 + ul;
+        const bool first = ug < u1;
+        const int ld = first ? ld1 : ld2;
+        const float2* q = (first ? b1 + ug : b2 + ug) + part * ld;  // b2 is already offset by -u1
+        const int step = tpg * ld;
+        int i = 0;
+        for (; i + 8 <= cnt; i += 8) {
           float2 v[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int64_t tt = t + k * tpg;
-            v[k] = (ug < u1) ? __ldg(b1 + tt * ld1 + ug) : __ldg(b2 + tt * ld2 + ug);
-          }
+          for (int k = 0; k < 8; ++k) v[k] = __ldg(q + (i + k) * step);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             su[k] += v[k].x;
             sq[k] += v[k].y;
           }
         }
-      for (; t < tpi; t += tpg)
-        for (int ul = 0; ul < upg; ++ul) {
-          const int ug = ug0 + ul;
-          const float2 v = (ug < u1) ? __ldg(b1 + (int64_t)t * ld1 + ug) : __ldg(b2 + (int64_t)t * ld2 + ug);
+        for (; i < cnt; ++i) {
+          const float2 v = __ldg(q + i * step);
           su[0] += v.x;
           sq[0] += v.y;
         }
+      }
     }
     float a = ((su[0] + su[1]) + (su[2] + su[3])) + ((su[4] + su[5]) + (su[6] + su[7]));
     float b = ((sq[0] + sq[1]) + (sq[2] + sq[3])) + ((sq[4] + sq[5]) + (sq[6] + sq[7]));
