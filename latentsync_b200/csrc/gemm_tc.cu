@@ -473,7 +473,8 @@ __device__ __forceinline__ void add_bias32(const GemmKParams& p, int64_t m, int 
 // on how a launch happens to split its slabs: rows 0..15 ascending, rows 16 + (i ^ 1) for i = 0..15, then first + second.
 // Pair layout (128-byte rows, SWIZZLE_128B): lane l owns columns 2l, 2l + 1 of the 64; every load touches one row = 32 banks.
 __device__ __forceinline__ void gn_colsum_pair(const uint8_t* st, int lane, float2* dst) {
-  float s0a = 0.f, s1a = 0.f, q0a = 0.f, q1a = 0.f, s0b = 0.f, s1b = 0.f, q0b = 0.f, q1b = 0.f;
+  // packed fp32 pairs (add.f32x2 / fma.rn.f32x2 of sm_100: the same roundings as two scalar operations, half the issue slots)
+  float2 sa = make_float2(0.f, 0.f), qa = sa, sb = sa, qb = sa;
   const int ch = lane >> 2, sub = (lane & 3) * 4;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -481,15 +482,18 @@ __device__ __forceinline__ void gn_colsum_pair(const uint8_t* st, int lane, floa
     const __half2 ha = *reinterpret_cast<const __half2*>(st + ra * 128 + ((ch ^ (ra & 7)) << 4) + sub);
     const __half2 hb = *reinterpret_cast<const __half2*>(st + rb * 128 + ((ch ^ (rb & 7)) << 4) + sub);
     const float2 a = __half22float2(ha), b = __half22float2(hb);
-    s0a += a.x; s1a += a.y; q0a = fmaf(a.x, a.x, q0a); q1a = fmaf(a.y, a.y, q1a);
-    s0b += b.x; s1b += b.y; q0b = fmaf(b.x, b.x, q0b); q1b = fmaf(b.y, b.y, q1b);
+    sa = __fadd2_rn(sa, a);
+    qa = __ffma2_rn(a, a, qa);
+    sb = __fadd2_rn(sb, b);
+    qb = __ffma2_rn(b, b, qb);
   }
-  *reinterpret_cast<float4*>(dst + 2 * lane) = make_float4(s0a + s0b, q0a + q0b, s1a + s1b, q1a + q1b);
+  const float2 s = __fadd2_rn(sa, sb), q = __fadd2_rn(qa, qb);
+  *reinterpret_cast<float4*>(dst + 2 * lane) = make_float4(s.x, q.x, s.y, q.y);
 }
 // Single-slab layout (64-byte rows, SWIZZLE_64B): lane l owns columns 2 (l & 15), + 1 over the row half l >> 4; the two
 // halves read rows of opposite parity (different 16-bank halves), then meet by one shuffle.
 __device__ __forceinline__ void gn_colsum_single(const uint8_t* st, int lane, float2* dst) {
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  float2 s = make_float2(0.f, 0.f), q = s;
   const int cp = lane & 15, hi = lane >> 4;
   const int ch = cp >> 2, sub = (cp & 3) * 4;
 #pragma unroll
@@ -497,11 +501,13 @@ __device__ __forceinline__ void gn_colsum_single(const uint8_t* st, int lane, fl
     const int r = hi ? 16 + (i ^ 1) : i;
     const __half2 h = *reinterpret_cast<const __half2*>(st + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4) + sub);
     const float2 a = __half22float2(h);
-    s0 += a.x; s1 += a.y; q0 = fmaf(a.x, a.x, q0); q1 = fmaf(a.y, a.y, q1);
+    s = __fadd2_rn(s, a);
+    q = __ffma2_rn(a, a, q);
   }
-  const float t0 = __shfl_xor_sync(0xffffffffu, s0, 16), t1 = __shfl_xor_sync(0xffffffffu, s1, 16);
-  const float u0 = __shfl_xor_sync(0xffffffffu, q0, 16), u1 = __shfl_xor_sync(0xffffffffu, q1, 16);
-  if (hi == 0) *reinterpret_cast<float4*>(dst + 2 * cp) = make_float4(s0 + t0, q0 + u0, s1 + t1, q1 + u1);
+  const float t0 = __shfl_xor_sync(0xffffffffu, s.x, 16), t1 = __shfl_xor_sync(0xffffffffu, s.y, 16);
+  const float u0 = __shfl_xor_sync(0xffffffffu, q.x, 16), u1 = __shfl_xor_sync(0xffffffffu, q.y, 16);
+  // (first half + second half, whichever lane computes it: the same bits as gn_colsum_pair)
+  if (hi == 0) *reinterpret_cast<float4*>(dst + 2 * cp) = make_float4(s.x + t0, q.x + u0, s.y + t1, q.y + u1);
 }
 
 // ----------------------------------------------------------------------------------------------------- kernel body
