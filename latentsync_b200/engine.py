@@ -677,7 +677,6 @@ class UNetPlan(Plan):
         per_b = self.F * h * wd
         cin = sum(ch for _, ch in srcs)
         x1, c1 = srcs[0]
-        x2p, c2 = (srcs[1][0].ptr, srcs[1][1]) if len(srcs) > 1 else (0, 0)
         g, eps = c["norm_num_groups"], c["norm_eps"]
         gu = self._gn_unit(lvl, cout)  # both convolutions emit the GroupNorm statistics of what they store
         y1 = self.buf(rows, cin)
