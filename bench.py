@@ -511,7 +511,7 @@ def main():
         nongemm_ms = uplan.time_kind_in_graph(None, reps=20, exclude="gemm")
         gemm_ms_instep = max(unet_ms - nongemm_ms, 1e-6)
         gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        seg_flops = ddim * uplan_full.flops() + vplan.flops()
+        seg_flops = ddim * uplan_full.flops(algorithmic=True) + vplan.flops(algorithmic=True)
         traffic, traffic_src = _traffic_record(n_gemm_all)  # the capture is one eager pass over ALL the plan's launches
         if args.profile_kernels:
             tot = sum(ms for _, ms in table.values())
@@ -533,6 +533,8 @@ def main():
                 "kernel": "gemm_tc_kernel / gemm_tc_pair_kernel (tcgen05 GEMM / implicit-GEMM conv, cta_group::1 / ::2)",
                 "launches_per_unet_forward": n_gemm,
                 "flops_per_unet_forward": gemm_flops,
+                "flops_note": "EXECUTED FLOPs of the timed plan's GEMM launches (the sub-pixel phases of the upsample + 3x3 "
+                              "convolutions execute 4/9 of the reference's multiply-adds; whole_step counts the reference's)",
                 "avg_launch_us": 1e3 * gemm_ms / n_gemm,
                 "how": "CUDA events around a CUDA graph holding only the plan's GEMM launches, in plan order, replayed "
                        "back to back for >= 1 s (sustained power state); peak = sustained cuBLAS bf16",

@@ -125,6 +125,16 @@ typedef struct LsGemmArgs {
   float* gn_partials_out;
   int32_t gn_unit;
   int32_t gn_partials_ld;
+  /* Nearest x2 upsample folded into the 3x3 convolution that follows it (Upsample3D, resnet.py:47-75: F.interpolate(scale 2,
+   * "nearest") then conv; diffusers Upsample2D in the VAE decoder): output pixel (2y + py, 2x + px) only ever sees the
+   * 2 x 2 low-resolution neighbourhood that starts at (y - 1 + py, x - 1 + px), so the convolution over the upsampled
+   * image is four convolutions ("phases") over the LOW-resolution image with 2 x 2 kernels whose weights are sums of the
+   * 3x3 taps that land on the same source pixel - 4/9 of the multiply-adds and no upsampled copy.  up2 = 1 + 2 py + px
+   * selects the phase: segments carry a_taps = 4 (K index = ((seg, a, b, c)), a / b = row / column of the 2 x 2 window),
+   * nimg / H / W are the LOW-resolution geometry, `out` is the high-resolution [nimg, 2H, 2W, ldo] tensor and the launch
+   * writes its quarter of the pixels.  Zero padding of the upsampled image = zero padding of the low-resolution one.
+   * Needs the staged fp16 epilogue, no residual / GEGLU / partials / split-K.  0 = off. */
+  int32_t up2;
 } LsGemmArgs;
 
 int ls_gemm(const LsGemmArgs* args, void* stream);

@@ -57,6 +57,7 @@ class LsGemmArgs(C.Structure):
         ("gn_partials_out", C.c_void_p),
         ("gn_unit", C.c_int32),
         ("gn_partials_ld", C.c_int32),
+        ("up2", C.c_int32),
     ]
 
 
@@ -236,10 +237,12 @@ def gemm(
     ln_eps: float = 1e-5,
     gn_partials_out: Optional[torch.Tensor] = None,
     gn_unit: int = 0,
+    up2: int = 0,
 ) -> None:
     """row_partials_in / row_partials_out: fp32 [parts, rows, 2] (LsGemmArgs: LayerNorm folded into the consuming GEMM);
     gn_partials_out: fp32 [rows / 128, N / gn_unit (or more), 2] (GroupNorm statistics from this GEMM's epilogue)"""
     a = LsGemmArgs()
+    a.up2 = up2  # 1 + 2 py + px: sub-pixel phase of upsample -> conv (segments with 4 taps, low-resolution geometry)
     if gn_partials_out is not None:
         t = gn_partials_out
         assert t.dtype == torch.float32 and t.dim() == 3 and t.stride(2) == 1 and t.stride(1) == 2 and t.stride(0) % 2 == 0

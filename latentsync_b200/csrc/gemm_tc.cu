@@ -147,6 +147,11 @@ struct GemmKParams {
   // output columns the (sum, sum of squares) of the fp16 values stored, gn_out[(m0 / 128) * gn_ld + column / gn_unit]
   float2* gn_out;
   int gn_unit, gn_ld, gn_upt;  // gn_upt = BN / gn_unit: units per tile
+  // Sub-pixel phase of "nearest x2 upsample -> 3x3 convolution" (LsGemmArgs.up2): a segment with 4 taps reads the 2 x 2
+  // window of the LOW-resolution image that starts at (tap_dy0, tap_dx0) in {-1, 0}^2; the tile's rows are low-resolution
+  // pixels and leave through 4-D output maps over [column][x][y][image] of the high-resolution tensor with strides of two
+  // pixels / two rows, based at the phase's pixel (py, px).  up2_bx x up2_by = 32 pixels: the box of one warp's rows.
+  int up2, tap_dy0, tap_dx0, up2_bx, up2_by;
 };
 
 // ----------------------------------------------------------------------------------------- pair-mode PTX wrappers
@@ -614,8 +619,8 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           int s = 0, tap = 0, cb = 0;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             const int taps = p.seg_taps[s];
-            const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
-            const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+            const int dy = (taps == 9) ? (tap / 3 - 1) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
+            const int dx = (taps == 9) ? (tap % 3 - 1) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
             if (!ready) mbar_wait(&empty_bar[stage], phase ^ 1u);
             const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
             const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
@@ -671,8 +676,8 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             for (int u = 0; u < 2; ++u) {
               if (u < n_here) {
                 const int taps = p.seg_taps[s];
-                const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
-                const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+                const int dy = (taps == 9) ? (tap / 3 - 1) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
+                const int dx = (taps == 9) ? (tap % 3 - 1) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
                 tma_a_4d<CTAS>(sa + u * A_STAGE_BYTES, &p.mapA[s], fb, cb * BK, x0 + dx, y0 + dy, i0);
                 tma_b_3d<CTAS>(sa + 2 * A_STAGE_BYTES + u * b_rows * 128, &p.mapB, fb, kcol, brow, bz);
                 kcol += BK;
@@ -692,8 +697,8 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int taps = p.seg_taps[s];
-          const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
-          const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+          const int dy = (taps == 9) ? (tap / 3 - 1) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
+          const int dx = (taps == 9) ? (tap % 3 - 1) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
 #ifdef LS_GEMM_PROBE
           const long long pc0 = clock64();
           pr_miss += ready ? 0 : 1;
@@ -1288,8 +1293,15 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && m0 + q * 32 < p.M) {
-              tma_store_2d(single ? &p.mapOut32 : &p.mapOut, my_stage, single ? ncol0 : ncol0 - half_sel * 32,
-                           (int)(m0 + q * 32));
+              const int col0 = single ? ncol0 : ncol0 - half_sel * 32;
+              if (p.up2) {
+                // the warp's 32 rows = up2_bx x up2_by low-resolution pixels of the tile's box -> every second pixel / row
+                const int o = q * 32;  // first row of the warp inside the tile: x fastest, then y, then image
+                const int ox = o % p.bw, oy = (o / p.bw) % p.bh, on = o / (p.bw * p.bh);
+                tma_store_4d(single ? &p.mapOut32 : &p.mapOut, my_stage, col0, x0 + ox, y0 + oy, i0 + on);
+              } else {
+                tma_store_2d(single ? &p.mapOut32 : &p.mapOut, my_stage, col0, (int)(m0 + q * 32));
+              }
               bulk_commit_group();
             }
             if constexpr (LN == 3) {
@@ -1554,9 +1566,10 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
     LS_CHECK(a->a_ch[s] > 0 && a->a_ch[s] % BK == 0, "ls_gemm: segment %d channels %d not a multiple of 64", s,
              a->a_ch[s]);
     LS_CHECK(a->a_ld[s] >= a->a_ch[s] && a->a_ld[s] % 8 == 0, "ls_gemm: segment %d ld %d invalid", s, a->a_ld[s]);
-    LS_CHECK(a->a_taps[s] == 1 || a->a_taps[s] == 9, "ls_gemm: taps must be 1 or 9");
+    LS_CHECK(a->a_taps[s] == 1 || a->a_taps[s] == 9 || (a->a_taps[s] == 4 && a->up2 >= 1 && a->up2 <= 4),
+             "ls_gemm: taps must be 1 or 9 (or 4 for a sub-pixel phase, up2 = 1..4)");
     LS_CHECK((reinterpret_cast<uintptr_t>(a->a_ptr[s]) & 15) == 0, "ls_gemm: segment %d pointer not 16B aligned", s);
-    any_conv |= (a->a_taps[s] == 9);
+    any_conv |= (a->a_taps[s] != 1);
     p.seg_taps[s] = a->a_taps[s];
     p.seg_cblk[s] = a->a_ch[s] / BK;
     ktot += a->a_taps[s] * a->a_ch[s];
@@ -1603,6 +1616,19 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
                     ? 1
                     : 0;
 
+  if (a->up2 != 0) {
+    // sub-pixel phase of upsample -> conv: rows are low-resolution pixels, stored to every second pixel / row of `out`
+    p.up2 = a->up2;
+    p.tap_dy0 = ((a->up2 - 1) >> 1) ? 0 : -1;  // py == 0: rows y - 1, y;  py == 1: rows y, y + 1
+    p.tap_dx0 = ((a->up2 - 1) & 1) ? 0 : -1;
+    p.up2_bx = p.bw < 32 ? p.bw : 32;
+    p.up2_by = 32 / p.up2_bx;
+    LS_CHECK(a->up2 >= 1 && a->up2 <= 4 && p.tma_store && a->residual == nullptr && !(a->flags & LS_EPI_GEGLU) &&
+                 p.bh % p.up2_by == 0 && (p.bw % p.up2_bx) == 0 && a->gn_partials_out == nullptr &&
+                 a->row_partials_in == nullptr && a->row_partials_out == nullptr,
+             "ls_gemm: up2 needs the staged fp16 epilogue without residual / GEGLU / partials and 32-pixel warp boxes "
+             "(W = %d, H = %d)", a->W, a->H);
+  }
   // ---- tile width, CTA pairing and split-K factor
   const int sms = num_sms();
   const bool geglu = (a->flags & LS_EPI_GEGLU) != 0;
@@ -1649,7 +1675,7 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   }
   // split-K only where SMs would idle: few output tiles, long K; needs the TMA-store epilogue and a plain GEMM
   const bool split_ok = env_split != 0 && p.tma_store && !geglu && !p.b_batched && !(a->flags & LS_EPI_SILU) &&
-                        (a->N % 8 == 0) && (a->bias_ld % 4 == 0) && ln_mode == 0;
+                        (a->N % 8 == 0) && (a->bias_ld % 4 == 0) && ln_mode == 0 && a->up2 == 0;
   int best_bn = 0, best_ctas = 1, best_split = 1;
   double best_cost = -1.0;
   const int step = geglu ? 64 : 32;
@@ -1751,7 +1777,27 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   }
 
   const int n_out = geglu ? a->N / 2 : a->N;
-  if (p.tma_store) {
+  if (p.tma_store && p.up2) {
+    // [column][x][y][image] view of the HIGH-resolution output (2H x 2W pixels per image, row pitch ldo), every second
+    // pixel and row, starting at this phase's pixel (py, px); one warp stores a box of up2_bx x up2_by pixels
+    const int py = (a->up2 - 1) >> 1, px = (a->up2 - 1) & 1;
+    const cuuint64_t ldb = (cuuint64_t)a->ldo * 2;
+    __half* base = reinterpret_cast<__half*>(a->out) + ((int64_t)py * (2 * a->W) + px) * a->ldo;
+    LS_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "ls_gemm: up2 output alignment");
+    cuuint64_t gdim[4] = {(cuuint64_t)a->N, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->nimg};
+    cuuint64_t gstr[3] = {2 * ldb, 2 * (cuuint64_t)(2 * a->W) * ldb, (cuuint64_t)(2 * a->H) * (2 * a->W) * ldb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.up2_bx, (cuuint32_t)p.up2_by, 1};
+    CUresult r = encode(&p.mapOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LS_CHECK(r == CUDA_SUCCESS, "ls_gemm: cuTensorMapEncodeTiled(out, up2) failed with %d", (int)r);
+    cuuint32_t box32[4] = {32, (cuuint32_t)p.up2_bx, (cuuint32_t)p.up2_by, 1};
+    r = encode(&p.mapOut32, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, gdim, gstr, box32, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LS_CHECK(r == CUDA_SUCCESS, "ls_gemm: cuTensorMapEncodeTiled(out32, up2) failed with %d", (int)r);
+  } else if (p.tma_store) {
     const int n_out = geglu ? a->N / 2 : a->N;
     cuuint64_t gdim[2] = {(cuuint64_t)n_out, (cuuint64_t)M};
     cuuint64_t gstr[1] = {(cuuint64_t)a->ldo * 2};

@@ -34,6 +34,12 @@ LN_TILE = 160  # tile width of every GEMM that emits partials (the cost model's 
 # (their convolutions are split-K and the tensors are latency-, not bandwidth-bound).
 GN_PARTS = os.environ.get("LS_GN_PARTS", "1") != "0"
 GN_PARTS_MIN_ROWS = 2048
+# Upsample3D / Upsample2D (nearest x2, then a 3x3 convolution) as four sub-pixel phase GEMMs over the LOW-resolution tensor
+# (LsGemmArgs.up2, Plan.upconv): no upsampled copy and 4/9 of the multiply-adds.  LS_UPCONV_FOLD=0 keeps ls_upsample2x + the
+# 3x3 convolution (A/B measurements); low-resolution tensors with < UPCONV_MIN_ROWS rows keep it too (four launches of
+# M = 512 rows are slower than one convolution of 2048).
+UPCONV_FOLD = os.environ.get("LS_UPCONV_FOLD", "1") != "0"
+UPCONV_MIN_ROWS = 2048
 
 
 def ln_parts(n: int) -> int:
@@ -122,7 +128,10 @@ class Plan:
         self.launches = 0
         self.kinds: List[str] = []  # one tag per recorded launch (bench.py times kernels by kind)
         self.descs: List[str] = []
-        self.op_flops: List[float] = []  # algorithmic FLOPs of each launch (2*M*N*K for GEMM/conv, 4*B*h*Sq*Sk*d for SDPA)
+        self.op_flops: List[float] = []  # EXECUTED FLOPs of each launch (2*M*N*K for GEMM/conv, 4*B*h*Sq*Sk*d for SDPA)
+        # ALGORITHMIC FLOPs of the reference operation the launch stands for: differs from the executed count only for the
+        # sub-pixel phases of an upsample + 3x3 convolution (each is credited a quarter of the 9-tap convolution)
+        self.op_flops_alg: List[float] = []
         self.op_bytes: List[float] = []  # algorithmic bytes of each GEMM launch: A once + W once + out (+ residual) once
         # indices of launches that do NOT depend on the loop state and are therefore kept out of the captured graph
         # (UNet: the time-embedding path = a function of t only, the audio K/V projection = a function of the audio only);
@@ -234,16 +243,19 @@ class Plan:
             self.graph.replay()
 
     # ---- emitters (each records ONE launch)
-    def _emit(self, fn, kind: str = "other", flops: float = 0.0, desc: str = "", nbytes: float = 0.0) -> None:
+    def _emit(self, fn, kind: str = "other", flops: float = 0.0, desc: str = "", nbytes: float = 0.0,
+              alg_flops: Optional[float] = None) -> None:
         self.ops.append(fn)
         self.kinds.append(kind)
         self.op_flops.append(flops)
+        self.op_flops_alg.append(flops if alg_flops is None else alg_flops)
         self.op_bytes.append(nbytes)
         self.descs.append(desc)
         self.launches += 1
 
-    def flops(self, kind: Optional[str] = None, in_graph_only: bool = False) -> float:
-        return sum(f for i, (k, f) in enumerate(zip(self.kinds, self.op_flops))
+    def flops(self, kind: Optional[str] = None, in_graph_only: bool = False, algorithmic: bool = False) -> float:
+        # executed FLOPs of the plan's launches, or (algorithmic) the FLOPs of the reference operations they stand for
+        return sum(f for i, (k, f) in enumerate(zip(self.kinds, self.op_flops_alg if algorithmic else self.op_flops))
                    if (kind is None or k == kind) and not (in_graph_only and i in self.hoisted))
 
     def bytes(self, kind: Optional[str] = None, in_graph_only: bool = False) -> float:
@@ -257,11 +269,13 @@ class Plan:
              out_ptr: int, ldo: int, bias_ptr: int = 0, bias_div: int = 0, bias_ld: int = 0, residual_ptr: int = 0,
              ldr: int = 0, flags: int = 0, tile_n: int = 0, b_batch_stride: int = 0, b_ptr: int = 0,
              col_sum_ptr: int = 0, parts_in: Optional[Tuple[int, int, int]] = None,
-             parts_out: Optional[Tuple[int, int, int]] = None, gn_out: Optional[Tuple[int, int, int]] = None) -> None:
+             parts_out: Optional[Tuple[int, int, int]] = None, gn_out: Optional[Tuple[int, int, int]] = None,
+             up2: int = 0, alg_flops: Optional[float] = None) -> None:
         """segs: (ptr, channels, ld, taps).  w: packed fp16 [N, Ktot] tensor (kept alive by the engine) or b_ptr.
         parts_in / parts_out: (pointer to the first row, parts, stride in rows) of LayerNorm partials (LsGemmArgs).
         gn_out: (pointer to the first tile, unit, ld) of GroupNorm partials (LsGemmArgs.gn_partials_out)."""
         a = L.LsGemmArgs()
+        a.up2 = up2  # 1 + 2 py + px: one sub-pixel phase of "nearest x2 upsample -> 3x3 conv" (segments with 4 taps)
         if gn_out is not None:
             a.gn_partials_out, a.gn_unit, a.gn_partials_ld = gn_out
         if parts_in is not None:
@@ -297,8 +311,19 @@ class Plan:
         self._emit(lambda: _chk(fn(C.byref(a), _stream()), "ls_gemm"), "gemm", 2.0 * M * N * ktot,
                    f"M={M} N={N} K={ktot} img={nimg}x{H}x{W} segs={taps} flags={flags} batched={int(b_batch_stride != 0)}"
                    + (" res" if residual_ptr else "") + (" ln=in" if parts_in is not None else "")
-                   + (" ln=out" if parts_out is not None else "") + (" gn=out" if gn_out is not None else ""),
-                   float(nbytes))
+                   + (" ln=out" if parts_out is not None else "") + (" gn=out" if gn_out is not None else "")
+                   + (f" up2={up2}" if up2 else ""),
+                   float(nbytes), alg_flops)
+
+    def upconv(self, x_ptr: int, cin: int, nimg: int, h: int, wd: int, phases: Sequence[torch.Tensor], cout: int,
+               out_ptr: int, bias_ptr: int) -> None:
+        """nearest x2 upsample + 3x3 convolution of a [nimg, h, wd, cin] tensor into [nimg, 2h, 2wd, cout]: four GEMM
+        launches over the LOW-resolution tensor (pack_upconv_phases), each writing its quarter of the output pixels -
+        no upsampled copy, 4/9 of the multiply-adds (resnet.py:47-75; diffusers Upsample2D)"""
+        alg = 2.0 * (4 * nimg * h * wd) * cout * (9 * cin) / 4  # a quarter of the 9-tap convolution over the upsampled image
+        for ph in range(4):
+            self.gemm([(x_ptr, cin, cin, 4)], nimg, h, wd, phases[ph], cout, out_ptr, cout, bias_ptr=bias_ptr, up2=ph + 1,
+                      alg_flops=alg)
 
     def begin_stats(self, nfloats: int) -> None:
         """one fp32 arena for the (sum, sumsq) results of every GroupNorm of the plan"""
@@ -403,6 +428,26 @@ def pack_conv3x3(w: torch.Tensor, splits: Optional[Sequence[int]] = None) -> tor
     return _h(torch.cat(parts, dim=1))
 
 
+def pack_upconv_phases(w: torch.Tensor) -> List[torch.Tensor]:
+    """OIHW 3x3 weight of a convolution that follows a nearest x2 upsample -> four fp16 [N, 4 * pad64(C)] matrices,
+    index 2 py + px, K index = (a, b, channel) over the 2 x 2 low-resolution window of output pixel (2y + py, 2x + px)
+    (LsGemmArgs.up2).  Window row a = 0 is low-resolution row y - 1 + py: with py = 0 only the tap ky = 0 lands on it and
+    ky = 1, 2 both land on row y; with py = 1 ky = 0, 1 land on row y and ky = 2 on row y + 1 - likewise for columns.  Taps
+    that land on the same source pixel are summed in fp32 before the rounding to fp16."""
+    n, c = w.shape[0], w.shape[1]
+    cp = (c + KPAD - 1) // KPAD * KPAD
+    taps = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            p = torch.zeros(n, 2, 2, cp, dtype=torch.float32, device=w.device)
+            for a in (0, 1):
+                for b in (0, 1):
+                    p[:, a, b, :c] = w[:, :, taps[py][a], :][:, :, :, taps[px][b]].float().sum(dim=(2, 3))
+            out.append(_h(p.reshape(n, 4 * cp)))
+    return out
+
+
 def pack_1x1(w: torch.Tensor) -> torch.Tensor:
     n, cin = w.shape[0], w.shape[1]
     cp = (cin + KPAD - 1) // KPAD * KPAD
@@ -446,6 +491,14 @@ class _Weights:
         if name not in self.t:
             self.put(name, pack_conv3x3(self.raw(key), splits))
         return self.t[name]
+
+    def upconv(self, key: str) -> List[torch.Tensor]:
+        """the four sub-pixel phase matrices of a 3x3 convolution that follows a nearest x2 upsample"""
+        names = [f"{key}#up{ph}" for ph in range(4)]
+        if names[0] not in self.t:
+            for nm, t in zip(names, pack_upconv_phases(self.raw(key))):
+                self.put(nm, t)
+        return [self.t[nm] for nm in names]
 
     def bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.t.values())
@@ -1065,10 +1118,18 @@ class UNetPlan(Plan):
             if i != nlev - 1:
                 # Upsample3D (resnet.py:47-75): nearest x2 on (h, w), then 3x3 conv
                 h, wd = self._geo(lvl)
-                up = self.buf(self._rows(lvl - 1), ch)
-                self.call("ls_upsample2x", x.ptr, B * F, h, wd, ch, up.ptr)
-                x = self._conv3x3(f"{p}.upsamplers.0.conv", up, ch, ch, lvl - 1)
-                del up
+                key = f"{p}.upsamplers.0.conv"
+                if UPCONV_FOLD and self._full_B * F * h * wd >= UPCONV_MIN_ROWS and wd >= 8 and ch % KPAD == 0:
+                    # the upsample is folded into the convolution: four sub-pixel phase GEMMs over the low-res tensor
+                    y = self.buf(self._rows(lvl - 1), ch)
+                    self.upconv(x.ptr, ch, B * F, h, wd, w.upconv(key + ".weight"), ch, y.ptr,
+                                w.f32(key + ".bias").data_ptr())
+                    x = y
+                else:
+                    up = self.buf(self._rows(lvl - 1), ch)
+                    self.call("ls_upsample2x", x.ptr, B * F, h, wd, ch, up.ptr)
+                    x = self._conv3x3(key, up, ch, ch, lvl - 1)
+                    del up
         # conv_norm_out -> SiLU -> conv_out (unet.py:464-466)
         y = self.buf(rows0, ch)
         self.gn([(x, ch)], rows0, F * self.H * self.W, c["norm_num_groups"], w.f32("conv_norm_out.weight"),
@@ -1212,11 +1273,18 @@ class VAEPlan(Plan):
                 x = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x, ch, cout, h, wd)
                 ch = cout
             if i != nup - 1:
-                up = self.buf(nimg * 4 * h * wd, ch)
-                self.call("ls_upsample2x", x.ptr, nimg, h, wd, ch, up.ptr)
-                h, wd = 2 * h, 2 * wd
-                x = self._conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", up, ch, ch, h, wd)
-                del up
+                key = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                if UPCONV_FOLD and nimg * h * wd >= UPCONV_MIN_ROWS and wd >= 8 and ch % KPAD == 0:
+                    y = self.buf(nimg * 4 * h * wd, ch)
+                    self.upconv(x.ptr, ch, nimg, h, wd, w.upconv(key + ".weight"), ch, y.ptr, w.f32(key + ".bias").data_ptr())
+                    h, wd = 2 * h, 2 * wd
+                    x = y
+                else:
+                    up = self.buf(nimg * 4 * h * wd, ch)
+                    self.call("ls_upsample2x", x.ptr, nimg, h, wd, ch, up.ptr)
+                    h, wd = 2 * h, 2 * wd
+                    x = self._conv(key, up, ch, ch, h, wd)
+                    del up
         y = self._gn("decoder.conv_norm_out", x, ch, h * wd, True)
         self.out_h, self.out_w = h, wd
         nout = c["out_channels"]

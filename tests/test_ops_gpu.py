@@ -184,6 +184,31 @@ def test_conv3x3_concat_and_shortcut():
     assert rel_l2(uncl(out, nimg, H, W), ref) < 2e-3
 
 
+@pytest.mark.parametrize("nimg,H,W,C,N", [(32, 8, 8, 1280, 1280), (32, 16, 16, 640, 640), (4, 32, 32, 512, 512),
+                                          (2, 64, 64, 256, 256), (1, 128, 128, 128, 128), (3, 16, 16, 128, 96)])
+def test_upsample_folded_into_conv(nimg, H, W, C, N):
+    """Upsample3D / diffusers Upsample2D (resnet.py:47-75: F.interpolate(scale_factor=2, mode="nearest") then a 3x3
+    convolution) as four sub-pixel phase GEMMs over the LOW-resolution tensor (LsGemmArgs.up2): 2 x 2 windows, weights =
+    sums of the 3x3 taps that land on the same source pixel, each launch writes every second pixel / row of the output"""
+    L = _ops()
+    from latentsync_b200.engine import pack_upconv_phases
+
+    g = torch.Generator(device="cpu").manual_seed(41)
+    x = torch.randn(nimg, C, H, W, generator=g).half().to(DEV)
+    w = (torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    phases = pack_upconv_phases(w)
+    out = torch.full((nimg * 4 * H * W, N), float("nan"), dtype=torch.float16, device=DEV)
+    for ph in range(4):
+        L.gemm([L.Seg(cl(x), C, C, 4)], nimg, H, W, phases[ph], N, out, N, bias=b, up2=ph + 1)
+    ref = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.half().float(), b, padding=1)
+    got = uncl(out, nimg, 2 * H, 2 * W)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 2e-3
+    with pytest.raises(RuntimeError):  # a residual cannot follow the strided store
+        L.gemm([L.Seg(cl(x), C, C, 4)], nimg, H, W, phases[0], N, out, N, bias=b, residual=out, ldr=N, up2=1)
+
+
 def test_conv_stride2_via_im2col():
     """Downsample3D (resnet.py:89): 3x3 stride 2 pad 1"""
     L = _ops()
