@@ -135,6 +135,12 @@ typedef struct LsGemmArgs {
    * writes its quarter of the pixels.  Zero padding of the upsampled image = zero padding of the low-resolution one.
    * Needs the staged fp16 epilogue, no residual / GEGLU / partials / split-K.  0 = off. */
   int32_t up2;
+  /* 3x3 convolution with stride 2 read in place (Downsample3D, resnet.py:78-101: Conv2d(stride=2, padding=1); diffusers
+   * Downsample2D of the VAE encoder: F.pad(x, (0, 1, 0, 1)) + Conv2d(stride=2, padding=0)): nimg / H / W are the OUTPUT geometry,
+   * the single 9-tap segment points at the [nimg, 2H, 2W, ld] input, whose pixels are fetched with TMA element strides of two -
+   * no im2col copy.  stride2_pad = zero padding before the first row / column (1 or 0; the far side is padded as needed). */
+  int32_t stride2;
+  int32_t stride2_pad;
 } LsGemmArgs;
 
 int ls_gemm(const LsGemmArgs* args, void* stream);

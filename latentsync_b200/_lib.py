@@ -58,6 +58,8 @@ class LsGemmArgs(C.Structure):
         ("gn_unit", C.c_int32),
         ("gn_partials_ld", C.c_int32),
         ("up2", C.c_int32),
+        ("stride2", C.c_int32),
+        ("stride2_pad", C.c_int32),
     ]
 
 
@@ -238,11 +240,14 @@ def gemm(
     gn_partials_out: Optional[torch.Tensor] = None,
     gn_unit: int = 0,
     up2: int = 0,
+    stride2: int = 0,
+    stride2_pad: int = 1,
 ) -> None:
     """row_partials_in / row_partials_out: fp32 [parts, rows, 2] (LsGemmArgs: LayerNorm folded into the consuming GEMM);
     gn_partials_out: fp32 [rows / 128, N / gn_unit (or more), 2] (GroupNorm statistics from this GEMM's epilogue)"""
     a = LsGemmArgs()
     a.up2 = up2  # 1 + 2 py + px: sub-pixel phase of upsample -> conv (segments with 4 taps, low-resolution geometry)
+    a.stride2, a.stride2_pad = stride2, stride2_pad  # stride-2 3x3 conv read in place (output geometry, input tensor)
     if gn_partials_out is not None:
         t = gn_partials_out
         assert t.dtype == torch.float32 and t.dim() == 3 and t.stride(2) == 1 and t.stride(1) == 2 and t.stride(0) % 2 == 0

@@ -152,6 +152,10 @@ struct GemmKParams {
   // pixels and leave through 4-D output maps over [column][x][y][image] of the high-resolution tensor with strides of two
   // pixels / two rows, based at the phase's pixel (py, px).  up2_bx x up2_by = 32 pixels: the box of one warp's rows.
   int up2, tap_dy0, tap_dx0, up2_bx, up2_by;
+  // Stride-2 3x3 convolution read in place (LsGemmArgs.stride2): tile coordinates are OUTPUT pixels, the A maps cover the
+  // INPUT image with element strides of two pixels / rows, so box coordinates are input pixels: cs * x0 + dx with cs = 2;
+  // tap9_off = -pad (first tap offset of a 9-tap segment: -1 for zero padding 1, 0 for the (0, 1, 0, 1) padding)
+  int cs, tap9_off;
 };
 
 // ----------------------------------------------------------------------------------------- pair-mode PTX wrappers
@@ -619,15 +623,15 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           int s = 0, tap = 0, cb = 0;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             const int taps = p.seg_taps[s];
-            const int dy = (taps == 9) ? (tap / 3 - 1) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
-            const int dx = (taps == 9) ? (tap % 3 - 1) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
+            const int dy = (taps == 9) ? (tap / 3 + p.tap9_off) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
+            const int dx = (taps == 9) ? (tap % 3 + p.tap9_off) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
             if (!ready) mbar_wait(&empty_bar[stage], phase ^ 1u);
             const int nstage = (stage + 1 == stages) ? 0 : stage + 1;
             const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
             const uint32_t fb = full0 + stage * 8;
             ready = mbar_probe(empty0 + nstage * 8, nphase ^ 1u);
             mbar_expect_tx_u32(fb, (uint32_t)A_STAGE_BYTES);
-            tma_a_4d<1>(a_ring + stage * A_STAGE_BYTES, &p.mapA[s], fb, cb * BK, x0 + dx, y0 + dy, i0);
+            tma_a_4d<1>(a_ring + stage * A_STAGE_BYTES, &p.mapA[s], fb, cb * BK, p.cs * x0 + dx, p.cs * y0 + dy, i0);
             stage = nstage;
             phase = nphase;
             if (++cb == p.seg_cblk[s]) {
@@ -676,9 +680,9 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
             for (int u = 0; u < 2; ++u) {
               if (u < n_here) {
                 const int taps = p.seg_taps[s];
-                const int dy = (taps == 9) ? (tap / 3 - 1) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
-                const int dx = (taps == 9) ? (tap % 3 - 1) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
-                tma_a_4d<CTAS>(sa + u * A_STAGE_BYTES, &p.mapA[s], fb, cb * BK, x0 + dx, y0 + dy, i0);
+                const int dy = (taps == 9) ? (tap / 3 + p.tap9_off) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
+                const int dx = (taps == 9) ? (tap % 3 + p.tap9_off) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
+                tma_a_4d<CTAS>(sa + u * A_STAGE_BYTES, &p.mapA[s], fb, cb * BK, p.cs * x0 + dx, p.cs * y0 + dy, i0);
                 tma_b_3d<CTAS>(sa + 2 * A_STAGE_BYTES + u * b_rows * 128, &p.mapB, fb, kcol, brow, bz);
                 kcol += BK;
                 if (++cb == p.seg_cblk[s]) {
@@ -697,8 +701,8 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int taps = p.seg_taps[s];
-          const int dy = (taps == 9) ? (tap / 3 - 1) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
-          const int dx = (taps == 9) ? (tap % 3 - 1) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
+          const int dy = (taps == 9) ? (tap / 3 + p.tap9_off) : (taps == 4 ? (tap >> 1) + p.tap_dy0 : 0);
+          const int dx = (taps == 9) ? (tap % 3 + p.tap9_off) : (taps == 4 ? (tap & 1) + p.tap_dx0 : 0);
 #ifdef LS_GEMM_PROBE
           const long long pc0 = clock64();
           pr_miss += ready ? 0 : 1;
@@ -725,7 +729,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
                 : "=r"(rdy) : "r"(empty0 + nstage * 8), "r"(nphase ^ 1u) : "memory");
             if (bytes) mbar_expect_tx(&full_bar[stage], bytes); else mbar_arrive(&full_bar[stage]);
             if (!(p.flags & LS_DBG_NO_A))
-              tma_load_4d(smem + stage * stage_bytes, &p.mapA[s], &full_bar[stage], cb * BK, x0 + dx, y0 + dy, i0);
+              tma_load_4d(smem + stage * stage_bytes, &p.mapA[s], &full_bar[stage], cb * BK, p.cs * x0 + dx, p.cs * y0 + dy, i0);
             if (!(p.flags & LS_DBG_NO_B))
               tma_load_3d(smem + stage * stage_bytes + A_STAGE_BYTES, &p.mapB, &full_bar[stage], kcol, brow, bz);
             (void)fb;
@@ -733,7 +737,7 @@ __device__ __forceinline__ void gemm_body(const GemmKParams& p) {
           } else
 #endif
           ready = produce_kblock<CTAS>(sa, sa + A_STAGE_BYTES, &p.mapA[s], &p.mapB, full0 + stage * 8, tx, cb * BK,
-                                       x0 + dx, y0 + dy, i0, kcol, brow, bz, empty0 + nstage * 8, nphase ^ 1u);
+                                       p.cs * x0 + dx, p.cs * y0 + dy, i0, kcol, brow, bz, empty0 + nstage * 8, nphase ^ 1u);
           kcol += BK;
           stage = nstage;
           phase = nphase;
@@ -1616,6 +1620,16 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
                     ? 1
                     : 0;
 
+  p.cs = 1;
+  p.tap9_off = -1;
+  if (a->stride2 != 0) {
+    // 3x3 convolution with stride 2 over the [nimg, 2H, 2W] input: output pixel (y, x) reads input rows 2y - pad .. 2y - pad + 2
+    LS_CHECK(a->stride2 == 1 && a->up2 == 0 && (a->stride2_pad == 0 || a->stride2_pad == 1) && a->nseg == 1 && a->a_taps[0] == 9,
+             "ls_gemm: stride2 needs one 9-tap segment, stride2_pad 0 or 1, no up2");
+    LS_CHECK(2 * p.bw <= 256 && 2 * p.bh <= 256, "ls_gemm: stride2 box %d x %d pixels exceeds the TMA box limit", 2 * p.bw, 2 * p.bh);
+    p.cs = 2;
+    p.tap9_off = -a->stride2_pad;
+  }
   if (a->up2 != 0) {
     // sub-pixel phase of upsample -> conv: rows are low-resolution pixels, stored to every second pixel / row of `out`
     p.up2 = a->up2;
@@ -1753,10 +1767,13 @@ static int gemm_impl(const LsGemmArgs* a, cudaStream_t stream) {
   // tensor maps
   for (int s = 0; s < a->nseg; ++s) {
     const cuuint64_t ld_b = (cuuint64_t)a->a_ld[s] * 2;
-    cuuint64_t gdim[4] = {(cuuint64_t)a->a_ch[s], (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->nimg};
-    cuuint64_t gstr[3] = {ld_b, ld_b * a->W, ld_b * a->W * a->H};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // stride2: the map covers the INPUT image (2H x 2W); the box spans 2 bw x 2 bh input pixels of which every second one
+    // (element strides 2) is loaded, i.e. bw x bh pixels land in shared memory as usual
+    const cuuint64_t cs = (cuuint64_t)p.cs;
+    cuuint64_t gdim[4] = {(cuuint64_t)a->a_ch[s], cs * a->W, cs * a->H, (cuuint64_t)a->nimg};
+    cuuint64_t gstr[3] = {ld_b, ld_b * cs * a->W, ld_b * cs * a->W * cs * a->H};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(p.cs * p.bw), (cuuint32_t)(p.cs * p.bh), (cuuint32_t)p.bn};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p.cs, (cuuint32_t)p.cs, 1};
     CUresult r = encode(&p.mapA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a->a_ptr[s]), gdim, gstr,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -40,6 +40,9 @@ GN_PARTS_MIN_ROWS = 2048
 # M = 512 rows are slower than one convolution of 2048).
 UPCONV_FOLD = os.environ.get("LS_UPCONV_FOLD", "1") != "0"
 UPCONV_MIN_ROWS = 2048
+# Downsample3D / Downsample2D (3x3 convolution, stride 2) read in place through TMA element strides (LsGemmArgs.stride2)
+# instead of an explicit 9-tap im2col copy.  LS_S2_INPLACE=0 keeps ls_im2col_s2 + a plain GEMM (A/B measurements).
+S2_INPLACE = os.environ.get("LS_S2_INPLACE", "1") != "0"
 
 
 def ln_parts(n: int) -> int:
@@ -270,12 +273,13 @@ class Plan:
              ldr: int = 0, flags: int = 0, tile_n: int = 0, b_batch_stride: int = 0, b_ptr: int = 0,
              col_sum_ptr: int = 0, parts_in: Optional[Tuple[int, int, int]] = None,
              parts_out: Optional[Tuple[int, int, int]] = None, gn_out: Optional[Tuple[int, int, int]] = None,
-             up2: int = 0, alg_flops: Optional[float] = None) -> None:
+             up2: int = 0, alg_flops: Optional[float] = None, stride2: int = 0, stride2_pad: int = 1) -> None:
         """segs: (ptr, channels, ld, taps).  w: packed fp16 [N, Ktot] tensor (kept alive by the engine) or b_ptr.
         parts_in / parts_out: (pointer to the first row, parts, stride in rows) of LayerNorm partials (LsGemmArgs).
         gn_out: (pointer to the first tile, unit, ld) of GroupNorm partials (LsGemmArgs.gn_partials_out)."""
         a = L.LsGemmArgs()
         a.up2 = up2  # 1 + 2 py + px: one sub-pixel phase of "nearest x2 upsample -> 3x3 conv" (segments with 4 taps)
+        a.stride2, a.stride2_pad = stride2, stride2_pad  # stride-2 3x3 conv read in place: OUTPUT geometry, input tensor
         if gn_out is not None:
             a.gn_partials_out, a.gn_unit, a.gn_partials_ld = gn_out
         if parts_in is not None:
@@ -312,7 +316,7 @@ class Plan:
                    f"M={M} N={N} K={ktot} img={nimg}x{H}x{W} segs={taps} flags={flags} batched={int(b_batch_stride != 0)}"
                    + (" res" if residual_ptr else "") + (" ln=in" if parts_in is not None else "")
                    + (" ln=out" if parts_out is not None else "") + (" gn=out" if gn_out is not None else "")
-                   + (f" up2={up2}" if up2 else ""),
+                   + (f" up2={up2}" if up2 else "") + (" stride2" if stride2 else ""),
                    float(nbytes), alg_flops)
 
     def upconv(self, x_ptr: int, cin: int, nimg: int, h: int, wd: int, phases: Sequence[torch.Tensor], cout: int,
@@ -1082,14 +1086,20 @@ class UNetPlan(Plan):
             if i != nlev - 1:
                 # Downsample3D (resnet.py:93-101): 3x3 stride 2 pad 1 via explicit im2col
                 h, wd = self._geo(i)
-                cols = self.buf(self._rows(i + 1), 9 * ch)
-                self.call("ls_im2col_s2", x.ptr, B * F, h, wd, ch, cols.ptr)
                 key = f"{p}.downsamplers.0.conv"
                 y = self.buf(self._rows(i + 1), ch)
                 gu = self._gn_unit(i + 1, ch)
-                self.gemm([(cols.ptr, 9 * ch, 9 * ch, 1)], 1, 1, self._rows(i + 1), w.conv(key + ".weight"), ch, y.ptr,
-                          ch, bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=self.with_gn_parts(y, gu) if gu else None)
-                del cols
+                gno = self.with_gn_parts(y, gu) if gu else None
+                if S2_INPLACE:
+                    # the stride-2 convolution reads its input in place (TMA element strides): no im2col copy
+                    self.gemm([(x.ptr, ch, ch, 9)], B * F, h // 2, wd // 2, w.conv(key + ".weight"), ch, y.ptr, ch,
+                              bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=gno, stride2=1, stride2_pad=1)
+                else:
+                    cols = self.buf(self._rows(i + 1), 9 * ch)
+                    self.call("ls_im2col_s2", x.ptr, B * F, h, wd, ch, cols.ptr)
+                    self.gemm([(cols.ptr, 9 * ch, 9 * ch, 1)], 1, 1, self._rows(i + 1), w.conv(key + ".weight"), ch, y.ptr,
+                              ch, bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=gno)
+                    del cols
                 x = y
                 skips.append((x, ch))
         lvl = nlev - 1
@@ -1330,13 +1340,19 @@ class VAEEncodePlan(VAEPlan):
             if i != len(boc) - 1:
                 key = f"encoder.down_blocks.{i}.downsamplers.0.conv"
                 rows = nimg * (h // 2) * (wd // 2)
-                cols = self.buf(rows, 9 * ch)
-                self.call("ls_im2col_s2_pad", x.ptr, nimg, h, wd, ch, 0, cols.ptr)
-                h, wd = h // 2, wd // 2
                 y = self.buf(rows, ch)
-                self.gemm([(cols.ptr, 9 * ch, 9 * ch, 1)], 1, 1, rows, w.conv(key + ".weight"), ch, y.ptr, ch,
-                          bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=self._gn_out(y, h * wd))
-                del cols
+                if S2_INPLACE:
+                    h, wd = h // 2, wd // 2
+                    self.gemm([(x.ptr, ch, ch, 9)], nimg, h, wd, w.conv(key + ".weight"), ch, y.ptr, ch,
+                              bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=self._gn_out(y, h * wd), stride2=1,
+                              stride2_pad=0)
+                else:
+                    cols = self.buf(rows, 9 * ch)
+                    self.call("ls_im2col_s2_pad", x.ptr, nimg, h, wd, ch, 0, cols.ptr)
+                    h, wd = h // 2, wd // 2
+                    self.gemm([(cols.ptr, 9 * ch, 9 * ch, 1)], 1, 1, rows, w.conv(key + ".weight"), ch, y.ptr, ch,
+                              bias_ptr=w.f32(key + ".bias").data_ptr(), gn_out=self._gn_out(y, h * wd))
+                    del cols
                 x = y
         x = self._resnet("encoder.mid_block.resnets.0", x, ch, ch, h, wd)
         x = self._mid_attention("encoder.mid_block.attentions.0", x, ch, h, wd)

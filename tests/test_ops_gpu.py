@@ -209,6 +209,26 @@ def test_upsample_folded_into_conv(nimg, H, W, C, N):
         L.gemm([L.Seg(cl(x), C, C, 4)], nimg, H, W, phases[0], N, out, N, bias=b, residual=out, ldr=N, up2=1)
 
 
+@pytest.mark.parametrize("nimg,H,W,C,N", [(32, 16, 16, 320, 320), (32, 8, 8, 640, 640), (32, 4, 4, 1280, 1280),
+                                          (2, 64, 64, 128, 128), (1, 128, 128, 128, 128), (3, 32, 32, 256, 96)])
+@pytest.mark.parametrize("pad", [1, 0])
+def test_conv_stride2_in_place(nimg, H, W, C, N, pad):
+    """Downsample3D (resnet.py:78-101: Conv2d 3x3, stride 2, padding 1) and diffusers Downsample2D of the VAE encoder
+    (F.pad(x, (0, 1, 0, 1)) + stride-2 conv) WITHOUT an im2col copy: LsGemmArgs.stride2 - output geometry, the 9-tap
+    segment points at the [nimg, 2H, 2W] input, TMA element strides of two fetch every second pixel / row"""
+    L = _ops()
+    g = torch.Generator(device="cpu").manual_seed(43)
+    x = torch.randn(nimg, C, 2 * H, 2 * W, generator=g).half().to(DEV)
+    w = (torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C)).half().to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    out = torch.full((nimg * H * W, N), float("nan"), dtype=torch.float16, device=DEV)
+    L.gemm([L.Seg(cl(x), C, C, 9)], nimg, H, W, pack_conv_w(w), N, out, N, bias=b, stride2=1, stride2_pad=pad)
+    xf = x.float() if pad else F.pad(x.float(), (0, 1, 0, 1))
+    ref = F.conv2d(xf, w.float(), b, stride=2, padding=pad)
+    assert ref.shape[-2:] == (H, W)
+    assert rel_l2(uncl(out, nimg, H, W), ref) < 2e-3
+
+
 def test_conv_stride2_via_im2col():
     """Downsample3D (resnet.py:89): 3x3 stride 2 pad 1"""
     L = _ops()

@@ -15,7 +15,7 @@ unet = UNet3DConditionModel.from_config(cfg); unet.load_state_dict(syn.unet_stat
 vae = AutoencoderKLDecoder(syn.vae_decoder_state_dict(seed=0), device=dev)
 pipe = LipsyncPipeline(vae, None, unet, DDIMScheduler()).to(dev)
 seg = {k: v.to(dev) for k, v in syn.segment_inputs(100, 0, 16, 256, 256).items()}
-uplan = unet.plan(2, 16, 32, 32, 50); vplan = vae.plan(16, 32, 32)
+uplan = unet.plan(2, 16, 32, 32, 50, uncond_zero=True, same_sample=True); vplan = vae.plan(16, 32, 32)
 def t(fn, n=3):
     fn(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
