@@ -721,6 +721,89 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const __half* _
   gn_cluster_wait();  // nobody reads this CTA's s_part any more: safe to exit
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// Group-local GroupNorm for SMALL instances: one CTA per (instance, group).  The slab of one group - rows_per_inst rows
+// x C / groups channels - is a few KB at the 8x8 / 4x4 levels (256 rows x 40 channels = 20 KB), so one CTA reads it
+// (pass 1: sums), reduces inside the block and reads it again from L1 / L2 to normalise (pass 2).  No cross-CTA
+// exchange at all: the cluster kernel above pays a cluster barrier + DSMEM round trip (~8-12 us per launch on tensors of
+// 1-5 MB); this one is bound by two dependent load round trips.  Fixed summation order: deterministic.
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_group_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2,
+                                                       int c2, int rows_per_inst, int groups,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, int silu, __half* __restrict__ y) {
+  pdl_prologue();
+  __shared__ float red[2][8];
+  __shared__ float s_mean, s_rstd;
+  const int C = c1 + c2;
+  const int cg = C / groups;
+  const int g = blockIdx.x, inst = blockIdx.y;
+  const int nvec = cg >> 2;  // 8-byte vectors (4 channels) per row
+  const int c0 = g * cg;
+  const int64_t row0 = (int64_t)inst * rows_per_inst;
+  const int total = rows_per_inst * nvec;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto src_of = [&](int row, int v) -> const __half* {
+    const int c = c0 + v * 4;
+    return (c < c1) ? x1 + (row0 + row) * c1 + c : x2 + (row0 + row) * c2 + (c - c1);
+  };
+  float su = 0.f, sq = 0.f;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int row = i / nvec, v = i - row * nvec;
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(src_of(row, v)));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    su += (a.x + a.y) + (b.x + b.y);
+    sq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, sq))));
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) {
+    red[0][warp] = su;
+    red[1][warp] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a += red[0][k];
+      b += red[1][k];
+    }
+    const float inv_n = 1.f / ((float)rows_per_inst * (float)cg);
+    const float mean = a * inv_n;
+    const float var = fmaxf(b * inv_n - mean * mean, 0.f);
+    s_mean = mean;
+    s_rstd = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const float mean = s_mean, rstd = s_rstd;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int row = i / nvec, v = i - row * nvec;
+    const int c = c0 + v * 4;
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(src_of(row, v)));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    float o0 = (a.x - mean) * rstd * ga.x + be.x, o1 = (a.y - mean) * rstd * ga.y + be.y;
+    float o2 = (b.x - mean) * rstd * ga.z + be.z, o3 = (b.y - mean) * rstd * ga.w + be.w;
+    if (silu) {
+      o0 = silu_f(o0);
+      o1 = silu_f(o1);
+      o2 = silu_f(o2);
+      o3 = silu_f(o3);
+    }
+    uint2 w;
+    *reinterpret_cast<__half2*>(&w.x) = __floats2half2_rn(o0, o1);
+    *reinterpret_cast<__half2*>(&w.y) = __floats2half2_rn(o2, o3);
+    *reinterpret_cast<uint2*>(y + (row0 + row) * C + c) = w;
+  }
+}
+
 static void gn_chunking(int64_t rows, int rows_per_inst, int target_ctas, int& ninst, int& chunks, int& rpc) {
   ninst = (int)(rows / rows_per_inst);
   chunks = (target_ctas + ninst - 1) / ninst;
@@ -1143,6 +1226,25 @@ extern "C" int ls_groupnorm(const void* x1, int32_t c1, const void* x2, int32_t 
            "ls_groupnorm: bad args");
   LS_CHECK(groups > 0 && groups <= 32 && C % groups == 0 && C % 8 == 0 && c1 % 8 == 0,
            "ls_groupnorm: C=%d groups=%d unsupported", C, groups);
+  {
+    // small instances: one CTA per (instance, group), no cross-CTA exchange (gn_group_kernel).  LS_GN_GROUP=0 disables.
+    static int env_grp = -1;
+    if (env_grp < 0) {
+      const char* e = getenv("LS_GN_GROUP");
+      env_grp = e ? atoi(e) : 1;
+    }
+    const int cg = C / groups;
+    const int64_t ninst_g = rows / rows_per_inst;
+    if (env_grp && cg % 4 == 0 && c1 % 4 == 0 && (int64_t)rows_per_inst * cg * 2 <= 48 * 1024 && ninst_g * groups >= 32 &&
+        ninst_g <= 65535 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0) {
+      LS_CUDA(launch_k(gn_group_kernel, dim3(groups, (unsigned)ninst_g), dim3(256), (size_t)0, (cudaStream_t)stream,
+                       (const __half*)x1, c1, (const __half*)x2, c2, rows_per_inst, groups, gamma, beta, eps, silu,
+                       (__half*)y));
+      LS_CUDA(cudaGetLastError());
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      return 0;
+    }
+  }
   if (ls::groupnorm_cluster_try(x1, c1, x2, c2, rows, rows_per_inst, groups, gamma, beta, eps, silu, y,
                                 (cudaStream_t)stream) == 0)
     return 0;
