@@ -12,6 +12,7 @@ the clip per rank and `gather_frames` collects decoded frames on rank 0 with one
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Union
 
 import torch
@@ -30,6 +31,12 @@ class LipsyncPipeline:
     cfg_null_audio_shortcut = True  # see UNetEngine.plan(uncond_zero=...); False keeps the full-batch cross-attention
     cfg_shared_prefix = True        # see UNetEngine.plan(same_sample=...): needs the shortcut above; not bitwise (GroupNorm
                                     # partial sums are chunked differently), same tolerance against the reference
+    # The whole denoising loop of a segment (lipsync_pipeline.py:537-568: per step concat13, time-embedding row, UNet, CFG +
+    # DDIM) as ONE CUDA graph per (plan, schedule, guidance): the same launches in the same order - bit-identical results -
+    # without the four small eager launches between the per-step graph replays, which cost ~0.2 ms per step because they
+    # keep the next replay from being queued behind the running one (tools/graph_alt.py).  Paths that look at every step
+    # (`trace`, `teacher_latents`, `callback`) keep the per-step loop.  LS_LOOP_GRAPH=0 / loop_graph = False disables.
+    loop_graph = os.environ.get("LS_LOOP_GRAPH", "1") != "0"
 
     def __init__(self, vae, audio_encoder, denoising_unet, scheduler):
         self.vae = vae
@@ -41,6 +48,7 @@ class LipsyncPipeline:
         self.device = torch.device("cpu")
         self.image_processor = None
         self._progress_bar_config = {}
+        self._loop_graphs: Dict[tuple, "_LoopGraph"] = {}
 
     def to(self, device):
         self.device = torch.device(device)
@@ -188,6 +196,14 @@ class LipsyncPipeline:
         # (a function of t: one batched pass, row j = step j)
         if S:
             plan.run_hoisted(plan.kv_ops)
+        if self.loop_graph and trace is None and teacher_latents is None and callback is None:
+            lg = self._loop_graph(plan, timesteps, float(guidance_scale), nb, F, h, w)
+            lg.lat.copy_(lat)
+            lg.mask.copy_(mask)
+            lg.masked.copy_(masked)
+            lg.ref.copy_(ref)
+            lg.graph.replay()
+            return lg.lat.clone()
         ttab = unet.engine().time_table(timesteps)
         tproj = plan.tproj.tensor()
         for j, t in enumerate(timesteps):
@@ -211,6 +227,14 @@ class LipsyncPipeline:
             if callback is not None and j % callback_steps == 0:
                 callback(j, t, lat)
         return lat
+
+    def _loop_graph(self, plan, timesteps, guidance_scale: float, nb: int, F: int, h: int, w: int) -> "_LoopGraph":
+        """the captured loop for this (plan, schedule, guidance); built on first use (one eager pass, then the capture)"""
+        key = (id(plan), tuple(float(t) for t in timesteps), guidance_scale)
+        lg = self._loop_graphs.get(key)
+        if lg is None:
+            lg = self._loop_graphs[key] = _LoopGraph(self, plan, timesteps, guidance_scale, nb, F, h, w)
+        return lg
 
     @torch.no_grad()
     def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
@@ -636,3 +660,47 @@ class LipsyncPipeline:
                 restorer.check_status()
                 out[chunk] = res.cpu().numpy()
         return out
+
+
+
+class _LoopGraph:
+    """One CUDA graph holding every launch of a segment's denoising loop (LipsyncPipeline.loop_graph): static fp32 state
+    (`lat` is updated in place by ls_cfg_ddim_step, `mask` / `masked` / `ref` are the conditioning channels of ls_concat13),
+    the time-embedding table of the schedule, and the graph.  The audio K/V projection stays outside (once per segment,
+    before the replay)."""
+
+    def __init__(self, pipe: "LipsyncPipeline", plan, timesteps, guidance_scale: float, nb: int, F: int, h: int, w: int):
+        unet, sch = pipe.denoising_unet, pipe.scheduler
+        dev = unet.device
+        self.plan = plan  # keeps id(plan) unique for the life of the entry
+        self.lat = torch.zeros(1, 4, F, h, w, dtype=torch.float32, device=dev)
+        self.mask = torch.zeros(1, 1, F, h, w, dtype=torch.float32, device=dev)
+        self.masked = torch.zeros(1, 4, F, h, w, dtype=torch.float32, device=dev)
+        self.ref = torch.zeros(1, 4, F, h, w, dtype=torch.float32, device=dev)
+        self.ttab = unet.engine().time_table(timesteps)
+        coeffs = [sch.step_coefficients(t) for t in timesteps]
+        lib = L.lib()
+        tproj = plan.tproj.tensor()
+
+        def loop():
+            st = torch.cuda.current_stream().cuda_stream
+            for j in range(len(timesteps)):
+                L._check(lib.ls_concat13(self.lat.data_ptr(), self.mask.data_ptr(), self.masked.data_ptr(),
+                                         self.ref.data_ptr(), nb, F, h * w, plan.x_in.ptr, st), "ls_concat13")
+                tproj.copy_(self.ttab[j].expand_as(tproj))
+                plan.run(hoisted=False)
+                a_t, a_p = coeffs[j]
+                L._check(lib.ls_cfg_ddim_step(plan.eps_out.ptr, plan.eps_out.cols, nb, F, h * w, guidance_scale, a_t, a_p,
+                                              self.lat.data_ptr(), None, st), "ls_cfg_ddim_step")
+
+        if plan.graph is None:
+            plan.capture()  # warms every launch of the plan up (function attributes, scratch) before our own capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            loop()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loop()

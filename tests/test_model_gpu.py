@@ -475,6 +475,28 @@ def test_loop_stage2_vs_reference_golden():
     assert p >= 40.0 and p_in >= 40.0
 
 
+def test_loop_graph_is_bitwise_identical_to_the_per_step_loop():
+    """LipsyncPipeline.loop_graph: the whole denoising loop of a segment (lipsync_pipeline.py:537-568) replayed as ONE CUDA
+    graph gives the same bits as the per-step loop (concat13 / time row / UNet graph / CFG + DDIM launched one by one),
+    for several segments through the same captured graph, with and without guidance"""
+    from latentsync_b200 import synthetic as syn
+
+    pipe, _ = get_pipe("tiny")
+    segs = [syn.segment_inputs(INPUT_SEED, s, 16, 128, 128) for s in range(3)]
+    for steps, g in ((4, 1.5), (3, 1.0)):
+        outs = {}
+        for mode in (True, False, True):
+            pipe.loop_graph = mode
+            outs.setdefault(mode, []).append([
+                pipe.denoise_segment(sg["latents"], sg["audio_embeds"], sg["mask_latents"], sg["masked_image_latents"],
+                                     sg["ref_latents"], num_inference_steps=steps, guidance_scale=g) for sg in segs])
+        pipe.loop_graph = True
+        for a, b, c in zip(outs[True][0], outs[False][0], outs[True][1]):
+            assert torch.equal(a, b) and torch.equal(a, c)
+        assert not torch.equal(outs[True][0][0], outs[True][0][1])
+    assert len(pipe._loop_graphs) >= 2
+
+
 def test_batched_segments_match_single_segment_path():
     """run_segments(..., segments_per_batch=2): two different segments advanced as one UNet batch give the same frames
     as one at a time (segments never interact; only GEMM tile shapes change, so agreement is to fp16 rounding)"""
