@@ -33,7 +33,9 @@
 extern "C" {
 #endif
 
-#define LS_ABI_VERSION 1
+/* 2: LsGemmArgs grew (gn_partials_out / gn_unit / gn_partials_ld, up2, stride2 / stride2_pad - all 0 = the version-1
+ * behaviour); ls_groupnorm_parts, ls_im2col1d, ls_whisper_chunks added */
+#define LS_ABI_VERSION 2
 
 /* returns the message of the last failing call on this thread ("" if none) */
 const char* ls_last_error(void);

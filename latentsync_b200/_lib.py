@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, os.environ.get("LS_SO_NAME", "_C.so"))  # LS_SO_NAME: instrumented debug builds
 _CSRC = os.path.join(_HERE, "csrc")
 
+ABI_VERSION = 2  # include/latentsync_b200.h LS_ABI_VERSION: bumped whenever an argument struct changes
 EPI_GEGLU = 1
 EPI_OUT_F32 = 2
 EPI_SILU = 4
@@ -173,11 +174,16 @@ def lib() -> C.CDLL:
                 f"latentsync_b200: CUDA extension {_SO} is missing - run `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (there is no CPU fallback)"
             )
-        _lib = C.CDLL(_SO)
+        loaded = C.CDLL(_SO)
         for name, (res, args) in SYMBOLS.items():
-            fn = getattr(_lib, name)
+            fn = getattr(loaded, name)
             fn.restype = res
             fn.argtypes = args
+        if loaded.ls_abi_version() != ABI_VERSION:
+            # a stale build would read the argument structs below with another layout: fail loudly instead
+            raise RuntimeError(f"latentsync_b200: {_SO} implements ABI v{loaded.ls_abi_version()}, this binding needs "
+                               f"v{ABI_VERSION} - rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
+        _lib = loaded
     return _lib
 
 

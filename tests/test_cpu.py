@@ -376,7 +376,7 @@ def test_cabi_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ls_abi_version() == 1
+    assert lib.ls_abi_version() == 2
     assert lib.ls_last_error() == b""
     # struct layouts agree with the header (sizes are part of the ABI)
     assert ctypes.sizeof(_lib.LsGemmArgs) % 8 == 0 and ctypes.sizeof(_lib.LsAttnArgs) % 8 == 0
